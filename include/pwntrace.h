@@ -1,0 +1,239 @@
+/*
+ * pwntrace.h -- C ABI of libpwntrace.so: the B200 (sm_100a) implementation of the
+ * pwnfps per-pixel portal ray cast.
+ *
+ * This is the drop-in boundary for ONE path of fanzyflani/pwnfps:
+ *
+ *     mainloop()                       main.c:93-109
+ *       level_prepare_render(lv)       main.c:95    level.h:64-81
+ *       trace_screen_centred(lv, 0, 0, rwidth, rheight, &cam)
+ *                                      main.c:107   screen.h:31-124
+ *         trace_ray_prelude(...)       screen.h:1-28      (per 32-row band)
+ *           trace_ray(...)             trace.h:186-679    (per pixel, +2 bounces)
+ *         POSTPROC_BLUR pass           screen.h:69-123
+ *
+ * The reference has no FFI/plugin layer: every function above is defined in a
+ * header #included into the single TU main.c (main.c:36-40).  The seam is
+ * therefore source level: the host includes pwnfps_b200/host/pwn_screen.h in
+ * place of trace.h + screen.h; that shim defines the same
+ * trace_screen_centred() and forwards to the entry points below
+ * (INTEGRATION.md shows the two-line change to main.c).
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no CUDA or torch types.
+ *   - every call returns 0 on success or a negative PWN_E_* code; the message
+ *     for the last failure on the calling thread is pwn_last_error().  The
+ *     reference trace has no error channel (void + assert, screen.h:35-36);
+ *     this library never calls exit()/abort().
+ *   - one pwn_ctx drives one GPU.  The caller is single threaded per context, as
+ *     the reference's main thread is (main.c:93-109); the library owns all
+ *     parallelism (streams, kernels).
+ *   - there is NO CPU fallback: without a usable sm_100 device pwn_create fails.
+ */
+#ifndef PWNTRACE_H
+#define PWNTRACE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PWN_ABI_VERSION 1
+
+enum
+{
+	PWN_OK = 0,
+	PWN_E_ARG = -1,        /* bad argument (null pointer, size, range)           */
+	PWN_E_CUDA = -2,       /* CUDA runtime failure; pwn_last_error has the text  */
+	PWN_E_NODEVICE = -3,   /* no sm_100 device / device index out of range       */
+	PWN_E_STATE = -4,      /* call order: level, tables or frame not set up yet  */
+	PWN_E_LIMIT = -5,      /* level exceeds a device-layout limit                */
+	PWN_E_HOSTMATH = -6,   /* host rcpps/rsqrtps is not a pure mantissa-bucket table */
+	PWN_E_UNSUPPORTED = -7 /* input outside what the reference host can produce  */
+};
+
+/* defs.h:25-33 */
+enum { PWN_FXP = 0, PWN_FZP, PWN_FXN, PWN_FZN, PWN_FYP, PWN_FYN };
+
+/*
+ * Cell codes.  The reference stores one char per cell (defs.h:105) and names
+ * portal pair p by the letter 'A'+p (defs.h:103).  Here a cell is an int32:
+ * values < 0x100 are the reference's chars unchanged; PWN_PORTAL_CODE(p)
+ * names portal pair p for p >= 26, which the reference cannot express.
+ */
+#define PWN_PORTAL_CODE(p) ((p) < 26 ? 'A' + (p) : 0x100 + (p))
+#define PWN_IS_PORTAL(c) (((c) >= 'A' && (c) <= 'Z') || (c) >= 0x100)
+#define PWN_PORTAL_INDEX(c) ((c) >= 0x100 ? (c) - 0x100 : (c) - 'A')
+
+/* defs.h:87-94 `portal` (double1/double2 are never read by the trace) */
+typedef struct pwn_portal
+{
+	int32_t x1, z1;
+	int32_t x2, z2;     /* x2 == -1: unpaired, renders as wall (trace.h:512-526) */
+	int32_t rot12;
+	int32_t c1, c2;     /* cell code in front of end 1 / end 2 (level.h:204-218) */
+} pwn_portal;
+
+/* defs.h:73-79 `part.sph` */
+typedef struct pwn_sphere
+{
+	float r, refl;
+	float pos[4];       /* x y z w; w must equal the camera's w (1.0f, script.h:28) */
+	float col[4];       /* b g r a (defs.h:40) */
+} pwn_sphere;
+
+/* per pixel, per segment (0 = primary, 1/2 = mirror bounces); test/diagnostic output */
+typedef struct pwn_ids
+{
+	int32_t cell;       /* cz*w + cx when the segment terminated; -1 = never ran    */
+	int16_t ldir;       /* PWN_FXP..PWN_FYN of the face hit; -1 = sphere            */
+	int16_t kind;       /* 0 wall/floor/ceiling, 1 sphere, 2 walk exhausted (trace.h:677) */
+	int32_t nstep;      /* walk-loop iterations entered (trace.h:250)               */
+	int32_t nportal;    /* portal crossings (trace.h:576)                           */
+} pwn_ids;
+
+/* one camera pose: mat4 cam rows x,y,z,w (defs.h:46-52) + the global sec_current (defs.h:23) */
+typedef struct pwn_pose
+{
+	float cam[16];
+	float sec_current;
+} pwn_pose;
+
+typedef struct pwn_ctx pwn_ctx;
+
+/* trace flags */
+#define PWN_F_BLUR 1u        /* run the POSTPROC_BLUR pass (screen.h:69-123)         */
+#define PWN_F_IDS 2u         /* also write pwn_ids (needs pwn_frame_config want_ids) */
+#define PWN_F_NO_REFLECT_BLUR 4u /* build without REFLECT_BLUR (defs.h:6); diagnostics */
+
+/* ---- lifetime ------------------------------------------------------------------ */
+int pwn_abi_version(void);
+const char *pwn_last_error(void);
+
+/* device: CUDA ordinal.  Fails with PWN_E_NODEVICE unless it is compute capability 10.x. */
+int pwn_create(pwn_ctx **out, int device);
+int pwn_destroy(pwn_ctx *ctx);
+
+/*
+ * rcpps / rsqrtps emulation tables (call sites trace.h:231, util.h:43).
+ * Both instructions are, on the CPUs probed, pure functions of (exponent parity,)
+ * the top `bits` mantissa bits; the device reproduces them from tables of the
+ * results for inputs in [1,2) (rcp) and [1,4) (rsqrt).
+ *   rcp_tab  : 1<<rcp_bits   entries, float bits of rcpps(1 + i*2^-rcp_bits)
+ *   rsqrt_tab: 2<<rsqrt_bits entries, float bits of rsqrtps over [1,2) then [2,4)
+ * pwn_math_tables_from_host() dumps them from the CPU it runs on and verifies the
+ * bucket property exhaustively (all 2^23 mantissas, every exponent the trace can
+ * produce); PWN_E_HOSTMATH if the property does not hold within 23 bits.
+ */
+int pwn_math_tables(pwn_ctx *ctx, const uint32_t *rcp_tab, int rcp_bits, const uint32_t *rsqrt_tab, int rsqrt_bits);
+int pwn_math_tables_from_host(pwn_ctx *ctx);
+/* same dump without a context (host-only, no GPU needed); tables may be NULL to query bits */
+int pwn_host_math_probe(int *rcp_bits, int *rsqrt_bits, uint32_t *rcp_tab, size_t rcp_cap, uint32_t *rsqrt_tab, size_t rsqrt_cap);
+
+/* ---- level: once per level (grid and portals are immutable after load, script.h:65-69) ---- */
+/*
+ * Flattens the reference's level (defs.h:96-111) into the device layout:
+ * a w*h plane of cell classes and one transform record per portal cell.
+ * cells: h rows of w int32 codes, row z then column x (lv->data[z][x]).
+ * portals: nportals entries indexed by PWN_PORTAL_INDEX (lv->pmap[]).
+ */
+int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells, int nportals, const pwn_portal *portals);
+
+/* per frame, after level_prepare_render (main.c:95): spheres in objs[] order; bins them per cell (level.h:1-39) */
+int pwn_parts_upload(pwn_ctx *ctx, int nsph, const pwn_sphere *sph);
+
+/* ---- frame buffers (the globals sbuf/tsbuf/zbuf, main.c:31-33,395-400) ------------ */
+int pwn_frame_config(pwn_ctx *ctx, int rwidth, int rheight, int want_ids);
+/* zero sbuf/zbuf (and ids) on the device: what a fresh malloc'd+memset frame is to the reference */
+int pwn_frame_clear(pwn_ctx *ctx);
+
+/*
+ * Row-band sharding for multi-GPU: this context traces only the
+ * 32-row bands b with b % nshards == shard (screen.h:63-64 bands).  Default 1/0.
+ */
+int pwn_shard_config(pwn_ctx *ctx, int nshards, int shard);
+
+/* ---- the hot path ------------------------------------------------------------------ */
+/*
+ * trace_ray_prelude for all bands of this shard (screen.h:1-28, 63-67) and, with
+ * PWN_F_BLUR, the blur pass.  from/rayb/rdx/rdy are the four vec4 that
+ * trace_screen_centred derives from cam (screen.h:43-57); their w lanes must be
+ * (1,0,0,0)-shaped as main.c:60-64 + mat4_roty produce (PWN_E_UNSUPPORTED
+ * otherwise).  Results stay on the device; asynchronous on the context's stream.
+ */
+int pwn_trace_frame(pwn_ctx *ctx, const float from[4], const float rayb[4], const float rdx[4], const float rdy[4],
+	int dimx, int dimy, float sec_current, unsigned flags);
+
+/*
+ * The blur pass alone (screen.h:69-123) over the frame currently in sbuf/zbuf: for
+ * harnesses that trace row bands on several GPUs and gather them first.
+ */
+int pwn_blur_frame(pwn_ctx *ctx, int dimx, int dimy);
+
+/* screen.h:31-57 on the host, bit-identical to the reference's arithmetic, then pwn_trace_frame */
+int pwn_trace_cam(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags);
+
+/* the ray basis alone (screen.h:43-57): exposed so a host can check it against its own build */
+void pwn_ray_setup(const float cam[16], int dimx, int dimy, float rayb[4], float rdx[4], float rdy[4]);
+
+/* wait for the context's stream */
+int pwn_sync(pwn_ctx *ctx);
+
+/* device -> host; any pointer may be NULL.  Full frames: rwidth*rheight elements (ids: x3). Synchronous. */
+int pwn_read_frame(pwn_ctx *ctx, uint32_t *sbuf, float *zbuf, pwn_ids *ids);
+
+/*
+ * The drop-in call: everything trace_screen_centred does for the host, with host
+ * buffers.  Uploads nothing but the pose, traces (and blurs with PWN_F_BLUR),
+ * copies sbuf (and zbuf if non-NULL) back, returns when they are complete -- the
+ * host reads sbuf immediately afterwards (screen_upscale, main.c:108).
+ */
+int pwn_trace_screen(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags,
+	uint32_t *sbuf_host, float *zbuf_host);
+
+/*
+ * A scripted fly-through: n poses, frame i written to sbuf_host + i*rwidth*rheight
+ * (pinned or pageable).  Trace of pose i+1 overlaps the device->host copy of
+ * pose i (two device frames, two streams).  sbuf_host may be NULL: frames then
+ * stay on the device.  sums, if non-NULL, receives one checksum per frame computed
+ * on the device: sum over pixels i = y*dimx+x of mix64(i<<32 | sbuf[y][x]) mod 2^64,
+ * mix64 = the splitmix64 finaliser (order independent, so it parallelises).
+ */
+int pwn_trace_poses(pwn_ctx *ctx, int n, const pwn_pose *poses, int dimx, int dimy, unsigned flags,
+	uint32_t *sbuf_host, uint64_t *sums);
+
+/* ---- device-resident access for harnesses that manage their own transfers ---------- */
+/* raw device pointers of the current frame (CUdeviceptr values); for peer mapping and zero-copy consumers */
+int pwn_frame_device_ptrs(pwn_ctx *ctx, uint64_t *sbuf_dev, uint64_t *zbuf_dev, uint64_t *tsbuf_dev);
+/*
+ * Redirect this context's K1/K2 output into another allocation (e.g. GPU 0's
+ * frame, peer-mapped or opened through CUDA IPC): the fused "trace + gather"
+ * path, bands land in the gathered frame as they are traced.  0 restores.
+ */
+int pwn_frame_redirect(pwn_ctx *ctx, uint64_t sbuf_dev, uint64_t zbuf_dev, uint64_t tsbuf_dev);
+/* CUDA IPC handle (64 bytes) of this context's frame allocation, and its inverse */
+int pwn_frame_ipc_export(pwn_ctx *ctx, void *handle64, uint64_t *sbuf_off, uint64_t *zbuf_off, uint64_t *tsbuf_off);
+int pwn_frame_ipc_import(pwn_ctx *ctx, const void *handle64, uint64_t *base_dev);
+int pwn_frame_ipc_close(pwn_ctx *ctx, uint64_t base_dev);
+
+/* pinned host memory for frames (cudaHostAlloc): what pwn_trace_poses copies into at full PCIe rate */
+int pwn_host_alloc(void **out, size_t bytes);
+int pwn_host_free(void *p);
+
+/* ---- measurement hooks (bench harness) ------------------------------------------------ */
+/* kernels launched by this context since creation (K1, K2, checksum, clear) */
+int pwn_launch_count(pwn_ctx *ctx, uint64_t *count);
+/* device time in ms of the last pwn_trace_frame's K1 and K2 launches (CUDA events on the context stream; syncs) */
+int pwn_last_kernel_ms(pwn_ctx *ctx, float *k1_ms, float *k2_ms);
+/* run n frames of the same pose back to back on the device, return total K1(+K2) event time in ms */
+int pwn_time_frames(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags, int n, float *total_ms);
+/* the CUDA stream the context launches on (cudaStream_t as an integer) */
+int pwn_stream(pwn_ctx *ctx, uint64_t *stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PWNTRACE_H */

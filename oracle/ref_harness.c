@@ -224,9 +224,9 @@ int ref_level_get(int32_t *cells, int32_t *pm)
 		cells[z*dim + x] = lvroot->data[z][x];
 	for(i = 0; i < ref_pm_max(); i++)
 	{
-		pm[i*7+0] = lvroot->pmap[i].x1; pm[i*7+1] = lvroot->pmap[i].z1;
-		pm[i*7+2] = lvroot->pmap[i].x2; pm[i*7+3] = lvroot->pmap[i].z2;
-		/* rot12 is uninitialised for unpaired slots (level.h:94-99) */
+		/* level_new resets only x1/x2 (level.h:94-99): z1/z2/rot12 of an unused end are stale */
+		pm[i*7+0] = lvroot->pmap[i].x1; pm[i*7+1] = lvroot->pmap[i].x1 == -1 ? 0 : lvroot->pmap[i].z1;
+		pm[i*7+2] = lvroot->pmap[i].x2; pm[i*7+3] = lvroot->pmap[i].x2 == -1 ? 0 : lvroot->pmap[i].z2;
 		pm[i*7+4] = lvroot->pmap[i].x2 == -1 ? 0 : lvroot->pmap[i].rot12;
 		pm[i*7+5] = lvroot->pmap[i].c1; pm[i*7+6] = lvroot->pmap[i].c2;
 	}

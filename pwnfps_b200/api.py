@@ -1,0 +1,454 @@
+"""pwnfps_b200.api -- ctypes binding of the C ABI (include/pwntrace.h) and of the C host
+library (pwnfps_b200/host), with the reference's own names for the path:
+
+    level_load(fname)                 level.h:107      -> Level
+    Tracer.level_prepare_render(lv)   level.h:64       (uploads the spheres)
+    Tracer.trace_screen_centred(lv, x1, y1, x2, y2, cam)   screen.h:31
+
+Everything here forwards to libpwntrace.so; there is no Python or CPU
+implementation of the trace.  Importing the module does not need a GPU; creating
+a Tracer does, and raises PwnError when no sm_100 device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+PWN_OK = 0
+PWN_F_BLUR = 1
+PWN_F_IDS = 2
+PWN_F_NO_REFLECT_BLUR = 4
+
+FXP, FZP, FXN, FZN, FYP, FYN = range(6)
+
+IDS_DTYPE = np.dtype([("cell", "<i4"), ("ldir", "<i2"), ("kind", "<i2"),
+                      ("nstep", "<i4"), ("nportal", "<i4")])
+PORTAL_DTYPE = np.dtype([("x1", "<i4"), ("z1", "<i4"), ("x2", "<i4"), ("z2", "<i4"),
+                         ("rot12", "<i4"), ("c1", "<i4"), ("c2", "<i4")])
+SPHERE_DTYPE = np.dtype([("r", "<f4"), ("refl", "<f4"), ("pos", "<f4", (4,)), ("col", "<f4", (4,))])
+POSE_DTYPE = np.dtype([("cam", "<f4", (16,)), ("sec_current", "<f4")])
+
+
+class PwnError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pwntrace error %d: %s" % (code, msg))
+        self.code = code
+
+
+def portal_code(p):
+    """PWN_PORTAL_CODE: cell code naming portal pair p."""
+    return ord("A") + p if p < 26 else 0x100 + p
+
+
+# ---------------------------------------------------------------------------------
+_lib = None
+_host = None
+
+# every symbol include/pwntrace.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "pwn_abi_version", "pwn_last_error", "pwn_create", "pwn_destroy",
+    "pwn_math_tables", "pwn_math_tables_from_host", "pwn_host_math_probe",
+    "pwn_level_upload", "pwn_parts_upload", "pwn_frame_config", "pwn_frame_clear",
+    "pwn_shard_config", "pwn_trace_frame", "pwn_blur_frame", "pwn_trace_cam", "pwn_ray_setup",
+    "pwn_sync", "pwn_read_frame", "pwn_trace_screen", "pwn_trace_poses",
+    "pwn_frame_device_ptrs", "pwn_frame_redirect", "pwn_frame_ipc_export",
+    "pwn_frame_ipc_import", "pwn_frame_ipc_close", "pwn_host_alloc", "pwn_host_free",
+    "pwn_launch_count", "pwn_last_kernel_ms", "pwn_time_frames", "pwn_stream",
+]
+
+
+def lib():
+    """libpwntrace.so (built in-tree on first use)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    L = C.CDLL(path)
+    vp, i, f, u = C.c_void_p, C.c_int, C.c_float, C.c_uint
+    u64p = C.POINTER(C.c_uint64)
+    L.pwn_last_error.restype = C.c_char_p
+    L.pwn_create.argtypes = [C.POINTER(vp), i]
+    L.pwn_destroy.argtypes = [vp]
+    L.pwn_math_tables.argtypes = [vp, vp, i, vp, i]
+    L.pwn_math_tables_from_host.argtypes = [vp]
+    L.pwn_host_math_probe.argtypes = [C.POINTER(i), C.POINTER(i), vp, C.c_size_t, vp, C.c_size_t]
+    L.pwn_level_upload.argtypes = [vp, i, i, vp, i, vp]
+    L.pwn_parts_upload.argtypes = [vp, i, vp]
+    L.pwn_frame_config.argtypes = [vp, i, i, i]
+    L.pwn_frame_clear.argtypes = [vp]
+    L.pwn_shard_config.argtypes = [vp, i, i]
+    L.pwn_trace_frame.argtypes = [vp, vp, vp, vp, vp, i, i, f, u]
+    L.pwn_blur_frame.argtypes = [vp, i, i]
+    L.pwn_trace_cam.argtypes = [vp, vp, i, i, f, u]
+    L.pwn_ray_setup.argtypes = [vp, i, i, vp, vp, vp]
+    L.pwn_ray_setup.restype = None
+    L.pwn_sync.argtypes = [vp]
+    L.pwn_read_frame.argtypes = [vp, vp, vp, vp]
+    L.pwn_trace_screen.argtypes = [vp, vp, i, i, f, u, vp, vp]
+    L.pwn_trace_poses.argtypes = [vp, i, vp, i, i, u, vp, vp]
+    L.pwn_frame_device_ptrs.argtypes = [vp, u64p, u64p, u64p]
+    L.pwn_frame_redirect.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64]
+    L.pwn_frame_ipc_export.argtypes = [vp, vp, u64p, u64p, u64p]
+    L.pwn_frame_ipc_import.argtypes = [vp, vp, u64p]
+    L.pwn_frame_ipc_close.argtypes = [vp, C.c_uint64]
+    L.pwn_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.pwn_host_free.argtypes = [vp]
+    L.pwn_launch_count.argtypes = [vp, u64p]
+    L.pwn_last_kernel_ms.argtypes = [vp, C.POINTER(f), C.POINTER(f)]
+    L.pwn_time_frames.argtypes = [vp, vp, i, i, f, u, i, C.POINTER(f)]
+    L.pwn_stream.argtypes = [vp, u64p]
+    _lib = L
+    return L
+
+
+class _CLevel(C.Structure):
+    _fields_ = [("w", C.c_int32), ("h", C.c_int32), ("cells", C.POINTER(C.c_int32)),
+                ("nportals", C.c_int32), ("portals", C.c_void_p), ("sx", C.c_int32), ("sz", C.c_int32)]
+
+
+def host():
+    """libpwnhost.so: the C host side (level loader, camera script)."""
+    global _host
+    if _host is not None:
+        return _host
+    H = C.CDLL(_build.build_host())
+    H.pwn_level_new.restype = C.POINTER(_CLevel)
+    H.pwn_level_new.argtypes = [C.c_int, C.c_int, C.c_int]
+    H.pwn_level_free.argtypes = [C.POINTER(_CLevel)]
+    H.pwn_level_load.restype = C.POINTER(_CLevel)
+    H.pwn_level_load.argtypes = [C.c_char_p]
+    H.pwn_level_parse.restype = C.POINTER(_CLevel)
+    H.pwn_level_parse.argtypes = [C.c_char_p, C.c_size_t]
+    H.pwn_level_link.argtypes = [C.POINTER(_CLevel)]
+    H.pwn_level_derive.argtypes = [C.POINTER(_CLevel)]
+    H.pwn_level_save_txt.argtypes = [C.POINTER(_CLevel), C.c_char_p]
+    H.pwn_cam_spawn.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    H.pwn_cam_spawn.restype = None
+    H.pwn_mat4_roty.argtypes = [C.c_void_p, C.c_float]
+    H.pwn_mat4_roty.restype = None
+    H.pwn_flythrough.argtypes = [C.POINTER(_CLevel), C.c_int, C.c_void_p]
+    H.pwn_flythrough.restype = C.c_int
+    _host = H
+    return H
+
+
+def _check(rc):
+    if rc != PWN_OK:
+        raise PwnError(rc, lib().pwn_last_error().decode("utf-8", "replace"))
+
+
+# ---------------------------------------------------------------------------------
+class Level:
+    """The reference's `level` as the trace reads it (defs.h:96-111): cells + portals + spawn."""
+
+    def __init__(self, cells, portals, sx=0, sz=0):
+        self.cells = np.ascontiguousarray(cells, dtype=np.int32)
+        assert self.cells.ndim == 2
+        self.portals = np.ascontiguousarray(portals, dtype=PORTAL_DTYPE).reshape(-1)
+        self.sx, self.sz = int(sx), int(sz)
+        self.spheres = np.zeros(0, SPHERE_DTYPE)   # lv->objs (defs.h:98)
+
+    @property
+    def h(self):
+        return self.cells.shape[0]
+
+    @property
+    def w(self):
+        return self.cells.shape[1]
+
+    def portals_i32(self):
+        """(n,7) int32 view: x1 z1 x2 z2 rot12 c1 c2."""
+        return self.portals.view(np.int32).reshape(-1, 7)
+
+    @classmethod
+    def _from_c(cls, p):
+        if not p:
+            raise PwnError(-1, "level load failed")
+        c = p.contents
+        cells = np.ctypeslib.as_array(c.cells, shape=(c.h, c.w)).copy()
+        n = c.nportals
+        pm = np.zeros(n, PORTAL_DTYPE)
+        if n:
+            C.memmove(pm.ctypes.data, c.portals, n * PORTAL_DTYPE.itemsize)
+        lv = cls(cells, pm, c.sx, c.sz)
+        host().pwn_level_free(p)
+        return lv
+
+    @classmethod
+    def from_grid(cls, cells, nportals, sx=0, sz=0):
+        """A level built in memory: portal pairing + rot12/c1/c2 derived as the loader does."""
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        h, w = cells.shape
+        H = host()
+        p = H.pwn_level_new(w, h, nportals)
+        C.memmove(p.contents.cells, cells.ctypes.data, cells.nbytes)
+        p.contents.sx, p.contents.sz = sx, sz
+        if H.pwn_level_link(p) != 0:
+            H.pwn_level_free(p)
+            raise PwnError(-1, "a portal cell names a pair outside the table")
+        return cls._from_c(p)
+
+    def sphere_add(self, r, refl, x, y, z, cb, cg, cr):
+        """obj_new + obj_set "sphere" (script.h:1-40)."""
+        s = np.zeros(1, SPHERE_DTYPE)
+        s["r"], s["refl"] = r, refl
+        s["pos"][0] = (x, y, z, 1.0)
+        s["col"][0] = (cb, cg, cr, 0.0)
+        self.spheres = np.concatenate([self.spheres, s])
+
+    def save_txt(self, path):
+        H = host()
+        p = H.pwn_level_new(self.w, self.h, len(self.portals))
+        C.memmove(p.contents.cells, self.cells.ctypes.data, self.cells.nbytes)
+        p.contents.sx, p.contents.sz = self.sx, self.sz
+        rc = H.pwn_level_save_txt(p, os.fsencode(path))
+        H.pwn_level_free(p)
+        if rc != 0:
+            raise PwnError(-1, "level does not fit the level.txt format")
+
+
+def level_load(fname):
+    """level_load (level.h:107-228) through the C host loader."""
+    p = host().pwn_level_load(os.fsencode(fname))
+    if not p:
+        raise PwnError(-1, "err loading level: %s" % fname)
+    return Level._from_c(p)
+
+
+def level_parse(text):
+    if isinstance(text, str):
+        text = text.encode("latin-1")
+    return Level._from_c(host().pwn_level_parse(text, len(text)))
+
+
+def cam_spawn(lv):
+    """cam as main.c:60-64."""
+    cam = np.zeros(16, np.float32)
+    host().pwn_cam_spawn(lv.sx, lv.sz, cam.ctypes.data)
+    return cam
+
+
+def mat4_roty(cam, ang):
+    """mat4_roty (util.h:96-110) on a copy."""
+    m = np.ascontiguousarray(cam, dtype=np.float32).reshape(16).copy()
+    host().pwn_mat4_roty(m.ctypes.data, float(ang))
+    return m
+
+
+def flythrough(lv, nframes):
+    """The fixed camera-path script of the headless harness: POSE_DTYPE[nframes]."""
+    H = host()
+    p = H.pwn_level_new(lv.w, lv.h, len(lv.portals))
+    C.memmove(p.contents.cells, lv.cells.ctypes.data, lv.cells.nbytes)
+    if len(lv.portals):
+        C.memmove(p.contents.portals, lv.portals.ctypes.data, lv.portals.nbytes)
+    p.contents.sx, p.contents.sz = lv.sx, lv.sz
+    poses = np.zeros(nframes, POSE_DTYPE)
+    rc = H.pwn_flythrough(p, nframes, poses.ctypes.data)
+    H.pwn_level_free(p)
+    if rc != 0:
+        raise PwnError(rc, "flythrough failed")
+    return poses
+
+
+def ray_setup(cam, dimx, dimy):
+    """screen.h:43-57 as the library computes it on the host."""
+    cam = np.ascontiguousarray(cam, dtype=np.float32).reshape(16)
+    rb, rx, ry = (np.zeros(4, np.float32) for _ in range(3))
+    lib().pwn_ray_setup(cam.ctypes.data, dimx, dimy, rb.ctypes.data, rx.ctypes.data, ry.ctypes.data)
+    return rb, rx, ry
+
+
+def host_math_probe():
+    """(rcp_bits, rsqrt_bits, rcp_tab, rsqrt_tab) of the CPU this runs on. No GPU needed."""
+    L = lib()
+    rb, sb = C.c_int(), C.c_int()
+    rc = L.pwn_host_math_probe(C.byref(rb), C.byref(sb), None, 0, None, 0)
+    if rc != 0:
+        raise PwnError(rc, "host rcpps/rsqrtps is not a mantissa-bucket table")
+    rt = np.zeros(1 << rb.value, np.uint32)
+    st = np.zeros(2 << sb.value, np.uint32)
+    rc = L.pwn_host_math_probe(C.byref(rb), C.byref(sb), rt.ctypes.data, rt.size, st.ctypes.data, st.size)
+    if rc != 0:
+        raise PwnError(rc, "host math probe failed")
+    return rb.value, sb.value, rt, st
+
+
+class PinnedBuffer:
+    """cudaHostAlloc'd memory viewed as a numpy array."""
+
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _check(lib().pwn_host_alloc(C.byref(p), self.nbytes))
+        self.ptr = p.value
+        buf = (C.c_char * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().pwn_host_free(self.ptr)
+            self.ptr = None
+
+
+class Tracer:
+    """One GPU: the device side of trace_screen_centred."""
+
+    def __init__(self, device=0, math_tables="host"):
+        self.L = lib()
+        h = C.c_void_p()
+        _check(self.L.pwn_create(C.byref(h), device))
+        self.h = h
+        self.device = device
+        self.rwidth = self.rheight = 0
+        self.want_ids = False
+        self.level = None
+        if math_tables == "host":
+            _check(self.L.pwn_math_tables_from_host(self.h))
+        elif math_tables is not None:
+            rb, sb, rt, st = math_tables
+            _check(self.L.pwn_math_tables(self.h, rt.ctypes.data, rb, st.ctypes.data, sb))
+
+    def close(self):
+        if self.h:
+            self.L.pwn_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- setup -----------------------------------------------------------------
+    def level_upload(self, lv):
+        pm = lv.portals
+        _check(self.L.pwn_level_upload(self.h, lv.w, lv.h, lv.cells.ctypes.data, len(pm),
+                                       pm.ctypes.data if len(pm) else None))
+        self.level = lv
+
+    def level_prepare_render(self, lv=None):
+        """level_prepare_render (level.h:64-81): re-bin the spheres for this frame."""
+        lv = lv or self.level
+        sp = np.ascontiguousarray(lv.spheres, dtype=SPHERE_DTYPE)
+        _check(self.L.pwn_parts_upload(self.h, len(sp), sp.ctypes.data if len(sp) else None))
+
+    def frame_config(self, rwidth, rheight, want_ids=False):
+        _check(self.L.pwn_frame_config(self.h, rwidth, rheight, 1 if want_ids else 0))
+        self.rwidth, self.rheight = rwidth, rheight
+        self.want_ids = self.want_ids or want_ids
+
+    def frame_clear(self):
+        _check(self.L.pwn_frame_clear(self.h))
+
+    def shard_config(self, nshards, shard):
+        _check(self.L.pwn_shard_config(self.h, nshards, shard))
+
+    # -- hot path ----------------------------------------------------------------
+    def trace_cam(self, cam, dimx, dimy, sec_current=0.0, flags=0):
+        cam = np.ascontiguousarray(cam, dtype=np.float32).reshape(16)
+        _check(self.L.pwn_trace_cam(self.h, cam.ctypes.data, dimx, dimy, float(sec_current), flags))
+
+    def trace_frame(self, frm, rayb, rdx, rdy, dimx, dimy, sec_current=0.0, flags=0):
+        v = [np.ascontiguousarray(a, dtype=np.float32).reshape(4) for a in (frm, rayb, rdx, rdy)]
+        _check(self.L.pwn_trace_frame(self.h, v[0].ctypes.data, v[1].ctypes.data, v[2].ctypes.data,
+                                      v[3].ctypes.data, dimx, dimy, float(sec_current), flags))
+
+    def blur_frame(self, dimx, dimy):
+        _check(self.L.pwn_blur_frame(self.h, dimx, dimy))
+
+    def sync(self):
+        _check(self.L.pwn_sync(self.h))
+
+    def read_frame(self, want_z=True, want_ids=False):
+        sbuf = np.zeros((self.rheight, self.rwidth), np.uint32)
+        zbuf = np.zeros((self.rheight, self.rwidth), np.float32) if want_z else None
+        ids = np.zeros((self.rheight, self.rwidth, 3), IDS_DTYPE) if want_ids else None
+        _check(self.L.pwn_read_frame(self.h, sbuf.ctypes.data,
+                                     zbuf.ctypes.data if want_z else None,
+                                     ids.ctypes.data if want_ids else None))
+        return sbuf, zbuf, ids
+
+    def trace_screen_centred(self, lv, x1, y1, x2, y2, cam, sec_current=0.0, blur=True, sbuf=None, zbuf=None):
+        """trace_screen_centred (screen.h:31): [p1,p2) window, frame returned in host memory.
+
+        As in the reference, x1/y1 only enter through dimx = x2-x1, dimy = y2-y1
+        (screen.h:39-40); buffers are indexed from (0,0) with stride rwidth."""
+        assert x1 < x2 and y1 < y2   # screen.h:35-36
+        if lv is not self.level:
+            self.level_upload(lv)
+        cam = np.ascontiguousarray(cam, dtype=np.float32).reshape(16)
+        if sbuf is None:
+            sbuf = np.zeros((self.rheight, self.rwidth), np.uint32)
+        _check(self.L.pwn_trace_screen(self.h, cam.ctypes.data, x2 - x1, y2 - y1, float(sec_current),
+                                       PWN_F_BLUR if blur else 0, sbuf.ctypes.data,
+                                       zbuf.ctypes.data if zbuf is not None else None))
+        return sbuf
+
+    def trace_poses(self, poses, dimx, dimy, flags=0, out=None, want_sums=False):
+        poses = np.ascontiguousarray(poses, dtype=POSE_DTYPE)
+        n = len(poses)
+        sums = np.zeros(n, np.uint64) if want_sums else None
+        optr = None
+        if out is not None:
+            optr = out.ctypes.data if isinstance(out, np.ndarray) else out
+        _check(self.L.pwn_trace_poses(self.h, n, poses.ctypes.data, dimx, dimy, flags, optr,
+                                      sums.ctypes.data if want_sums else None))
+        return sums
+
+    # -- measurement ---------------------------------------------------------------
+    def launch_count(self):
+        c = C.c_uint64()
+        _check(self.L.pwn_launch_count(self.h, C.byref(c)))
+        return c.value
+
+    def last_kernel_ms(self):
+        a, b = C.c_float(), C.c_float()
+        _check(self.L.pwn_last_kernel_ms(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def time_frames(self, cam, dimx, dimy, sec_current, flags, n):
+        cam = np.ascontiguousarray(cam, dtype=np.float32).reshape(16)
+        t = C.c_float()
+        _check(self.L.pwn_time_frames(self.h, cam.ctypes.data, dimx, dimy, float(sec_current), flags, n, C.byref(t)))
+        return t.value
+
+    def device_ptrs(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(self.L.pwn_frame_device_ptrs(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def frame_redirect(self, sbuf_dev, zbuf_dev, tsbuf_dev):
+        _check(self.L.pwn_frame_redirect(self.h, sbuf_dev, zbuf_dev, tsbuf_dev))
+
+    def ipc_export(self):
+        hnd = (C.c_char * 64)()
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(self.L.pwn_frame_ipc_export(self.h, hnd, C.byref(a), C.byref(b), C.byref(c)))
+        return bytes(hnd), a.value, b.value, c.value
+
+    def ipc_import(self, handle):
+        base = C.c_uint64()
+        buf = C.create_string_buffer(handle, 64)
+        _check(self.L.pwn_frame_ipc_import(self.h, buf, C.byref(base)))
+        return base.value
+
+    def ipc_close(self, base):
+        _check(self.L.pwn_frame_ipc_close(self.h, base))
+
+
+def checksum_ref(sbuf, dimx, dimy):
+    """Host restatement of the device frame checksum (pwntrace.h, pwn_trace_poses)."""
+    w = np.ascontiguousarray(sbuf[:dimy, :dimx]).astype(np.uint64).reshape(-1)
+    i = np.arange(w.size, dtype=np.uint64)
+    z = (i << np.uint64(32)) | w
+    with np.errstate(over="ignore"):
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        return np.uint64(z.sum(dtype=np.uint64))

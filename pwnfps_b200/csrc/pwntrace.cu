@@ -1,0 +1,717 @@
+// pwntrace.cu -- libpwntrace.so: the C ABI of include/pwntrace.h over the sm_100a kernels.
+//
+// Host side of the boundary described in pwntrace.h: level flattening (the
+// reference walks its AoS `level` in place, defs.h:96-111; the device gets a
+// class plane + per-portal-cell transform records), per-frame sphere binning
+// (level.h:1-39,64-81), frame buffers (main.c:31-33,395-400), launches, copies.
+// No CPU implementation of the trace exists in this library.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "pwntrace.h"
+#include "trace_kernel.cuh"
+#include "blur_kernel.cuh"
+
+using namespace pwn;
+
+// ---- errors ----------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) \
+	return fail(PWN_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while(0)
+
+extern "C" const char *pwn_last_error(void) { return g_err; }
+extern "C" int pwn_abi_version(void) { return PWN_ABI_VERSION; }
+
+// ---- context -----------------------------------------------------------------------------
+struct FrameSet
+{
+	void *base = nullptr;      // one allocation: sbuf | tsbuf | zbuf  (so one IPC handle covers the frame)
+	uint32_t *sbuf = nullptr, *tsbuf = nullptr;
+	float *zbuf = nullptr;
+	size_t off_sbuf = 0, off_tsbuf = 0, off_zbuf = 0, bytes = 0;
+};
+
+struct pwn_ctx
+{
+	int device = -1;
+	cudaStream_t stream = nullptr, copy_stream = nullptr;
+	cudaEvent_t ev_k1a = nullptr, ev_k1b = nullptr, ev_k2b = nullptr;
+	cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+
+	// level
+	uint16_t *d_cellmap = nullptr;
+	PortalRec *d_portals = nullptr;
+	int w = 0, h = 0;
+	bool have_level = false;
+
+	// math tables
+	uint32_t *d_rcp = nullptr, *d_rsqrt = nullptr;
+	int rcp_bits = 0, rsqrt_bits = 0;
+	bool have_tables = false;
+
+	// spheres
+	float4 *d_sph_pos = nullptr, *d_sph_col = nullptr;
+	float2 *d_sph_rr = nullptr;
+	uint32_t *d_parts_off = nullptr, *d_parts_idx = nullptr;
+	size_t sph_cap = 0, idx_cap = 0;
+	int nsph = 0;
+	float sph_w = 1.0f;
+
+	// frame
+	int rwidth = 0, rheight = 0;
+	FrameSet fs[2];
+	pwn_ids *d_ids = nullptr;
+	uint32_t *r_sbuf = nullptr, *r_tsbuf = nullptr;   // redirect targets (peer frame) or null
+	float *r_zbuf = nullptr;
+	unsigned long long *d_sums = nullptr;
+	size_t sums_cap = 0;
+
+	int nshards = 1, shard = 0;
+	unsigned long long launches = 0;
+	bool timed = false;        // events of the last trace are valid
+	bool timed_blur = false;
+};
+
+static int set_device(pwn_ctx *ctx)
+{
+	CU(cudaSetDevice(ctx->device));
+	return PWN_OK;
+}
+
+#define CTX_ENTER(ctx) do { if((ctx) == nullptr) return fail(PWN_E_ARG, "null context"); \
+	int rc_ = set_device(ctx); if(rc_ != PWN_OK) return rc_; } while(0)
+
+extern "C" int pwn_create(pwn_ctx **out, int device)
+{
+	if(out == nullptr) return fail(PWN_E_ARG, "pwn_create: null out");
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if(e != cudaSuccess || n <= 0)
+		return fail(PWN_E_NODEVICE, "no CUDA device (%s); this library has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "count 0");
+	if(device < 0 || device >= n) return fail(PWN_E_NODEVICE, "device %d out of range (%d devices)", device, n);
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, device));
+	if(prop.major != 10)
+		return fail(PWN_E_NODEVICE, "device %d is sm_%d%d; libpwntrace is built for sm_100a only", device, prop.major, prop.minor);
+
+	pwn_ctx *ctx = new pwn_ctx();
+	ctx->device = device;
+	CU(cudaSetDevice(device));
+	CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+	CU(cudaEventCreate(&ctx->ev_k1a));
+	CU(cudaEventCreate(&ctx->ev_k1b));
+	CU(cudaEventCreate(&ctx->ev_k2b));
+	for(int i = 0; i < 2; i++)
+	{
+		CU(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+	}
+
+	// LCG jump table for K2: s -> A s + C composed 2^k times (util.h:1-6)
+	uint32_t ja[32], jc[32];
+	ja[0] = 25739u; jc[0] = 4u;
+	for(int k = 1; k < 32; k++) { ja[k] = ja[k-1]*ja[k-1]; jc[k] = ja[k-1]*jc[k-1] + jc[k-1]; }
+	CU(cudaMemcpyToSymbol(c_jumpA, ja, sizeof(ja)));
+	CU(cudaMemcpyToSymbol(c_jumpC, jc, sizeof(jc)));
+
+	*out = ctx;
+	return PWN_OK;
+}
+
+static void free_frames(pwn_ctx *ctx)
+{
+	for(int i = 0; i < 2; i++) { cudaFree(ctx->fs[i].base); ctx->fs[i] = FrameSet(); }
+	cudaFree(ctx->d_ids); ctx->d_ids = nullptr;
+	ctx->rwidth = ctx->rheight = 0;
+}
+
+extern "C" int pwn_destroy(pwn_ctx *ctx)
+{
+	if(ctx == nullptr) return PWN_OK;
+	cudaSetDevice(ctx->device);
+	cudaDeviceSynchronize();
+	free_frames(ctx);
+	cudaFree(ctx->d_cellmap); cudaFree(ctx->d_portals);
+	cudaFree(ctx->d_rcp); cudaFree(ctx->d_rsqrt);
+	cudaFree(ctx->d_sph_pos); cudaFree(ctx->d_sph_col); cudaFree(ctx->d_sph_rr);
+	cudaFree(ctx->d_parts_off); cudaFree(ctx->d_parts_idx);
+	cudaFree(ctx->d_sums);
+	cudaEventDestroy(ctx->ev_k1a); cudaEventDestroy(ctx->ev_k1b); cudaEventDestroy(ctx->ev_k2b);
+	for(int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_done[i]); cudaEventDestroy(ctx->ev_copied[i]); }
+	cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->copy_stream);
+	delete ctx;
+	return PWN_OK;
+}
+
+// ---- math tables ---------------------------------------------------------------------------
+extern "C" int pwn_math_tables(pwn_ctx *ctx, const uint32_t *rcp_tab, int rcp_bits, const uint32_t *rsqrt_tab, int rsqrt_bits)
+{
+	CTX_ENTER(ctx);
+	if(rcp_tab == nullptr || rsqrt_tab == nullptr || rcp_bits < 1 || rcp_bits > 23 || rsqrt_bits < 1 || rsqrt_bits > 23)
+		return fail(PWN_E_ARG, "pwn_math_tables: bad tables (bits %d, %d)", rcp_bits, rsqrt_bits);
+	CU(cudaStreamSynchronize(ctx->stream));
+	cudaFree(ctx->d_rcp); cudaFree(ctx->d_rsqrt);
+	ctx->d_rcp = ctx->d_rsqrt = nullptr;
+	ctx->have_tables = false;
+	size_t nr = (size_t)1 << rcp_bits, ns = (size_t)2 << rsqrt_bits;
+	CU(cudaMalloc(&ctx->d_rcp, nr*sizeof(uint32_t)));
+	CU(cudaMalloc(&ctx->d_rsqrt, ns*sizeof(uint32_t)));
+	CU(cudaMemcpy(ctx->d_rcp, rcp_tab, nr*sizeof(uint32_t), cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(ctx->d_rsqrt, rsqrt_tab, ns*sizeof(uint32_t), cudaMemcpyHostToDevice));
+	ctx->rcp_bits = rcp_bits; ctx->rsqrt_bits = rsqrt_bits;
+	ctx->have_tables = true;
+	return PWN_OK;
+}
+
+extern "C" int pwn_math_tables_from_host(pwn_ctx *ctx)
+{
+	CTX_ENTER(ctx);
+	int rb = 0, sb = 0;
+	int rc = pwn_host_math_probe(&rb, &sb, nullptr, 0, nullptr, 0);
+	if(rc != PWN_OK) return fail(rc, "host rcpps/rsqrtps is not a mantissa-bucket table on this CPU");
+	std::vector<uint32_t> rt((size_t)1 << rb), st((size_t)2 << sb);
+	rc = pwn_host_math_probe(&rb, &sb, rt.data(), rt.size(), st.data(), st.size());
+	if(rc != PWN_OK) return fail(rc, "host math probe failed");
+	return pwn_math_tables(ctx, rt.data(), rb, st.data(), sb);
+}
+
+// ---- level ---------------------------------------------------------------------------------
+static uint32_t class_of(int32_t c)
+{
+	switch(c)
+	{
+		case ';': return CL_ONE;
+		case '$': return CL_ONE_FOG;
+		case '"': return CL_RAISED;
+		case '#': return CL_TWO;
+		case '&': return CL_TWO_FOG;
+		case '>': return CL_RAMP_GT;
+		case '<': return CL_RAMP_LT;
+		case ',': return CL_RAMP_COMMA;
+		case '^': return CL_RAMP_CARET;
+		default: return PWN_IS_PORTAL(c) ? CL_PORTAL : CL_SOLID;
+	}
+}
+
+// what `switch(xcell)` at trace.h:416-440 does with a cell code
+static uint8_t peek_of(int32_t xcell)
+{
+	if(xcell == '#' || xcell == '&') return PK_PASS;
+	if(xcell == '"') return PK_RAISED;
+	return PK_WALL;
+}
+
+extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells, int nportals, const pwn_portal *portals)
+{
+	CTX_ENTER(ctx);
+	if(cells == nullptr || w <= 0 || h <= 0 || nportals < 0 || (nportals > 0 && portals == nullptr))
+		return fail(PWN_E_ARG, "pwn_level_upload: bad arguments");
+	if(w > 16384 || h > 16384) return fail(PWN_E_LIMIT, "level %dx%d exceeds 16384 cells per axis", w, h);
+
+	std::vector<uint16_t> map((size_t)w*h);
+	std::vector<PortalRec> recs;
+	for(int z = 0; z < h; z++)
+	for(int x = 0; x < w; x++)
+	{
+		const int32_t c = cells[(size_t)z*w + x];
+		uint32_t cls = class_of(c);
+		uint32_t entry = cls;
+		if(cls == CL_PORTAL)
+		{
+			const int pi = PWN_PORTAL_INDEX(c);
+			if(pi < 0 || pi >= nportals)
+				return fail(PWN_E_ARG, "cell (%d,%d) names portal %d but the table has %d entries", x, z, pi, nportals);
+			const pwn_portal &pm = portals[pi];
+			PortalRec r;
+			memset(&r, 0, sizeof(r));
+			// peek through the portal from a 2-high room (trace.h:404-413)
+			int32_t xcell = c;
+			if(pm.x1 == x && pm.z1 == z) xcell = pm.c2;
+			else if(pm.x2 == x && pm.z2 == z) xcell = pm.c1;
+			r.peek = peek_of(xcell);
+			if(pm.x2 == -1) r.kind = PR_UNPAIRED;                    // trace.h:512-526
+			else if(pm.x1 == x && pm.z1 == z)                        // 1 -> 2, trace.h:530-537
+			{
+				r.kind = PR_OK;
+				r.dcx = (int16_t)pm.x2; r.dcz = (int16_t)pm.z2;
+				r.dx = (int16_t)(pm.x2 - pm.x1); r.dz = (int16_t)(pm.z2 - pm.z1);
+				r.rot = (uint8_t)((-pm.rot12) & 3);
+			}
+			else if(pm.x2 == x && pm.z2 == z)                        // 2 -> 1, trace.h:539-545
+			{
+				r.kind = PR_OK;
+				r.dcx = (int16_t)pm.x1; r.dcz = (int16_t)pm.z1;
+				r.dx = (int16_t)(-(pm.x2 - pm.x1)); r.dz = (int16_t)(-(pm.z2 - pm.z1));
+				r.rot = (uint8_t)(pm.rot12 & 3);
+			}
+			else r.kind = PR_STRAY;                                  // trace.h:547-559
+			if(recs.size() >= 4096) return fail(PWN_E_LIMIT, "more than 4096 portal cells");
+			entry |= (uint32_t)recs.size() << 4;
+			recs.push_back(r);
+		}
+		map[(size_t)z*w + x] = (uint16_t)entry;
+	}
+	if(recs.empty()) { PortalRec r; memset(&r, 0, sizeof(r)); recs.push_back(r); }
+
+	CU(cudaStreamSynchronize(ctx->stream));
+	cudaFree(ctx->d_cellmap); cudaFree(ctx->d_portals);
+	ctx->d_cellmap = nullptr; ctx->d_portals = nullptr;
+	ctx->have_level = false;
+	CU(cudaMalloc(&ctx->d_cellmap, map.size()*sizeof(uint16_t)));
+	CU(cudaMalloc(&ctx->d_portals, recs.size()*sizeof(PortalRec)));
+	CU(cudaMemcpy(ctx->d_cellmap, map.data(), map.size()*sizeof(uint16_t), cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(ctx->d_portals, recs.data(), recs.size()*sizeof(PortalRec), cudaMemcpyHostToDevice));
+	ctx->w = w; ctx->h = h;
+	ctx->have_level = true;
+	ctx->nsph = 0;
+	return PWN_OK;
+}
+
+// (int)float the way the reference's x86 build converts (cvttss2si)
+static int cvtt_host(float v)
+{
+	if(!(v < 2147483648.0f && v >= -2147483648.0f)) return (int)0x80000000;
+	return (int)v;
+}
+
+extern "C" int pwn_parts_upload(pwn_ctx *ctx, int nsph, const pwn_sphere *sph)
+{
+	CTX_ENTER(ctx);
+	if(!ctx->have_level) return fail(PWN_E_STATE, "pwn_parts_upload before pwn_level_upload");
+	if(nsph < 0 || (nsph > 0 && sph == nullptr)) return fail(PWN_E_ARG, "pwn_parts_upload: bad arguments");
+	if(nsph == 0) { ctx->nsph = 0; return PWN_OK; }
+	for(int i = 1; i < nsph; i++)
+		if(sph[i].pos[3] != sph[0].pos[3]) return fail(PWN_E_UNSUPPORTED, "sphere %d: pos.w differs (script.h:28 sets 1.0f)", i);
+	ctx->sph_w = sph[0].pos[3];
+
+	// level_prepare_render + level_part_add_bbox (level.h:1-39,64-81): objs[] order per cell
+	const int w = ctx->w, h = ctx->h;
+	const size_t ncell = (size_t)w*h;
+	std::vector<uint32_t> off(ncell + 1, 0), idx, cur;
+	for(int pass = 0; pass < 2; pass++)
+	{
+		if(pass == 1) { idx.assign(off[ncell] ? off[ncell] : 1, 0); cur.assign(off.begin(), off.end() - 1); }
+		for(int i = 0; i < nsph; i++)
+		{
+			const int cx1 = cvtt_host(sph[i].pos[0] - sph[i].r), cz1 = cvtt_host(sph[i].pos[2] - sph[i].r);
+			const int cx2 = cvtt_host(sph[i].pos[0] + sph[i].r), cz2 = cvtt_host(sph[i].pos[2] + sph[i].r);
+			for(int z = cz1; z <= cz2; z++)
+			for(int x = cx1; x <= cx2; x++)
+			{
+				if(x < 0 || x >= w || z < 0 || z >= h) continue;   // the reference writes out of bounds here
+				if(pass == 0) off[(size_t)z*w + x + 1]++;
+				else idx[cur[(size_t)z*w + x]++] = (uint32_t)i;
+			}
+		}
+		if(pass == 0) for(size_t c = 0; c < ncell; c++) off[c+1] += off[c];
+		else
+		{
+			CU(cudaStreamSynchronize(ctx->stream));
+			if((size_t)nsph > ctx->sph_cap)
+			{
+				cudaFree(ctx->d_sph_pos); cudaFree(ctx->d_sph_col); cudaFree(ctx->d_sph_rr);
+				ctx->sph_cap = (size_t)nsph*2;
+				CU(cudaMalloc(&ctx->d_sph_pos, ctx->sph_cap*sizeof(float4)));
+				CU(cudaMalloc(&ctx->d_sph_col, ctx->sph_cap*sizeof(float4)));
+				CU(cudaMalloc(&ctx->d_sph_rr, ctx->sph_cap*sizeof(float2)));
+			}
+			if(ctx->d_parts_off == nullptr) CU(cudaMalloc(&ctx->d_parts_off, (ncell + 1)*sizeof(uint32_t)));
+			if(idx.size() > ctx->idx_cap)
+			{
+				cudaFree(ctx->d_parts_idx);
+				ctx->idx_cap = idx.size()*2;
+				CU(cudaMalloc(&ctx->d_parts_idx, ctx->idx_cap*sizeof(uint32_t)));
+			}
+			std::vector<float4> pos(nsph), col(nsph);
+			std::vector<float2> rr(nsph);
+			for(int i = 0; i < nsph; i++)
+			{
+				pos[i] = make_float4(sph[i].pos[0], sph[i].pos[1], sph[i].pos[2], sph[i].pos[3]);
+				col[i] = make_float4(sph[i].col[0], sph[i].col[1], sph[i].col[2], sph[i].col[3]);
+				rr[i] = make_float2(sph[i].r, sph[i].refl);
+			}
+			CU(cudaMemcpy(ctx->d_sph_pos, pos.data(), nsph*sizeof(float4), cudaMemcpyHostToDevice));
+			CU(cudaMemcpy(ctx->d_sph_col, col.data(), nsph*sizeof(float4), cudaMemcpyHostToDevice));
+			CU(cudaMemcpy(ctx->d_sph_rr, rr.data(), nsph*sizeof(float2), cudaMemcpyHostToDevice));
+			CU(cudaMemcpy(ctx->d_parts_off, off.data(), (ncell + 1)*sizeof(uint32_t), cudaMemcpyHostToDevice));
+			CU(cudaMemcpy(ctx->d_parts_idx, idx.data(), idx.size()*sizeof(uint32_t), cudaMemcpyHostToDevice));
+		}
+	}
+	ctx->nsph = nsph;
+	return PWN_OK;
+}
+
+// ---- frame buffers ----------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int pwn_frame_config(pwn_ctx *ctx, int rwidth, int rheight, int want_ids)
+{
+	CTX_ENTER(ctx);
+	if(rwidth <= 0 || rheight <= 0) return fail(PWN_E_ARG, "pwn_frame_config: %dx%d", rwidth, rheight);
+	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaStreamSynchronize(ctx->copy_stream));
+	if(rwidth != ctx->rwidth || rheight != ctx->rheight)
+	{
+		free_frames(ctx);
+		const size_t plane = align_up((size_t)rwidth*rheight*4, 512);
+		for(int i = 0; i < 2; i++)
+		{
+			FrameSet &f = ctx->fs[i];
+			f.bytes = 3*plane;
+			CU(cudaMalloc(&f.base, f.bytes));
+			f.off_sbuf = 0; f.off_tsbuf = plane; f.off_zbuf = 2*plane;
+			f.sbuf = (uint32_t *)((char *)f.base + f.off_sbuf);
+			f.tsbuf = (uint32_t *)((char *)f.base + f.off_tsbuf);
+			f.zbuf = (float *)((char *)f.base + f.off_zbuf);
+			CU(cudaMemset(f.base, 0, f.bytes));
+		}
+		ctx->rwidth = rwidth; ctx->rheight = rheight;
+	}
+	if(want_ids && ctx->d_ids == nullptr)
+	{
+		CU(cudaMalloc(&ctx->d_ids, (size_t)rwidth*rheight*3*sizeof(pwn_ids)));
+		CU(cudaMemset(ctx->d_ids, 0xFF, (size_t)rwidth*rheight*3*sizeof(pwn_ids)));
+	}
+	ctx->r_sbuf = ctx->r_tsbuf = nullptr; ctx->r_zbuf = nullptr;
+	return PWN_OK;
+}
+
+extern "C" int pwn_frame_clear(pwn_ctx *ctx)
+{
+	CTX_ENTER(ctx);
+	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "pwn_frame_clear before pwn_frame_config");
+	for(int i = 0; i < 2; i++) CU(cudaMemsetAsync(ctx->fs[i].base, 0, ctx->fs[i].bytes, ctx->stream));
+	if(ctx->d_ids) CU(cudaMemsetAsync(ctx->d_ids, 0xFF, (size_t)ctx->rwidth*ctx->rheight*3*sizeof(pwn_ids), ctx->stream));
+	return PWN_OK;
+}
+
+extern "C" int pwn_shard_config(pwn_ctx *ctx, int nshards, int shard)
+{
+	if(ctx == nullptr) return fail(PWN_E_ARG, "null context");
+	if(nshards < 1 || shard < 0 || shard >= nshards) return fail(PWN_E_ARG, "pwn_shard_config: shard %d of %d", shard, nshards);
+	ctx->nshards = nshards; ctx->shard = shard;
+	return PWN_OK;
+}
+
+// ---- the hot path ----------------------------------------------------------------------------------
+static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], const float rayb[4], const float rdx[4], const float rdy[4],
+	int dimx, int dimy, float sec, unsigned flags, bool timing)
+{
+	if(!ctx->have_level) return fail(PWN_E_STATE, "trace before pwn_level_upload");
+	if(!ctx->have_tables) return fail(PWN_E_STATE, "trace before pwn_math_tables");
+	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "trace before pwn_frame_config");
+	if(dimx <= 0 || dimy <= 0 || dimx > ctx->rwidth || dimy > ctx->rheight)
+		return fail(PWN_E_ARG, "trace %dx%d does not fit the %dx%d frame", dimx, dimy, ctx->rwidth, ctx->rheight);
+	// w lanes: cam rows x,y,z carry w == 0 and the position w == 1 through everything the
+	// reference host does to cam (main.c:60-64,188,201-208,267,372-377)
+	if(rayb[3] != 0.0f || rdx[3] != 0.0f || rdy[3] != 0.0f)
+		return fail(PWN_E_UNSUPPORTED, "ray basis with non-zero w lanes");
+	if(ctx->nsph > 0 && from[3] != ctx->sph_w)
+		return fail(PWN_E_UNSUPPORTED, "camera w (%g) differs from sphere w (%g)", from[3], ctx->sph_w);
+	if((flags & PWN_F_IDS) && ctx->d_ids == nullptr) return fail(PWN_E_STATE, "PWN_F_IDS without pwn_frame_config(want_ids)");
+	if((flags & PWN_F_BLUR) && ctx->nshards > 1)
+		return fail(PWN_E_UNSUPPORTED, "blur needs the whole pre-blur frame: gather the bands, then pwn_blur_frame");
+
+	TraceParams P;
+	memset(&P, 0, sizeof(P));
+	P.lv.cellmap = ctx->d_cellmap; P.lv.portals = ctx->d_portals; P.lv.w = ctx->w; P.lv.h = ctx->h;
+	P.lv.rcp_tab = ctx->d_rcp; P.lv.rsqrt_tab = ctx->d_rsqrt;
+	P.lv.rcp_shift = 23 - ctx->rcp_bits; P.lv.rsqrt_shift = 23 - ctx->rsqrt_bits;
+	P.lv.sph_pos = ctx->d_sph_pos; P.lv.sph_col = ctx->d_sph_col; P.lv.sph_rr = ctx->d_sph_rr;
+	P.lv.parts_off = ctx->d_parts_off; P.lv.parts_idx = ctx->d_parts_idx; P.lv.nsph = ctx->nsph;
+	for(int i = 0; i < 4; i++) { P.from[i] = from[i]; P.rayb[i] = rayb[i]; P.rdx[i] = rdx[i]; P.rdy[i] = rdy[i]; }
+	P.sec_current = sec;
+	P.dimx = dimx; P.dimy = dimy; P.rwidth = ctx->rwidth;
+	P.nshards = ctx->nshards; P.shard = ctx->shard;
+	const int nbands = (dimy + 31)/32;
+	P.nbands_local = nbands > ctx->shard ? (nbands - ctx->shard + ctx->nshards - 1)/ctx->nshards : 0;
+	const bool blur = (flags & PWN_F_BLUR) != 0;
+	uint32_t *sb = ctx->r_sbuf ? ctx->r_sbuf : f.sbuf, *tsb = ctx->r_tsbuf ? ctx->r_tsbuf : f.tsbuf;
+	P.sbuf = blur ? tsb : sb;
+	P.zbuf = ctx->r_zbuf ? ctx->r_zbuf : f.zbuf;
+	P.ids = (flags & PWN_F_IDS) ? ctx->d_ids : nullptr;
+	P.reflect_blur = (flags & PWN_F_NO_REFLECT_BLUR) ? 0 : 1;
+
+	ctx->timed = ctx->timed_blur = false;
+	if(P.nbands_local > 0)
+	{
+		dim3 grid((dimx + 31)/32, P.nbands_local*4), block(256);
+		if(timing) CU(cudaEventRecord(ctx->ev_k1a, ctx->stream));
+		const bool sph = ctx->nsph > 0, ids = P.ids != nullptr;
+		if(sph) { if(ids) k_trace<true, true><<<grid, block, 0, ctx->stream>>>(P); else k_trace<true, false><<<grid, block, 0, ctx->stream>>>(P); }
+		else { if(ids) k_trace<false, true><<<grid, block, 0, ctx->stream>>>(P); else k_trace<false, false><<<grid, block, 0, ctx->stream>>>(P); }
+		CU(cudaGetLastError());
+		ctx->launches++;
+		if(timing) { CU(cudaEventRecord(ctx->ev_k1b, ctx->stream)); ctx->timed = true; }
+	}
+	if(blur)
+	{
+		BlurParams B;
+		B.src = tsb; B.zbuf = P.zbuf; B.dst = sb;
+		B.dimx = dimx; B.dimy = dimy; B.rwidth = ctx->rwidth; B.y0 = 0; B.y1 = dimy;
+		B.fstr = 0.002f * (float)dimy;
+		dim3 grid((dimx + 255)/256, dimy), block(256);
+		k_blur<<<grid, block, 0, ctx->stream>>>(B);
+		CU(cudaGetLastError());
+		ctx->launches++;
+		if(timing) { CU(cudaEventRecord(ctx->ev_k2b, ctx->stream)); ctx->timed_blur = true; }
+	}
+	return PWN_OK;
+}
+
+extern "C" int pwn_trace_frame(pwn_ctx *ctx, const float from[4], const float rayb[4], const float rdx[4], const float rdy[4],
+	int dimx, int dimy, float sec_current, unsigned flags)
+{
+	CTX_ENTER(ctx);
+	if(from == nullptr || rayb == nullptr || rdx == nullptr || rdy == nullptr) return fail(PWN_E_ARG, "pwn_trace_frame: null vector");
+	return launch_trace(ctx, ctx->fs[0], from, rayb, rdx, rdy, dimx, dimy, sec_current, flags, true);
+}
+
+extern "C" int pwn_blur_frame(pwn_ctx *ctx, int dimx, int dimy)
+{
+	CTX_ENTER(ctx);
+	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "pwn_blur_frame before pwn_frame_config");
+	if(dimx <= 0 || dimy <= 0 || dimx > ctx->rwidth || dimy > ctx->rheight) return fail(PWN_E_ARG, "pwn_blur_frame: bad size");
+	const FrameSet &f = ctx->fs[0];
+	// the traced (pre-blur) frame is in sbuf: it becomes the gather source, as memcpy(tsbuf, sbuf) does (screen.h:75)
+	CU(cudaMemcpyAsync(f.tsbuf, f.sbuf, (size_t)ctx->rwidth*ctx->rheight*4, cudaMemcpyDeviceToDevice, ctx->stream));
+	BlurParams B;
+	B.src = f.tsbuf; B.zbuf = f.zbuf; B.dst = f.sbuf;
+	B.dimx = dimx; B.dimy = dimy; B.rwidth = ctx->rwidth; B.y0 = 0; B.y1 = dimy;
+	B.fstr = 0.002f * (float)dimy;
+	dim3 grid((dimx + 255)/256, dimy), block(256);
+	k_blur<<<grid, block, 0, ctx->stream>>>(B);
+	CU(cudaGetLastError());
+	ctx->launches++;
+	return PWN_OK;
+}
+
+extern "C" int pwn_trace_cam(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags)
+{
+	CTX_ENTER(ctx);
+	if(cam == nullptr) return fail(PWN_E_ARG, "pwn_trace_cam: null cam");
+	if(dimx <= 0 || dimy <= 0) return fail(PWN_E_ARG, "pwn_trace_cam: bad size");
+	float rayb[4], rdx[4], rdy[4];
+	pwn_ray_setup(cam, dimx, dimy, rayb, rdx, rdy);
+	return launch_trace(ctx, ctx->fs[0], cam + 12, rayb, rdx, rdy, dimx, dimy, sec_current, flags, true);
+}
+
+extern "C" int pwn_sync(pwn_ctx *ctx)
+{
+	CTX_ENTER(ctx);
+	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaStreamSynchronize(ctx->copy_stream));
+	return PWN_OK;
+}
+
+extern "C" int pwn_read_frame(pwn_ctx *ctx, uint32_t *sbuf, float *zbuf, pwn_ids *ids)
+{
+	CTX_ENTER(ctx);
+	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "pwn_read_frame before pwn_frame_config");
+	const size_t n = (size_t)ctx->rwidth*ctx->rheight;
+	const FrameSet &f = ctx->fs[0];
+	if(sbuf) CU(cudaMemcpyAsync(sbuf, f.sbuf, n*4, cudaMemcpyDeviceToHost, ctx->stream));
+	if(zbuf) CU(cudaMemcpyAsync(zbuf, f.zbuf, n*4, cudaMemcpyDeviceToHost, ctx->stream));
+	if(ids)
+	{
+		if(ctx->d_ids == nullptr) return fail(PWN_E_STATE, "no ids buffer configured");
+		CU(cudaMemcpyAsync(ids, ctx->d_ids, n*3*sizeof(pwn_ids), cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	CU(cudaStreamSynchronize(ctx->stream));
+	return PWN_OK;
+}
+
+extern "C" int pwn_trace_screen(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags,
+	uint32_t *sbuf_host, float *zbuf_host)
+{
+	CTX_ENTER(ctx);
+	if(cam == nullptr || sbuf_host == nullptr) return fail(PWN_E_ARG, "pwn_trace_screen: null pointer");
+	int rc = pwn_trace_cam(ctx, cam, dimx, dimy, sec_current, flags & ~PWN_F_IDS);
+	if(rc != PWN_OK) return rc;
+	const size_t n = (size_t)ctx->rwidth*ctx->rheight;
+	const FrameSet &f = ctx->fs[0];
+	CU(cudaMemcpyAsync(sbuf_host, f.sbuf, n*4, cudaMemcpyDeviceToHost, ctx->stream));
+	if(zbuf_host) CU(cudaMemcpyAsync(zbuf_host, f.zbuf, n*4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return PWN_OK;
+}
+
+extern "C" int pwn_trace_poses(pwn_ctx *ctx, int n, const pwn_pose *poses, int dimx, int dimy, unsigned flags,
+	uint32_t *sbuf_host, uint64_t *sums)
+{
+	CTX_ENTER(ctx);
+	if(n < 0 || (n > 0 && poses == nullptr)) return fail(PWN_E_ARG, "pwn_trace_poses: bad arguments");
+	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "pwn_trace_poses before pwn_frame_config");
+	if(ctx->r_sbuf) return fail(PWN_E_STATE, "pwn_trace_poses with a redirected frame");
+	const size_t fpix = (size_t)ctx->rwidth*ctx->rheight;
+	flags &= ~PWN_F_IDS;
+	if(sums != nullptr)
+	{
+		if((size_t)n > ctx->sums_cap)
+		{
+			cudaFree(ctx->d_sums);
+			ctx->sums_cap = (size_t)n;
+			CU(cudaMalloc(&ctx->d_sums, ctx->sums_cap*sizeof(unsigned long long)));
+		}
+		CU(cudaMemsetAsync(ctx->d_sums, 0, (size_t)n*sizeof(unsigned long long), ctx->stream));
+	}
+	for(int i = 0; i < n; i++)
+	{
+		const int s = i & 1;
+		float rayb[4], rdx[4], rdy[4];
+		pwn_ray_setup(poses[i].cam, dimx, dimy, rayb, rdx, rdy);
+		// frame set s is free again once the copy of pose i-2 has drained
+		if(sbuf_host != nullptr && i >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[s], 0));
+		int rc = launch_trace(ctx, ctx->fs[s], poses[i].cam + 12, rayb, rdx, rdy, dimx, dimy, poses[i].sec_current, flags, false);
+		if(rc != PWN_OK) return rc;
+		if(sums != nullptr)
+		{
+			k_checksum<<<296, 256, 0, ctx->stream>>>(ctx->fs[s].sbuf, dimx, dimy, ctx->rwidth, ctx->d_sums + i);
+			CU(cudaGetLastError());
+			ctx->launches++;
+		}
+		if(sbuf_host != nullptr)
+		{
+			CU(cudaEventRecord(ctx->ev_done[s], ctx->stream));
+			CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[s], 0));
+			CU(cudaMemcpyAsync(sbuf_host + (size_t)i*fpix, ctx->fs[s].sbuf, fpix*4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+			CU(cudaEventRecord(ctx->ev_copied[s], ctx->copy_stream));
+		}
+	}
+	if(sums != nullptr && n > 0)
+		CU(cudaMemcpyAsync(sums, ctx->d_sums, (size_t)n*sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaStreamSynchronize(ctx->copy_stream));
+	return PWN_OK;
+}
+
+// ---- device-resident access ----------------------------------------------------------------------------
+extern "C" int pwn_frame_device_ptrs(pwn_ctx *ctx, uint64_t *sbuf_dev, uint64_t *zbuf_dev, uint64_t *tsbuf_dev)
+{
+	if(ctx == nullptr) return fail(PWN_E_ARG, "null context");
+	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "no frame configured");
+	if(sbuf_dev) *sbuf_dev = (uint64_t)(uintptr_t)ctx->fs[0].sbuf;
+	if(zbuf_dev) *zbuf_dev = (uint64_t)(uintptr_t)ctx->fs[0].zbuf;
+	if(tsbuf_dev) *tsbuf_dev = (uint64_t)(uintptr_t)ctx->fs[0].tsbuf;
+	return PWN_OK;
+}
+
+extern "C" int pwn_frame_redirect(pwn_ctx *ctx, uint64_t sbuf_dev, uint64_t zbuf_dev, uint64_t tsbuf_dev)
+{
+	if(ctx == nullptr) return fail(PWN_E_ARG, "null context");
+	ctx->r_sbuf = (uint32_t *)(uintptr_t)sbuf_dev;
+	ctx->r_zbuf = (float *)(uintptr_t)zbuf_dev;
+	ctx->r_tsbuf = (uint32_t *)(uintptr_t)tsbuf_dev;
+	return PWN_OK;
+}
+
+extern "C" int pwn_frame_ipc_export(pwn_ctx *ctx, void *handle64, uint64_t *sbuf_off, uint64_t *zbuf_off, uint64_t *tsbuf_off)
+{
+	CTX_ENTER(ctx);
+	if(handle64 == nullptr) return fail(PWN_E_ARG, "null handle");
+	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "no frame configured");
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	cudaIpcMemHandle_t hnd;
+	CU(cudaIpcGetMemHandle(&hnd, ctx->fs[0].base));
+	memcpy(handle64, &hnd, 64);
+	if(sbuf_off) *sbuf_off = ctx->fs[0].off_sbuf;
+	if(zbuf_off) *zbuf_off = ctx->fs[0].off_zbuf;
+	if(tsbuf_off) *tsbuf_off = ctx->fs[0].off_tsbuf;
+	return PWN_OK;
+}
+
+extern "C" int pwn_frame_ipc_import(pwn_ctx *ctx, const void *handle64, uint64_t *base_dev)
+{
+	CTX_ENTER(ctx);
+	if(handle64 == nullptr || base_dev == nullptr) return fail(PWN_E_ARG, "null pointer");
+	cudaIpcMemHandle_t hnd;
+	memcpy(&hnd, handle64, 64);
+	void *p = nullptr;
+	CU(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+	*base_dev = (uint64_t)(uintptr_t)p;
+	return PWN_OK;
+}
+
+extern "C" int pwn_frame_ipc_close(pwn_ctx *ctx, uint64_t base_dev)
+{
+	CTX_ENTER(ctx);
+	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaIpcCloseMemHandle((void *)(uintptr_t)base_dev));
+	return PWN_OK;
+}
+
+extern "C" int pwn_host_alloc(void **out, size_t bytes)
+{
+	if(out == nullptr) return fail(PWN_E_ARG, "null out");
+	CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+	return PWN_OK;
+}
+
+extern "C" int pwn_host_free(void *p)
+{
+	CU(cudaFreeHost(p));
+	return PWN_OK;
+}
+
+// ---- measurement hooks ------------------------------------------------------------------------------------
+extern "C" int pwn_launch_count(pwn_ctx *ctx, uint64_t *count)
+{
+	if(ctx == nullptr || count == nullptr) return fail(PWN_E_ARG, "null pointer");
+	*count = ctx->launches;
+	return PWN_OK;
+}
+
+extern "C" int pwn_last_kernel_ms(pwn_ctx *ctx, float *k1_ms, float *k2_ms)
+{
+	CTX_ENTER(ctx);
+	CU(cudaStreamSynchronize(ctx->stream));
+	if(k1_ms) { *k1_ms = 0.0f; if(ctx->timed) CU(cudaEventElapsedTime(k1_ms, ctx->ev_k1a, ctx->ev_k1b)); }
+	if(k2_ms) { *k2_ms = 0.0f; if(ctx->timed && ctx->timed_blur) CU(cudaEventElapsedTime(k2_ms, ctx->ev_k1b, ctx->ev_k2b)); }
+	return PWN_OK;
+}
+
+extern "C" int pwn_time_frames(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags, int n, float *total_ms)
+{
+	CTX_ENTER(ctx);
+	if(cam == nullptr || total_ms == nullptr || n <= 0) return fail(PWN_E_ARG, "pwn_time_frames: bad arguments");
+	float rayb[4], rdx[4], rdy[4];
+	pwn_ray_setup(cam, dimx, dimy, rayb, rdx, rdy);
+	cudaEvent_t a, b;
+	CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaEventRecord(a, ctx->stream));
+	for(int i = 0; i < n; i++)
+	{
+		int rc = launch_trace(ctx, ctx->fs[0], cam + 12, rayb, rdx, rdy, dimx, dimy, sec_current, flags & ~PWN_F_IDS, false);
+		if(rc != PWN_OK) { cudaEventDestroy(a); cudaEventDestroy(b); return rc; }
+	}
+	CU(cudaEventRecord(b, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaEventElapsedTime(total_ms, a, b));
+	cudaEventDestroy(a); cudaEventDestroy(b);
+	return PWN_OK;
+}
+
+extern "C" int pwn_stream(pwn_ctx *ctx, uint64_t *stream)
+{
+	if(ctx == nullptr || stream == nullptr) return fail(PWN_E_ARG, "null pointer");
+	*stream = (uint64_t)(uintptr_t)ctx->stream;
+	return PWN_OK;
+}

@@ -1,0 +1,220 @@
+/*
+ * pwn_level.c -- level.txt loader and portal derivation, restating level.h:83-228 and
+ * util.h:128-158 for the pwn_level model (see pwn_level.h).  Host code, runs once per
+ * level; checked against the reference's own loader in tests/test_level.py.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "pwn_level.h"
+
+pwn_level *pwn_level_new(int w, int h, int nportals)
+{
+	int i;
+	if(w <= 0 || h <= 0 || nportals < 0) return NULL;
+	pwn_level *lv = calloc(1, sizeof(pwn_level));
+	if(lv == NULL) return NULL;
+	lv->w = w; lv->h = h; lv->nportals = nportals;
+	lv->cells = malloc(sizeof(int32_t)*(size_t)w*h);
+	lv->portals = calloc((size_t)(nportals > 0 ? nportals : 1), sizeof(pwn_portal));
+	if(lv->cells == NULL || lv->portals == NULL) { pwn_level_free(lv); return NULL; }
+	for(i = 0; i < w*h; i++) lv->cells[i] = '.';
+	for(i = 0; i < nportals; i++)
+	{
+		lv->portals[i].x1 = lv->portals[i].x2 = -1;
+		lv->portals[i].z1 = lv->portals[i].z2 = 0;
+		lv->portals[i].c1 = ';';
+		lv->portals[i].c2 = ';';
+	}
+	return lv;
+}
+
+void pwn_level_free(pwn_level *lv)
+{
+	if(lv == NULL) return;
+	free(lv->cells);
+	free(lv->portals);
+	free(lv);
+}
+
+int32_t pwn_level_get_cell(const pwn_level *lv, int cx, int cz)
+{
+	if(cx < 0 || cx >= lv->w) cx = 0;
+	if(cz < 0 || cz >= lv->h) cz = 0;
+	return lv->cells[cz*lv->w + cx];
+}
+
+/* util.h:128-138 */
+static int celltype_is_free(int32_t c)
+{
+	if(c == ';' || c == '$' || c == '"') return 1;
+	if(c == '#' || c == '&') return 1;
+	if(c == '>' || c == '<' || c == '^' || c == ',') return 1;
+	return 0;
+}
+
+/*
+ * The reference indexes data[z][x+-1] / data[z+-1][x] unchecked (util.h:140-149); on its
+ * contiguous 64x64 array an x overflow lands in the neighbouring row.  Same here through
+ * the flat index; anything outside the array counts as not free.
+ */
+static int32_t cell_flat(const pwn_level *lv, int x, int z)
+{
+	long idx = (long)z*lv->w + x;
+	if(idx < 0 || idx >= (long)lv->w*lv->h) return '.';
+	return lv->cells[idx];
+}
+
+static int find_free_dir_2d(const pwn_level *lv, int x, int z)
+{
+	if(celltype_is_free(cell_flat(lv, x+1, z))) return PWN_FXP;
+	if(celltype_is_free(cell_flat(lv, x, z+1))) return PWN_FZP;
+	if(celltype_is_free(cell_flat(lv, x-1, z))) return PWN_FXN;
+	if(celltype_is_free(cell_flat(lv, x, z-1))) return PWN_FZN;
+	return PWN_FXP;   /* "stuff it" (util.h:148) */
+}
+
+static int32_t cell_in_dir(const pwn_level *lv, int x, int z, int d)
+{
+	switch(d)
+	{
+		case PWN_FXP: return cell_flat(lv, x+1, z);
+		case PWN_FZP: return cell_flat(lv, x, z+1);
+		case PWN_FXN: return cell_flat(lv, x-1, z);
+		default: return cell_flat(lv, x, z-1);
+	}
+}
+
+void pwn_level_derive(pwn_level *lv)
+{
+	int i;
+	for(i = 0; i < lv->nportals; i++)
+	{
+		pwn_portal *pm = &lv->portals[i];
+		if(pm->x2 == -1) continue;
+		int d1 = find_free_dir_2d(lv, pm->x1, pm->z1);
+		int d2 = find_free_dir_2d(lv, pm->x2, pm->z2);
+		pm->rot12 = (d2 - d1 + 2) & 3;
+		pm->c1 = cell_in_dir(lv, pm->x1, pm->z1, d1);
+		pm->c2 = cell_in_dir(lv, pm->x2, pm->z2, d2);
+	}
+}
+
+static void portal_register(pwn_portal *pm, int x, int z)
+{
+	if(pm->x1 == -1) { pm->x1 = x; pm->z1 = z; }
+	else if(pm->x2 == -1) { pm->x2 = x; pm->z2 = z; }
+}
+
+int pwn_level_link(pwn_level *lv)
+{
+	int x, z, i;
+	for(i = 0; i < lv->nportals; i++)
+	{
+		lv->portals[i].x1 = lv->portals[i].x2 = -1;
+		lv->portals[i].c1 = lv->portals[i].c2 = ';';
+	}
+	for(z = 0; z < lv->h; z++)
+	for(x = 0; x < lv->w; x++)
+	{
+		int32_t c = lv->cells[z*lv->w + x];
+		if(PWN_IS_PORTAL(c))
+		{
+			int pi = PWN_PORTAL_INDEX(c);
+			if(pi < 0 || pi >= lv->nportals) return -1;
+			portal_register(&lv->portals[pi], x, z);
+		}
+	}
+	pwn_level_derive(lv);
+	return 0;
+}
+
+/* level.h:107-228 over a byte stream */
+typedef struct { const unsigned char *p, *end; } rd_t;
+static int rd_getc(rd_t *r) { return r->p < r->end ? *r->p++ : -1; }
+
+pwn_level *pwn_level_parse(const char *text, size_t len)
+{
+	int x, z;
+	rd_t r;
+	r.p = (const unsigned char *)text; r.end = r.p + len;
+	pwn_level *lv = pwn_level_new(64, 64, 26);
+	if(lv == NULL) return NULL;
+
+	for(z = 0; z < 64; z++)
+	{
+		for(x = 0; x < 64; x++)
+		{
+			int c = rd_getc(&r);
+			if(c == -1 || c == '\r' || c == '\n')
+			{
+				if(c == -1) goto done_load;
+				else if(x == 0) { x--; continue; }   /* blank line / LF of a CRLF */
+				else break;
+			}
+			if(c == '*')   /* spawn (level.h:137-142) */
+			{
+				c = ';';
+				lv->sx = x; lv->sz = z;
+			}
+			if(c >= 'a' && c <= 'z'-1)   /* level.h:144-161: registers in its own slot, then becomes the NEXT letter */
+			{
+				portal_register(&lv->portals[c-'a'], x, z);
+				c = (c-'a')+'A' + 1;
+			}
+			if(c >= 'A' && c <= 'Z')     /* level.h:163-178 */
+				portal_register(&lv->portals[c-'A'], x, z);
+			lv->cells[z*64 + x] = c;
+		}
+	}
+done_load:
+	pwn_level_derive(lv);
+	return lv;
+}
+
+pwn_level *pwn_level_load(const char *fname)
+{
+	FILE *fp = fopen(fname, "rb");
+	if(fp == NULL) return NULL;
+	size_t cap = 1 << 16, len = 0;
+	char *buf = malloc(cap);
+	if(buf == NULL) { fclose(fp); return NULL; }
+	for(;;)
+	{
+		size_t n = fread(buf + len, 1, cap - len, fp);
+		len += n;
+		if(n == 0) break;
+		if(len == cap) { cap *= 2; buf = realloc(buf, cap); if(buf == NULL) { fclose(fp); return NULL; } }
+	}
+	fclose(fp);
+	pwn_level *lv = pwn_level_parse(buf, len);
+	free(buf);
+	return lv;
+}
+
+int pwn_level_save_txt(const pwn_level *lv, const char *fname)
+{
+	int x, z;
+	if(lv->w > 64 || lv->h > 64) return -1;
+	for(z = 0; z < lv->h; z++)
+	for(x = 0; x < lv->w; x++)
+	{
+		int32_t c = lv->cells[z*lv->w + x];
+		if(c < 32 || c > 126 || c == '*' || (c >= 'a' && c <= 'z')) return -1;
+	}
+	FILE *fp = fopen(fname, "wb");
+	if(fp == NULL) return -1;
+	for(z = 0; z < lv->h; z++)
+	{
+		for(x = 0; x < lv->w; x++)
+		{
+			int32_t c = lv->cells[z*lv->w + x];
+			if(x == lv->sx && z == lv->sz && c == ';') c = '*';
+			fputc(c, fp);
+		}
+		fputc('\n', fp);
+	}
+	fclose(fp);
+	return 0;
+}

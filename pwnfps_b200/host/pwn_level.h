@@ -1,0 +1,57 @@
+/*
+ * pwn_level.h -- host-side level model of the B200 build: the part of the reference's
+ * `level` (defs.h:96-111) the trace reads, without the 64x64 / 26-letter limits, plus
+ * a loader for the reference's level.txt format (level.h:107-228).
+ *
+ * A host that keeps the reference's own level.h loader does not need this file: it
+ * hands its `level` to the library through pwn_screen.h.  This loader exists for the
+ * headless bench harness and for levels beyond the reference's limits.
+ */
+#ifndef PWN_LEVEL_H
+#define PWN_LEVEL_H
+
+#include <stdint.h>
+#include "pwntrace.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pwn_level
+{
+	int32_t w, h;            /* grid, reference: 64 x 64 (defs.h:105) */
+	int32_t *cells;          /* [h][w] codes, see pwntrace.h "Cell codes" */
+	int32_t nportals;        /* reference: 26 (defs.h:103) */
+	pwn_portal *portals;
+	int32_t sx, sz;          /* spawn cell (defs.h:101) */
+} pwn_level;
+
+/* level_new (level.h:85-105): all '.', portals unpaired with c1 = c2 = ';' */
+pwn_level *pwn_level_new(int w, int h, int nportals);
+void pwn_level_free(pwn_level *lv);
+
+/* level_load (level.h:107-228): 64x64 grid, 26 portals, same parsing quirks. NULL on I/O error. */
+pwn_level *pwn_level_load(const char *fname);
+/* same parser over a memory buffer */
+pwn_level *pwn_level_parse(const char *text, size_t len);
+
+/*
+ * Portal pairing for levels built in memory: scans the grid row-major and registers
+ * every portal cell in its slot the way the loader does (first two occurrences,
+ * level.h:163-178), then derives rot12/c1/c2 (level.h:194-221).
+ */
+int pwn_level_link(pwn_level *lv);
+
+/* level.h:194-221 alone: rot12, c1, c2 of every paired portal from the facing free cells */
+void pwn_level_derive(pwn_level *lv);
+
+/* util.h:151-158 */
+int32_t pwn_level_get_cell(const pwn_level *lv, int cx, int cz);
+
+/* writes the level in level.txt format; fails (-1) if it does not fit 64x64 / 26 letters */
+int pwn_level_save_txt(const pwn_level *lv, const char *fname);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,87 @@
+"""Host logic: the C level loader (pwnfps_b200/host/pwn_level.c) against the reference's own
+loader (level.h:107-228 via oracle/_ref) and the synthetic level generators."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import REFERENCE
+from pwnfps_b200 import api, levels
+
+
+def test_default_level_kat(default_level):
+    """portal table printed by level_load for level.txt, spawn 9,4."""
+    lv = default_level
+    assert (lv.w, lv.h, lv.sx, lv.sz) == (64, 64, 9, 4)
+    got = " ".join("%s%d" % (chr(65 + i), p["rot12"]) for i, p in enumerate(lv.portals) if p["x2"] != -1)
+    assert got == "A0 B0 C0 D0 E1 F0 G0 H3 I1 J2 K3 L0 M0 O3 P0 Q0 R0 S0 T2 X0 Y1 Z2"
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REFERENCE, "level.txt")), reason="reference absent")
+def test_loader_matches_reference_loader(refs, default_level):
+    ref = refs("libref_ids.so")
+    ref.level_load(os.path.join(REFERENCE, "level.txt"))
+    cells, pm = ref.level_get()
+    lv = api.level_load(os.path.join(REFERENCE, "level.txt"))
+    assert (lv.cells == cells).all()
+    assert (lv.portals_i32() == pm).all()
+    assert (lv.sx, lv.sz) == ref.spawn()
+    # and the committed copy of the parsed level is that same level
+    assert (default_level.cells == cells).all() and (default_level.portals_i32() == pm).all()
+
+
+def test_loader_quirks():
+    # lowercase double registration (level.h:144-161): 'm' closes M and opens N
+    txt = ".....\r\n.M;m.\r\n.....\r\n..*..\r\n"
+    lv = api.level_parse(txt)
+    assert chr(lv.cells[1, 1]) == "M" and chr(lv.cells[1, 3]) == "N"
+    m, n = lv.portals[12], lv.portals[13]
+    assert (m["x1"], m["z1"], m["x2"], m["z2"]) == (1, 1, 3, 1)
+    assert (n["x1"], n["z1"], n["x2"]) == (3, 1, -1)
+    assert (lv.sx, lv.sz) == (2, 3) and chr(lv.cells[3, 2]) == ";"
+    # a third occurrence of a letter is ignored by the table but stays in the grid
+    lv = api.level_parse(";A;\n;A;\n;A;\n")
+    a = lv.portals[0]
+    assert (a["x1"], a["z1"], a["x2"], a["z2"]) == (1, 0, 1, 1) and chr(lv.cells[2, 1]) == "A"
+
+
+def test_mirror_hall_roundtrips_through_level_txt(tmp_path, refs):
+    lv = levels.mirror_hall()
+    paired = lv.portals["x2"] != -1
+    assert paired.sum() == 17
+    assert set(lv.portals["rot12"][paired].tolist()) == {0, 1, 2, 3}
+    p = str(tmp_path / "hall.txt")
+    lv.save_txt(p)
+    back = api.level_load(p)
+    assert (back.cells == lv.cells).all() and (back.portals_i32() == lv.portals_i32()).all()
+    ref = refs("libref_ids.so")
+    ref.level_load(p)
+    cells, pm = ref.level_get()
+    assert (cells == lv.cells).all() and (pm == lv.portals_i32()).all()
+
+
+def test_maze_is_deterministic_and_sized():
+    a, b = levels.maze(seed=1), levels.maze(seed=1)
+    assert (a.cells == b.cells).all() and (a.portals_i32() == b.portals_i32()).all()
+    walk = np.isin(a.cells, [ord(c) for c in ';$"#&><,^']).sum()
+    assert 9500 <= walk <= 10500
+    paired = a.portals["x2"] != -1
+    assert paired.all() and len(a.portals) >= 100
+    assert (levels.maze(seed=2).cells != a.cells).any()
+    # portal cells sit off the border with exactly one walkable neighbour
+    for pm in a.portals:
+        for (x, z) in ((pm["x1"], pm["z1"]), (pm["x2"], pm["z2"])):
+            assert 1 <= x < a.w - 1 and 1 <= z < a.h - 1
+            nb = [a.cells[z, x + 1], a.cells[z + 1, x], a.cells[z, x - 1], a.cells[z - 1, x]]
+            assert sum(1 for c in nb if chr(c) in ';$"#&><,^') == 1 if all(c < 256 for c in nb) else True
+
+
+def test_flythrough_is_deterministic(default_level):
+    a = api.flythrough(default_level, 300)
+    b = api.flythrough(default_level, 300)
+    assert a.tobytes() == b.tobytes()
+    # it moves, turns and crosses at least one portal (a jump of more than 2 cells in one tick)
+    pos = a["cam"][:, 12:15]
+    step = np.abs(np.diff(pos[:, [0, 2]], axis=0)).max(axis=1)
+    assert (step > 2.0).any() and np.ptp(a["cam"][:, 8]) > 0.5
+    assert abs(float(a["sec_current"][60]) - 1.0) < 1e-4

@@ -1,0 +1,205 @@
+"""Pins the CPU restatement (oracle/pwn_oracle.c) against the reference's own code compiled
+headless (oracle/_ref) and against the committed fixtures generated from it.
+
+Bars:  ids and zbuf bit-exact vs the shipped-flags build; sbuf bit-exact vs the same sources
+built without -ffast-math, and within 1 LSB on < 1e-5 of pixels vs the shipped-flags build
+(gcc's fast-math code generation, DESIGN.md "Oracle")."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, oracle_set_level, rgb_diff
+from pwnfps_b200 import api, levels
+
+IDF = ("cell", "ldir", "kind", "nstep", "nportal")
+
+
+def same_tables_as_golden():
+    g = np.load(os.path.join(GOLDEN, "host_tables.npz"))
+    rb, sb, rt, st = api.host_math_probe()
+    return rb == int(g["rcp_bits"]) and sb == int(g["rsqrt_bits"]) and (rt == g["rcp_tab"]).all() and (st == g["rsqrt_tab"]).all()
+
+
+def test_util_kats(oracle):
+    """RNG / pack known answers dumped from the reference build (exact integer parts)."""
+    k = np.load(os.path.join(GOLDEN, "kat_util.npz"))
+    for s in k["seeds"]:
+        v, st = oracle.randfs_seq(int(s), 64)
+        assert (st == k["randst_%d" % s]).all()
+        assert (v.view(np.uint32) == k["randfs_%d" % s].view(np.uint32)).all()
+    got = np.array([oracle.col_ftoint(c) for c in k["cols"]], np.uint32)
+    assert (got == k["packed"]).all()
+    for a, want in zip(k["angs"], k["roty"]):
+        got = api.mat4_roty(np.eye(4, dtype=np.float32).reshape(16), a)
+        assert np.allclose(got, want, atol=1e-6)
+
+
+def test_randfs_exhaustive_vs_reference(oracle, refs):
+    """every residue r in 0..3758 gives the reference's float"""
+    ref = refs("libref_noblur.so")
+    # seeds that produce each residue: walk the LCG long enough to see them all
+    seen = {}
+    v_o, st_o = oracle.randfs_seq(99, 40000)
+    v_r, st_r = ref.randfs_seq(99, 40000)
+    assert (st_o == st_r).all()
+    assert (v_o.view(np.uint32) == v_r.view(np.uint32)).all()
+    for s in st_o:
+        seen[int(s) % 3759] = 1
+    assert len(seen) == 3759
+
+
+@pytest.mark.skipif(not same_tables_as_golden(), reason="this CPU's rcpps/rsqrtps differ from the fixture's")
+def test_golden_frames(oracle, default_level):
+    g = np.load(os.path.join(GOLDEN, "frames_default.npz"))
+    oracle_set_level(oracle, default_level)
+    for name in g["names"]:
+        w, h = g[name + "_size"]
+        s, z, ids = oracle.trace_frame(g[name + "_cam"], float(g[name + "_sec"]), int(w), int(h), want_ids=True)
+        assert (z.view(np.uint32) == g[name + "_zbuf"].view(np.uint32)).all()
+        for f in IDF:
+            assert (ids[f] == g[name + "_ids"][f]).all(), f
+        d = rgb_diff(s, g[name + "_sbuf"])
+        assert d.max() <= 1 and (d > 0).mean() < 1e-4
+        if d.max() == 0:
+            b = oracle.blur(s, z, int(w), int(h))
+            assert (b == g[name + "_sbuf_blur"]).all()
+
+
+def _compare(oracle, ref, ref_strict, cam, sec, w, h, dim_ref=64):
+    s, z, ids, _ = ref.trace_frame(cam, sec, w, h, want_ids=True)
+    so, zo, io = oracle.trace_frame(cam, sec, w, h, want_ids=True)
+    assert (z.view(np.uint32) == zo.view(np.uint32)).all()
+    for f in IDF:
+        assert (ids[f] == io[f]).all(), f
+    d = rgb_diff(s, so)
+    assert d.max() <= 1 and (d > 0).mean() < 1e-5
+    if ref_strict is not None:
+        ss, zs, _, _ = ref_strict.trace_frame(cam, sec, w, h)
+        assert (ss == so).all() and (zs.view(np.uint32) == zo.view(np.uint32)).all()
+    return s, z, so, zo
+
+
+def _compare_ids_only(oracle, ref, cam, sec, w, h):
+    s, z, ids, _ = ref.trace_frame(cam, sec, w, h, want_ids=True)
+    so, zo, io = oracle.trace_frame(cam, sec, w, h, want_ids=True)
+    assert (z.view(np.uint32) == zo.view(np.uint32)).all()
+    for f in IDF:
+        assert (ids[f] == io[f]).all(), f
+    return so, zo, io
+
+
+def test_default_level_vs_reference(oracle, refs, default_level, tmp_path):
+    ref, strict, refb = refs("libref_ids.so"), refs("libref_strict.so"), refs("libref.so")
+    p = str(tmp_path / "level.txt")
+    default_level.save_txt(p)
+    for r in (ref, strict, refb):
+        r.level_load(p)
+    oracle_set_level(oracle, default_level)
+    cam0 = api.cam_spawn(default_level)
+    for yaw, sec, (w, h) in [(0.0, 0.0, (320, 240)), (0.9, 0.7, (333, 77)), (2.2, 1.3, (640, 360)),
+                             (3.9, 5.0, (160, 300)), (5.1, 2.0, (642, 33))]:
+        cam = api.mat4_roty(cam0, yaw)
+        s, z, so, zo = _compare(oracle, ref, strict, cam, sec, w, h)
+        # blur pass: same input -> bit-identical output (integer pavgb + LCG)
+        if w % 4:
+            continue   # the reference's blur needs rwidth % 4 == 0 (aligned store, screen.h:88,117)
+        sb, _, _, _ = refb.trace_frame(cam, sec, w, h)
+        if (s == so).all():
+            assert (oracle.blur(so, zo, w, h) == sb).all()
+
+
+def test_flythrough_poses_vs_reference(oracle, refs, default_level, tmp_path):
+    ref = refs("libref_ids.so")
+    p = str(tmp_path / "level.txt")
+    default_level.save_txt(p)
+    ref.level_load(p)
+    oracle_set_level(oracle, default_level)
+    poses = api.flythrough(default_level, 600)
+    for i in range(0, 600, 75):
+        _compare(oracle, ref, None, poses["cam"][i], float(poses["sec_current"][i]), 240, 136)
+
+
+def test_mirror_hall_vs_reference(oracle, refs, tmp_path):
+    lv = levels.mirror_hall()
+    ref, strict = refs("libref_ids.so"), refs("libref_strict.so")
+    p = str(tmp_path / "hall.txt")
+    lv.save_txt(p)
+    ref.level_load(p)
+    strict.level_load(p)
+    oracle_set_level(oracle, lv)
+    cam0 = api.cam_spawn(lv)
+    deep = 0
+    for yaw in (0.0, 1.57, 0.4, 3.3, 4.6):
+        cam = api.mat4_roty(cam0, yaw)
+        _compare(oracle, ref, strict, cam, 0.5, 320, 180)
+        # a wide, flat frame: pixel pitch 2/dimx in tan(angle) keeps the centre rows in the chain
+        _, _, ids = _compare_ids_only(oracle, ref, cam, 0.5, 1920, 8)
+        deep = max(deep, int(ids["nportal"].max()))
+    assert deep >= 12   # the chain really is walked deep
+    # a pose inside the endless hall: walks that exhaust maxsteps (trace.h:677) must agree too
+    last = lv.portals[16]
+    cam = np.eye(4, dtype=np.float32)
+    cam[3, :3] = (last["x1"] - 2.5, 0.5, last["z1"] + 0.5)
+    cam = api.mat4_roty(cam.reshape(16), 1.5707964)
+    _, _, so, zo = _compare(oracle, ref, strict, cam, 0.0, 256, 144)
+
+
+def test_spheres_vs_reference(oracle, refs, default_level, tmp_path):
+    ref, strict = refs("libref_ids.so"), refs("libref_strict.so")
+    p = str(tmp_path / "level.txt")
+    default_level.save_txt(p)
+    lv = levels.game_spheres(levels.default_level(), sec=0.3)
+    for r in (ref, strict):
+        r.level_load(p)
+        r.objs_clear()
+        for sp in lv.spheres:
+            r.obj_sphere(sp["r"], sp["refl"], sp["pos"][0], sp["pos"][1], sp["pos"][2], sp["col"][0], sp["col"][1], sp["col"][2])
+    oracle_set_level(oracle, lv)
+    cam0 = api.cam_spawn(lv)
+    hits = 0
+    for yaw in (0.0, 0.35, -0.4):
+        cam = api.mat4_roty(cam0, yaw)
+        _compare(oracle, ref, strict, cam, 0.3, 320, 240)
+        _, _, ids = oracle.trace_frame(cam, 0.3, 320, 240, want_ids=True)
+        hits += int((ids["kind"] == 1).sum())
+    assert hits > 1000
+    for r in (ref, strict):
+        r.objs_clear()
+
+
+def test_wide_reference_equals_unmodified_on_default_level(refs, default_level, tmp_path):
+    """The widened build (128x128 int cells, 4096 portals) is accepted only if it reproduces
+    the unmodified build bit for bit."""
+    ref, wide = refs("libref_ids.so"), refs("libref_wide_ids.so")
+    p = str(tmp_path / "level.txt")
+    default_level.save_txt(p)
+    ref.level_load(p)
+    cells = np.full((wide.dim, wide.dim), ord("."), np.int32)
+    cells[:64, :64] = default_level.cells
+    wide.level_set(cells, default_level.portals_i32(), default_level.sx, default_level.sz)
+    cam0 = api.cam_spawn(default_level)
+    for yaw in (0.0, 2.0, 4.0):
+        cam = api.mat4_roty(cam0, yaw)
+        a = ref.trace_frame(cam, 0.25, 320, 240, want_ids=True)
+        b = wide.trace_frame(cam, 0.25, 320, 240, want_ids=True)
+        assert (a[0] == b[0]).all() and (a[1].view(np.uint32) == b[1].view(np.uint32)).all()
+        for f in ("ldir", "kind", "nstep", "nportal"):
+            assert (a[2][f] == b[2][f]).all()
+        # cell ids use each build's own row stride
+        ca, cb = a[2]["cell"], b[2]["cell"]
+        assert ((ca // 64 == cb // 128) & (ca % 64 == cb % 128)).all()
+
+
+def test_maze_vs_wide_reference(oracle, refs):
+    lv = levels.maze(dim=128, seed=1)
+    wide = refs("libref_wide_ids.so")
+    wide.level_set(lv.cells, lv.portals_i32(), lv.sx, lv.sz)
+    oracle_set_level(oracle, lv)
+    poses = levels.poses_random(lv, 6, seed=1)
+    crossed = 0
+    for pz in poses:
+        s, z, so, zo = _compare(oracle, wide, None, pz["cam"], float(pz["sec_current"]), 256, 144)
+        _, _, ids = oracle.trace_frame(pz["cam"], float(pz["sec_current"]), 64, 36, want_ids=True)
+        crossed += int(ids["nportal"].sum())
+    assert crossed > 0
