@@ -1,0 +1,251 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs, against the committed golden fixtures, and -- at
+BASELINE.json's full sizes -- through size-independent properties.
+
+Bars (north_star): hit ids (cell, face, steps, portal crossings) and zbuf of the PRIMARY
+segment bit-exact; every segment's ids bit-exact except pixels whose bounce passes within the
+libm tolerance below; RGB within 1 LSB per channel on >= 99.9% of pixels."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, oracle_set_level, rgb_diff
+from pwnfps_b200 import api, levels
+
+pytestmark = pytest.mark.gpu
+
+IDF = ("cell", "ldir", "kind", "nstep", "nportal")
+
+# RGB tolerance stated by north_star: <= 1 LSB per channel on >= 99.9% of pixels
+RGB_LSB = 1
+RGB_FRACTION = 0.999
+
+
+def check_frame(tracer, oracle, cam, sec, w, h, exact_rgb=None, label=""):
+    tracer.frame_config(w, h, want_ids=True)
+    tracer.frame_clear()
+    tracer.trace_cam(cam, w, h, sec, api.PWN_F_IDS)
+    s, z, ids = tracer.read_frame(want_ids=True)
+    so, zo, io = oracle.trace_frame(cam, sec, w, h, want_ids=True)
+    # primary segment: bit-exact
+    assert (z.view(np.uint32) == zo.view(np.uint32)).all(), label
+    for f in IDF:
+        assert (ids[..., 0][f] == io[..., 0][f]).all(), (label, f)
+    # bounce segments: count mismatching pixels ("grazing", reported)
+    bad = np.zeros((h, w), bool)
+    for seg in (1, 2):
+        for f in IDF:
+            bad |= ids[..., seg][f] != io[..., seg][f]
+    d = rgb_diff(s, so)
+    frac_ok = (d <= RGB_LSB).mean()
+    assert frac_ok >= RGB_FRACTION, (label, frac_ok)
+    assert bad.mean() <= 1e-3, (label, bad.mean())
+    return {"rgb_exact": float((d == 0).mean()), "rgb_le1": float(frac_ok), "ids_bounce_mismatch": float(bad.mean()),
+            "sbuf": s, "zbuf": z, "osbuf": so, "ozbuf": zo}
+
+
+def test_default_level_poses(tracer, oracle, default_level):
+    tracer.level_upload(default_level)
+    tracer.level_prepare_render()
+    oracle_set_level(oracle, default_level)
+    cam0 = api.cam_spawn(default_level)
+    for yaw, sec, (w, h) in [(0.0, 0.0, (320, 240)), (0.9, 0.7, (333, 77)), (2.2, 1.3, (640, 360)),
+                             (3.9, 5.0, (160, 300)), (5.1, 2.0, (642, 33)), (1.1, 0.1, (1920, 1080))]:
+        r = check_frame(tracer, oracle, api.mat4_roty(cam0, yaw), sec, w, h, label="yaw%.1f %dx%d" % (yaw, w, h))
+        print("default yaw %.1f %dx%d: rgb exact %.6f, <=1LSB %.6f, bounce-id mismatch %.2e"
+              % (yaw, w, h, r["rgb_exact"], r["rgb_le1"], r["ids_bounce_mismatch"]))
+
+
+def test_blur_pass_bit_exact(tracer, oracle, default_level):
+    """K2 is integer pavgb + LCG: given the same pre-blur frame and zbuf it must be bit-identical."""
+    tracer.level_upload(default_level)
+    tracer.level_prepare_render()
+    oracle_set_level(oracle, default_level)
+    cam = api.mat4_roty(api.cam_spawn(default_level), 0.6)
+    for (w, h) in [(320, 240), (322, 100), (1920, 1080)]:
+        tracer.frame_config(w, h)
+        tracer.frame_clear()
+        tracer.trace_cam(cam, w, h, 0.5, 0)
+        pre, z, _ = tracer.read_frame()
+        tracer.trace_cam(cam, w, h, 0.5, api.PWN_F_BLUR)
+        post, z2, _ = tracer.read_frame()
+        assert (z.view(np.uint32) == z2.view(np.uint32)).all()
+        want = oracle.blur(pre, z, w, h)
+        assert (post == want).all()
+        # the separate entry point (multi-GPU harness) gives the same frame
+        tracer.trace_cam(cam, w, h, 0.5, 0)
+        tracer.blur_frame(w, h)
+        post2, _, _ = tracer.read_frame()
+        assert (post2 == want).all()
+
+
+def test_golden_fixtures_with_fixture_tables(oracle, default_level):
+    """Reference frames generated on another host: the device is given THAT host's
+    rcpps/rsqrtps tables, so the comparison is valid on any CPU."""
+    g = np.load(os.path.join(GOLDEN, "frames_default.npz"))
+    t = np.load(os.path.join(GOLDEN, "host_tables.npz"))
+    tr = api.Tracer(0, math_tables=(int(t["rcp_bits"]), int(t["rsqrt_bits"]), t["rcp_tab"], t["rsqrt_tab"]))
+    try:
+        tr.level_upload(default_level)
+        tr.level_prepare_render()
+        for name in g["names"]:
+            w, h = (int(v) for v in g[name + "_size"])
+            tr.frame_config(w, h, want_ids=True)
+            tr.frame_clear()
+            tr.trace_cam(g[name + "_cam"], w, h, float(g[name + "_sec"]), api.PWN_F_IDS)
+            s, z, ids = tr.read_frame(want_ids=True)
+            assert (z.view(np.uint32) == g[name + "_zbuf"].view(np.uint32)).all()
+            for f in IDF:
+                assert (ids[..., 0][f] == g[name + "_ids"][..., 0][f]).all(), f
+            d = rgb_diff(s, g[name + "_sbuf"])
+            assert (d <= RGB_LSB).mean() >= RGB_FRACTION
+            tr.trace_cam(g[name + "_cam"], w, h, float(g[name + "_sec"]), api.PWN_F_BLUR)
+            sb, _, _ = tr.read_frame()
+            db = rgb_diff(sb, g[name + "_sbuf_blur"])
+            assert (db <= RGB_LSB).mean() >= 0.995   # a differing pre-blur pixel is gathered 4x
+    finally:
+        tr.close()
+
+
+def test_mirror_hall(tracer, oracle):
+    lv = levels.mirror_hall()
+    tracer.level_upload(lv)
+    tracer.level_prepare_render()
+    oracle_set_level(oracle, lv)
+    cam0 = api.cam_spawn(lv)
+    for yaw in (0.0, 1.5707964, 0.4, 3.3, 4.6):
+        r = check_frame(tracer, oracle, api.mat4_roty(cam0, yaw), 0.5, 640, 360, label="hall yaw %.2f" % yaw)
+    r = check_frame(tracer, oracle, api.mat4_roty(cam0, 1.5707964), 0.5, 1920, 8, label="hall deep")
+    # endless hall: exhausted walks leave zbuf untouched and return the ray as the colour
+    last = lv.portals[16]
+    cam = np.eye(4, dtype=np.float32)
+    cam[3, :3] = (last["x1"] - 2.5, 0.5, last["z1"] + 0.5)
+    cam = api.mat4_roty(cam.reshape(16), 1.5707964)
+    check_frame(tracer, oracle, cam, 0.0, 256, 144, label="endless")
+
+
+def test_spheres(tracer, oracle):
+    lv = levels.game_spheres(levels.default_level(), sec=0.3)
+    tracer.level_upload(lv)
+    tracer.level_prepare_render()
+    oracle_set_level(oracle, lv)
+    cam0 = api.cam_spawn(lv)
+    for yaw in (0.0, 0.35, -0.4):
+        check_frame(tracer, oracle, api.mat4_roty(cam0, yaw), 0.3, 320, 240, label="spheres %.2f" % yaw)
+    lv.spheres = lv.spheres[:0]
+    tracer.level_prepare_render()
+
+
+def test_maze_wide_level(tracer, oracle):
+    """10k-sector level (beyond the reference's 64x64/26 limits), seeded poses."""
+    lv = levels.maze(dim=128, seed=1)
+    tracer.level_upload(lv)
+    tracer.level_prepare_render()
+    oracle_set_level(oracle, lv)
+    for pz in levels.poses_random(lv, 6, seed=1):
+        check_frame(tracer, oracle, pz["cam"], float(pz["sec_current"]), 480, 270, label="maze")
+
+
+def test_row_band_sharding_stitches(tracer, default_level):
+    """bands b % N == r traced separately land on exactly the 1-shard frame."""
+    tracer.level_upload(default_level)
+    tracer.level_prepare_render()
+    cam = api.mat4_roty(api.cam_spawn(default_level), 2.0)
+    w, h = 640, 361
+    tracer.frame_config(w, h)
+    tracer.shard_config(1, 0)
+    tracer.frame_clear()
+    tracer.trace_cam(cam, w, h, 0.0, 0)
+    full, zfull, _ = tracer.read_frame()
+    for n in (2, 3, 8):
+        acc = np.zeros_like(full)
+        zacc = np.zeros_like(zfull)
+        for r in range(n):
+            tracer.shard_config(n, r)
+            tracer.frame_clear()
+            tracer.trace_cam(cam, w, h, 0.0, 0)
+            s, z, _ = tracer.read_frame()
+            rows = np.array([((y // 32) % n) == r for y in range(h)])
+            assert (s[~rows] == 0).all()
+            acc[rows] = s[rows]
+            zacc[rows] = z[rows]
+        assert (acc == full).all() and (zacc.view(np.uint32) == zfull.view(np.uint32)).all()
+    tracer.shard_config(1, 0)
+
+
+def test_trace_screen_centred_and_poses(tracer, oracle, default_level):
+    """The drop-in call and the batched fly-through: host buffers, checksums."""
+    tracer.level_upload(default_level)
+    tracer.level_prepare_render()
+    oracle_set_level(oracle, default_level)
+    w, h = 320, 240
+    tracer.frame_config(w, h)
+    cam = api.cam_spawn(default_level)
+    zb = np.zeros((h, w), np.float32)
+    sb = tracer.trace_screen_centred(default_level, 0, 0, w, h, cam, 0.0, blur=True, zbuf=zb)
+    so, zo, _ = oracle.trace_frame(cam, 0.0, w, h)
+    assert (zb.view(np.uint32) == zo.view(np.uint32)).all()
+    assert (rgb_diff(sb, oracle.blur(so, zo, w, h)) <= RGB_LSB).mean() >= 0.995
+    poses = api.flythrough(default_level, 12)
+    out = np.zeros((12, h, w), np.uint32)
+    sums = tracer.trace_poses(poses, w, h, 0, out=out, want_sums=True)
+    for i in range(12):
+        assert int(sums[i]) == int(api.checksum_ref(out[i], w, h))
+        tracer.trace_cam(poses["cam"][i], w, h, float(poses["sec_current"][i]), 0)
+        s, _, _ = tracer.read_frame(want_z=False)
+        assert (s == out[i]).all()
+    sums2 = tracer.trace_poses(poses, w, h, 0, out=None, want_sums=True)
+    assert (sums == sums2).all()
+
+
+def test_full_size_properties(tracer, default_level):
+    """BASELINE sizes (4K, 8K): determinism, band-stitch equality by checksum, zbuf sanity."""
+    tracer.level_upload(default_level)
+    tracer.level_prepare_render()
+    poses = api.flythrough(default_level, 2)
+    for (w, h) in [(3840, 2160), (7680, 4320)]:
+        tracer.frame_config(w, h)
+        tracer.shard_config(1, 0)
+        a = tracer.trace_poses(poses, w, h, 0, want_sums=True)
+        b = tracer.trace_poses(poses, w, h, 0, want_sums=True)
+        assert (a == b).all()
+        tracer.trace_cam(poses["cam"][1], w, h, float(poses["sec_current"][1]), 0)
+        s, z, _ = tracer.read_frame()
+        assert int(api.checksum_ref(s, w, h)) == int(a[1])
+        assert np.isfinite(z).all() and z.min() > 0 and z.max() < 200
+        # seed wrap rows: bottom rows exist and are not constant
+        assert len(np.unique(s[-8:])) > 16
+        acc = np.zeros_like(s)
+        for r in range(2):
+            tracer.shard_config(2, r)
+            tracer.frame_clear()
+            tracer.trace_cam(poses["cam"][1], w, h, float(poses["sec_current"][1]), 0)
+            t, _, _ = tracer.read_frame(want_z=False)
+            rows = ((np.arange(h) // 32) % 2) == r
+            acc[rows] = t[rows]
+        tracer.shard_config(1, 0)
+        assert int(api.checksum_ref(acc, w, h)) == int(a[1])
+
+
+def test_error_paths(tracer, default_level):
+    tracer.level_upload(default_level)
+    tracer.frame_config(64, 64)
+    cam = api.cam_spawn(default_level)
+    with pytest.raises(api.PwnError):
+        tracer.trace_cam(cam, 128, 64, 0.0, 0)        # larger than the frame
+    bad = cam.copy()
+    bad[3] = 0.5                                       # cam.x.w != 0
+    with pytest.raises(api.PwnError):
+        tracer.trace_cam(bad, 64, 64, 0.0, 0)
+    with pytest.raises(api.PwnError):
+        tracer.shard_config(2, 2)
+    tracer.shard_config(2, 0)
+    with pytest.raises(api.PwnError):
+        tracer.trace_cam(cam, 64, 64, 0.0, api.PWN_F_BLUR)   # blur needs the gathered frame
+    tracer.shard_config(1, 0)
+    cells = default_level.cells.copy()
+    cells[0, 0] = api.portal_code(40)
+    with pytest.raises(api.PwnError):
+        tracer.level_upload(api.Level(cells, default_level.portals))
+    tracer.level_upload(default_level)
