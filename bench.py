@@ -1,0 +1,355 @@
+#!/usr/bin/env python3
+"""bench.py -- headless bench harness of the pwnfps per-pixel portal ray cast on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Metric (BASELINE.json): primary Mrays/s (= pixels/s / 1e6; every pixel also traces two
+bounce segments) and frames/s.  A "step" is one pass of the hot path over one batch of
+synthetic input: the 600-frame scripted camera fly-through of the default level at 1920x1080
+(BASELINE configs[1]), blur pass on as the reference ships it (defs.h:9).
+
+  value      whole-job Mrays/s with frames left resident in HBM (device-timed, CUDA events
+             on the library's stream, max over ranks)
+  e2e        the same batch through the C ABI with HOST buffers: pwn_trace_poses() into pinned
+             host memory, device->host copy of every frame inside the timed region
+  roofline   the dominant kernel K1 (trace+shade+pack) against the FP32 issue roofline, plus
+             its framebuffer stores against the measured HBM peak
+  cpu_baseline  the reference's own OpenMP+SSE2 path (oracle/_ref, built from /root/reference
+             by oracle/make_ref.py) timed on this box's host cores on a bounded sample
+
+N > 1: one process per GPU (torchrun).  The path shards by camera pose with no data-path
+collective: rank r traces its own 600-frame slice of a 600*N-frame fly-through
+("scaling": "weak").  The row-band sharded single-frame mode with the bands gathered into
+GPU 0's frame is measured beside it and reported under "band_gather".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FRAMES = 600
+SIZE = (1920, 1080)
+SM_COUNT = 148
+FP32_LANES = 128
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "sm_max_mhz": float(d.get("sm_max_mhz", 1965.0)), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for i, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
+            if any(r[i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_time(lv, poses, idx, w, h, variant="libref.so", nthreads=0, repeat=1):
+    """The reference's own trace_screen_centred (oracle/_ref) on the host cores: seconds per frame list."""
+    import tempfile
+    from oracle import refbind
+    ref = refbind.Ref(variant)
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "level.txt")
+        lv.save_txt(p)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)          # level_load prints its portal table (level.h:220,225)
+        try:
+            ref.level_load(p)
+        finally:
+            os.dup2(saved, 1)
+            os.close(devnull)
+            os.close(saved)
+    nt = nthreads or ref.max_threads()
+    ref.time_frames(poses["cam"][idx[0]], float(poses["sec_current"][idx[0]]), w, h, nt, 1)   # warm-up frame discarded
+    secs = []
+    for i in idx:
+        secs.append(ref.time_frames(poses["cam"][i], float(poses["sec_current"][i]), w, h, nt, repeat) / repeat)
+    return secs, nt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on this box's cores."""
+    if rank != 0:
+        return
+    from pwnfps_b200 import api, levels
+    from oracle import refbind
+    w, h = SIZE
+    lv = levels.default_level()
+    poses = api.flythrough(lv, FRAMES)
+    idx = list(range(0, FRAMES, 100))          # bounded sample: 6 of the 600 poses per step
+    kind = "reference" if refbind.available("libref.so") else "port"
+    if kind != "reference":
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref.so not built (needs /root/reference at build time)"}))
+        return
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_time(lv, poses, idx[:1], w, h)
+    t0 = time.time()
+    per = []
+    nt = 1
+    for _ in range(args.steps):
+        secs, nt = cpu_reference_time(lv, poses, idx, w, h)
+        per.append(sum(secs))
+    total = sum(per)
+    mrays = args.steps * len(idx) * w * h / total / 1e6
+    line = {
+        "impl": "reference", "metric": "primary_mrays_per_s", "value": mrays, "unit": "Mrays/s",
+        "frames_per_s": args.steps * len(idx) / total,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "default level, 1920x1080, scripted 600-frame fly-through, blur on (BASELINE configs[1])",
+                   "sample": "%d of the 600 poses per step (every 100th)" % len(idx), "resolution": [w, h]},
+        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": nt, "kind": kind,
+                         "sample": "%d frames/step x %d steps of the fly-through at %dx%d, OpenMP threads = all host cores" % (len(idx), args.steps, w, h)},
+        "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from pwnfps_b200 import api, levels
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the trace has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    w, h = SIZE
+    peaks = load_peaks()
+    lv = levels.default_level()
+    tr = api.Tracer(local_rank)
+    tr.level_upload(lv)
+    tr.level_prepare_render()
+    tr.frame_config(w, h, want_ids=True)
+    all_poses = api.flythrough(lv, FRAMES * world)
+    poses = all_poses[rank * FRAMES:(rank + 1) * FRAMES].copy()
+    flags = 0 if args.no_blur else api.PWN_F_BLUR
+
+    stream = torch.cuda.ExternalStream(tr.stream_ptr(), device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def l2_flush():
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+
+    def step_device():
+        tr.trace_poses(poses, w, h, flags)
+
+    chunk = 50
+    pinned = api.PinnedBuffer((chunk, h, w), np.uint32)
+
+    def step_e2e():
+        for c in range(0, FRAMES, chunk):
+            tr.trace_poses(poses[c:c + chunk], w, h, flags, out=pinned.ptr)
+
+    def timed(fn, steps):
+        """per-step CUDA events on the launching stream; L2 flushed between steps outside them"""
+        ms = []
+        for _ in range(steps):
+            l2_flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            b.synchronize()
+            ms.append(a.elapsed_time(b))
+        return ms
+
+    # ---- value: frames stay in HBM -----------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    tr.sync()
+    barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = tr.launch_count()
+    wall0 = time.time()
+    ms = timed(step_device, args.steps)
+    barrier()
+    torch.cuda.synchronize()
+    wall = time.time() - wall0
+    launches = tr.launch_count() - launches0
+    clocks = sampler.summary()
+    dev_ms = allmax(sum(ms))
+    wall = allmax(wall)
+    pixels_job = float(args.steps) * FRAMES * w * h * world
+    value = pixels_job / (dev_ms * 1e-3) / 1e6
+
+    # ---- e2e: host buffers, copies inside the timed region ---------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    torch.cuda.synchronize()
+    e2e_steps = max(2, min(args.steps, 5))
+    t0 = time.time()
+    ms_e2e = timed(step_e2e, e2e_steps)
+    barrier()
+    torch.cuda.synchronize()
+    e2e_ms = allmax(sum(ms_e2e))
+    e2e_value = float(e2e_steps) * FRAMES * w * h * world / (e2e_ms * 1e-3) / 1e6
+
+    # ---- roofline of K1, live: per-launch events over the same 600 poses ---------------------
+    k1 = k2 = 0.0
+    for i in range(FRAMES):
+        tr.trace_cam(poses["cam"][i], w, h, float(poses["sec_current"][i]), flags)
+        a, b = tr.last_kernel_ms()
+        k1 += a
+        k2 += b
+    ops = 0
+    nsample = 0
+    for i in range(0, FRAMES, 10):          # the work model is counted, not timed: every 10th pose
+        tr.trace_cam(poses["cam"][i], w, h, float(poses["sec_current"][i]), api.PWN_F_IDS)
+        ops += tr.last_opcount()
+        nsample += 1
+    ops_per_frame = ops / nsample
+    k1_ms, k2_ms = k1 / FRAMES, k2 / FRAMES
+    sm_mhz = clocks["sm_mhz"] or peaks["sm_max_mhz"]
+    peak_issue = SM_COUNT * FP32_LANES * peaks["sm_max_mhz"] * 1e6 / 1e12          # T lane-op/s at max boost
+    achieved = ops_per_frame / (k1_ms * 1e-3) / 1e12
+    store_bytes = 8.0 * w * h                                                        # 4 B sbuf + 4 B zbuf per pixel
+    roofline = {
+        "bound": "fp32_issue", "kernel": "k_trace (K1: ray gen + walk + shade + bounces + pack)",
+        "achieved": achieved, "peak": peak_issue, "unit": "Tlaneop/s", "frac": achieved / peak_issue,
+        "peak_how": "148 SMs x 128 FP32 lanes x %.0f MHz max boost (1 lane-op per slot; FMA-counted peak is 2x)" % peaks["sm_max_mhz"],
+        "frac_at_measured_clock": achieved / (SM_COUNT * FP32_LANES * sm_mhz * 1e6 / 1e12),
+        "ops_per_pixel": ops_per_frame / (w * h), "k1_ms_per_launch": k1_ms, "k2_ms_per_launch": k2_ms,
+        "k1_share_of_step": k1 / (k1 + k2) if (k1 + k2) > 0 else None,
+        "traffic": None,
+        "hbm": {"bound": "hbm", "achieved": store_bytes / (k1_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": store_bytes / (k1_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["source"],
+                "algorithmic_bytes_per_pixel": 8},
+    }
+
+    # ---- CPU baseline: the reference's own code on this box's cores (rank 0, N == 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            from oracle import refbind
+            if refbind.available("libref.so"):
+                idx = [0, 150, 300, 450]
+                secs, nt = cpu_reference_time(lv, poses, idx, w, h, "libref.so" if flags else "libref_noblur.so")
+                secs1, _ = cpu_reference_time(lv, poses, idx[:2], w, h, "libref.so" if flags else "libref_noblur.so", nthreads=1)
+                cpu = {"value": len(idx) * w * h / sum(secs) / 1e6, "unit": "Mrays/s", "cores": nt, "kind": "reference",
+                       "sample": "4 of the 600 fly-through poses at %dx%d, warm-up frame discarded" % (w, h),
+                       "one_thread_value": 2 * w * h / sum(secs1) / 1e6}
+        except Exception as e:     # the baseline is a reported number, never a gate
+            cpu = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
+
+    band = None
+    if world > 1:
+        from pwnfps_b200 import shard
+        band = shard.bench_band_gather(tr, rank, world, local_rank, stream)
+
+    if rank == 0:
+        line = {
+            "metric": "primary_mrays_per_s", "value": value, "unit": "Mrays/s",
+            "frames_per_s": value * 1e6 / (w * h),
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "default level, 1920x1080, scripted 600-frame fly-through%s (BASELINE configs[1])"
+                       % (", blur on" if flags else ", blur off"),
+                       "resolution": [w, h], "frames_per_step": FRAMES, "sharding": "pose" if world > 1 else "none",
+                       "l2": "256 MiB flush between steps, outside the per-step events; frames are written once and never re-read"},
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": FRAMES * api.POSE_DTYPE.itemsize,
+                    "d2h_bytes_per_step": FRAMES * w * h * 4, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "how": "pwn_trace_poses into pinned host memory, %d-frame chunks; trace of frame i+1 overlaps the copy of frame i" % chunk},
+            "gpu_launches": int(launches), "wall_s": wall,
+        }
+        if band is not None:
+            line["band_gather"] = band
+        print(json.dumps(line))
+    pinned.free()
+    tr.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-blur", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

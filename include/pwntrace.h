@@ -225,6 +225,12 @@ int pwn_host_free(void *p);
 /* ---- measurement hooks (bench harness) ------------------------------------------------ */
 /* kernels launched by this context since creation (K1, K2, checksum, clear) */
 int pwn_launch_count(pwn_ctx *ctx, uint64_t *count);
+/*
+ * Algorithmic FP32 lane-ops of the last trace that ran with PWN_F_IDS: the work model of
+ * DESIGN.md (per-event constants counted from the reference source) summed over all pixels.
+ * This is the numerator of the FP32 roofline; it is counted, not timed.
+ */
+int pwn_last_opcount(pwn_ctx *ctx, uint64_t *ops);
 /* device time in ms of the last pwn_trace_frame's K1 and K2 launches (CUDA events on the context stream; syncs) */
 int pwn_last_kernel_ms(pwn_ctx *ctx, float *k1_ms, float *k2_ms);
 /* run n frames of the same pose back to back on the device, return total K1(+K2) event time in ms */

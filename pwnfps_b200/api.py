@@ -57,7 +57,7 @@ ABI_SYMBOLS = [
     "pwn_sync", "pwn_read_frame", "pwn_trace_screen", "pwn_trace_poses",
     "pwn_frame_device_ptrs", "pwn_frame_redirect", "pwn_frame_ipc_export",
     "pwn_frame_ipc_import", "pwn_frame_ipc_close", "pwn_host_alloc", "pwn_host_free",
-    "pwn_launch_count", "pwn_last_kernel_ms", "pwn_time_frames", "pwn_stream",
+    "pwn_launch_count", "pwn_last_opcount", "pwn_last_kernel_ms", "pwn_time_frames", "pwn_stream",
 ]
 
 
@@ -98,6 +98,7 @@ def lib():
     L.pwn_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.pwn_host_free.argtypes = [vp]
     L.pwn_launch_count.argtypes = [vp, u64p]
+    L.pwn_last_opcount.argtypes = [vp, u64p]
     L.pwn_last_kernel_ms.argtypes = [vp, C.POINTER(f), C.POINTER(f)]
     L.pwn_time_frames.argtypes = [vp, vp, i, i, f, u, i, C.POINTER(f)]
     L.pwn_stream.argtypes = [vp, u64p]
@@ -407,6 +408,11 @@ class Tracer:
         _check(self.L.pwn_launch_count(self.h, C.byref(c)))
         return c.value
 
+    def last_opcount(self):
+        c = C.c_uint64()
+        _check(self.L.pwn_last_opcount(self.h, C.byref(c)))
+        return c.value
+
     def last_kernel_ms(self):
         a, b = C.c_float(), C.c_float()
         _check(self.L.pwn_last_kernel_ms(self.h, C.byref(a), C.byref(b)))
@@ -417,6 +423,11 @@ class Tracer:
         t = C.c_float()
         _check(self.L.pwn_time_frames(self.h, cam.ctypes.data, dimx, dimy, float(sec_current), flags, n, C.byref(t)))
         return t.value
+
+    def stream_ptr(self):
+        s = C.c_uint64()
+        _check(self.L.pwn_stream(self.h, C.byref(s)))
+        return s.value
 
     def device_ptrs(self):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()

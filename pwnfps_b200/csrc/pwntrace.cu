@@ -80,6 +80,7 @@ struct pwn_ctx
 	float *r_zbuf = nullptr;
 	unsigned long long *d_sums = nullptr;
 	size_t sums_cap = 0;
+	unsigned long long *d_opcount = nullptr;
 
 	int nshards = 1, shard = 0;
 	unsigned long long launches = 0;
@@ -152,7 +153,7 @@ extern "C" int pwn_destroy(pwn_ctx *ctx)
 	cudaFree(ctx->d_rcp); cudaFree(ctx->d_rsqrt);
 	cudaFree(ctx->d_sph_pos); cudaFree(ctx->d_sph_col); cudaFree(ctx->d_sph_rr);
 	cudaFree(ctx->d_parts_off); cudaFree(ctx->d_parts_idx);
-	cudaFree(ctx->d_sums);
+	cudaFree(ctx->d_sums); cudaFree(ctx->d_opcount);
 	cudaEventDestroy(ctx->ev_k1a); cudaEventDestroy(ctx->ev_k1b); cudaEventDestroy(ctx->ev_k2b);
 	for(int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_done[i]); cudaEventDestroy(ctx->ev_copied[i]); }
 	cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->copy_stream);
@@ -447,6 +448,13 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 	P.sbuf = blur ? tsb : sb;
 	P.zbuf = ctx->r_zbuf ? ctx->r_zbuf : f.zbuf;
 	P.ids = (flags & PWN_F_IDS) ? ctx->d_ids : nullptr;
+	P.opcount = nullptr;
+	if(flags & PWN_F_IDS)
+	{
+		if(ctx->d_opcount == nullptr) CU(cudaMalloc(&ctx->d_opcount, sizeof(unsigned long long)));
+		CU(cudaMemsetAsync(ctx->d_opcount, 0, sizeof(unsigned long long), ctx->stream));
+		P.opcount = ctx->d_opcount;
+	}
 	P.reflect_blur = (flags & PWN_F_NO_REFLECT_BLUR) ? 0 : 1;
 
 	ctx->timed = ctx->timed_blur = false;
@@ -675,6 +683,18 @@ extern "C" int pwn_launch_count(pwn_ctx *ctx, uint64_t *count)
 {
 	if(ctx == nullptr || count == nullptr) return fail(PWN_E_ARG, "null pointer");
 	*count = ctx->launches;
+	return PWN_OK;
+}
+
+extern "C" int pwn_last_opcount(pwn_ctx *ctx, uint64_t *ops)
+{
+	CTX_ENTER(ctx);
+	if(ops == nullptr) return fail(PWN_E_ARG, "null pointer");
+	if(ctx->d_opcount == nullptr) return fail(PWN_E_STATE, "no PWN_F_IDS trace has run");
+	unsigned long long v = 0;
+	CU(cudaMemcpyAsync(&v, ctx->d_opcount, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	*ops = v;
 	return PWN_OK;
 }
 

@@ -83,7 +83,26 @@ struct TraceParams
 	uint32_t *sbuf;            // pre-blur or final frame (BGRA8)
 	float *zbuf;
 	pwn_ids *ids;              // [rwidth*rheight][3] or null
+	unsigned long long *opcount; // IDS builds: sum of algorithmic FP32 lane-ops (DESIGN.md "Work model")
 	int reflect_blur;
+};
+
+// Algorithmic FP32 lane-ops per event (counted from the reference source: mul, add,
+// cmp, abs, cvt, rcp, rsqrt = 1 each, live lanes only).  Only the IDS instantiation counts.
+enum : uint32_t
+{
+	W_PIXEL = 20,     // ray generation + pack            (screen.h:12-24, util.h:48-59)
+	W_SEGMENT = 40,   // normalise, signs, rcp, wdist     (trace.h:203-241)
+	W_ONE = 14,       // 1-high room step                 (trace.h:156-184,302-352)
+	W_TWO = 18,       // 2-high room step                 (trace.h:354-441)
+	W_RAMP = 30,      // ramp step                        (trace.h:443-505)
+	W_PORTAL = 12,    // portal crossing                  (trace.h:528-647)
+	W_SPH_TEST = 14,  // one sphere test                  (trace.h:259-273)
+	W_SPH_HIT = 20,   //   ... that becomes the nearest   (trace.h:276-292)
+	W_WALL = 9,       // trace_hit_wall                   (trace.h:108-150)
+	W_BOUNCE = 40,    // reflect + jitter + blend         (trace.h:12-37,77-93)
+	W_FLOOR = 42,     // wavy floor normal: 38 + 4 libm   (trace.h:39-56)
+	W_FOG = 13        // fog blend: 12 + expf             (trace.h:95-101)
 };
 
 // ---- host-CPU primitives, emulated ---------------------------------------------------
@@ -182,6 +201,7 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 	}
 
 	// screen.h:19-21 (uint32 wrap)
+	uint32_t ops = W_PIXEL;
 	uint32_t seed = (uint32_t)x + (uint32_t)y*(uint32_t)y*(uint32_t)(P.rwidth + 1);
 	seed *= seed*seed;
 	seed *= seed*seed;
@@ -199,6 +219,7 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 	for(int seg = 0; ; seg++)
 	{
 		// ================= trace.h:203-248: segment setup =================
+		if(IDS) ops += W_SEGMENT;
 		float rx, ry, rz;
 		{
 			const float d = __fadd_rn(__fadd_rn(__fmul_rn(irx, irx), __fmul_rn(irz, irz)), __fmul_rn(iry, iry));
@@ -279,6 +300,7 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 						// v_dot: (x + z) + (y + w), w lanes are 0 (pwn_parts_upload checks)
 						const float dist2 = __fadd_rn(__fadd_rn(__fmul_rn(sx, sx), __fmul_rn(sz, sz)), __fmul_rn(sy, sy));
 						const float dot = __fadd_rn(__fadd_rn(__fmul_rn(sx, rx), __fmul_rn(sz, rz)), __fmul_rn(sy, ry));
+						if(IDS) ops += W_SPH_TEST;
 						if(dot > 0.0f)
 						{
 							const float calcrad2 = __fsub_rn(dist2, __fmul_rn(dot, dot));
@@ -289,6 +311,7 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 								const float ad = __fadd_rn(sd, cdist);
 								if(aux.dist == -1.0f || ad < aux.dist)
 								{
+									if(IDS) ops += W_SPH_HIT;
 									aux.dist = ad;
 									aux.px = __fadd_rn(px, __fmul_rn(sd, rx));
 									aux.py = __fadd_rn(py, __fmul_rn(sd, ry));
@@ -318,6 +341,7 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 			{
 				// 1-high (trace.h:302-352) and 2-high (trace.h:354-441) rooms share the step
 				const bool two = cls >= CL_TWO;
+				if(IDS) ops += two ? W_TWO : W_ONE;
 				const bool fogc = (cls == CL_ONE_FOG) || (cls == CL_TWO_FOG);
 				const bool up2 = two && gy > 0;
 				if(up2) wy = __fadd_rn(wy, iay);   // ceiling one unit further (trace.h:357)
@@ -365,6 +389,7 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 			else if(cls >= CL_RAMP_GT && cls <= CL_RAMP_CARET)
 			{
 				// trace.h:443-505
+				if(IDS) ops += W_RAMP;
 				const float tilt = __fmul_rn(0.5f, (cls <= CL_RAMP_LT) ? rx : rz);
 				const bool minus = (cls == CL_RAMP_GT) || (cls == CL_RAMP_COMMA);
 				ry = minus ? __fsub_rn(ry, tilt) : __fadd_rn(ry, tilt);
@@ -411,6 +436,7 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 				const int rot = (int)(pr.z & 255u);
 				ldir = (ldir - rot) & 3;
 				nport++;
+				if(IDS) ops += W_PORTAL;
 				const float ccx = __fadd_rn((float)cx, 0.5f), ccz = __fadd_rn((float)cz, 0.5f);
 				if(rot == 1)
 				{
@@ -483,6 +509,7 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 		if(hit.kind == 0)
 		{
 			// trace_hit_wall, trace.h:108-154
+			if(IDS) ops += W_WALL;
 			float sb, sg, sr;
 			if(hit.surf == SF_CEIL) { sb = 30.0f; sg = 30.0f; sr = 0.0f; }
 			else if(hit.surf == SF_FLOOR) { sb = 1.0f; sg = 1.0f; sr = 1.0f; }
@@ -518,6 +545,7 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 			break;
 		}
 
+		if(IDS) ops += W_BOUNCE + (hit.ldir == PWN_FYN ? W_FLOOR : 0u) + (fog != 0.0f ? W_FOG : 0u);
 		float nrx = rx, nry = ry, nrz = rz;
 		float npx, npy, npz;
 		if(hit.kind == 1) { npx = aux.px; npy = aux.py; npz = aux.pz; }
@@ -612,6 +640,18 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 			ob = __fadd_rn(__fmul_rn(f, ob), g); og = __fadd_rn(__fmul_rn(f, og), g);
 			orr = __fadd_rn(__fmul_rn(f, orr), g); oa = __fadd_rn(__fmul_rn(f, oa), g);
 		}
+	}
+
+	if(IDS && P.opcount != nullptr)
+	{
+		unsigned long long tot = ops;
+		const unsigned m = __activemask();
+		for(int o = 16; o > 0; o >>= 1)
+		{
+			const unsigned long long v = __shfl_xor_sync(m, tot, o);
+			if(m & (1u << ((threadIdx.x & 31) ^ o))) tot += v;
+		}
+		if((threadIdx.x & 31) == (__ffs(m) - 1)) atomicAdd(P.opcount, tot);
 	}
 
 	// ---- col_ftoint (util.h:48-59): B | G<<8 | R<<16 | A<<24 ------------------------------
