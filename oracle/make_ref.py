@@ -15,6 +15,8 @@ Variants (all from ref_harness.c):
   libref_wide.so       build-time WIDENED copy (LV_DIM x LV_DIM int cells, PM_MAX
   libref_wide_ids.so   portals) for the levels that exceed 64x64 / 26 letters
   libref_strict.so     same sources, -O2 and no -ffast-math (diagnostic)
+  libref_shim.so       the reference host (defs.h util.h level.h) with the PRODUCT's drop-in
+  libref_shim_noblur.so  pwn_screen.h in place of trace.h + screen.h, linked to libpwntrace.so
 
 The patched copies live only in a temporary directory during the build and are
 deleted afterwards: no reference source text enters this repository.  Every
@@ -134,12 +136,12 @@ def widen(files):
     return out
 
 
-def cc(out_name, inc_dirs, defines, cflags):
+def cc(out_name, inc_dirs, defines, cflags, libs=()):
     cmd = ["gcc"] + cflags + ["-shared", "-fPIC"]
     for i in inc_dirs:
         cmd += ["-I", i]
     cmd += ["-D" + x for x in defines]
-    cmd += ["-o", os.path.join(OUT, out_name), HARNESS, "-lm"]
+    cmd += ["-o", os.path.join(OUT, out_name), HARNESS, "-lm"] + list(libs)
     subprocess.run(cmd, check=True)
 
 
@@ -163,6 +165,16 @@ def main():
         cc("libref.so", [REF], [], REF_CFLAGS)
         cc("libref_noblur.so", [REF], ["REF_NO_BLUR"], REF_CFLAGS)
         cc("libref_strict.so", [REF], ["REF_NO_BLUR"], STRICT_CFLAGS)
+
+        # the reference HOST (defs.h util.h level.h + this harness as main.c) with the product's
+        # drop-in shim in place of trace.h/screen.h, linked against libpwntrace.so
+        root = os.path.dirname(HERE)
+        pkg = os.path.join(root, "pwnfps_b200")
+        if os.path.isfile(os.path.join(pkg, "libpwntrace.so")):
+            shim_inc = [os.path.join(pkg, "host"), os.path.join(root, "include"), REF]
+            shim_lib = ["-L" + pkg, "-lpwntrace", "-Wl,-rpath,$ORIGIN/../../pwnfps_b200"]
+            cc("libref_shim.so", shim_inc, ["REF_SHIM"], REF_CFLAGS, shim_lib)
+            cc("libref_shim_noblur.so", shim_inc, ["REF_SHIM", "REF_NO_BLUR"], REF_CFLAGS, shim_lib)
 
         d_ids = os.path.join(tmp, "ids")
         os.makedirs(d_ids)

@@ -18,6 +18,8 @@
  *   -DREF_REFLECT=n    redefine REFLECT (segment-split timing)
  *   -DREF_IDS          the including TU is the build-time *instrumented* copy
  *                      made by oracle/make_ref.py (ORC_* hooks, see below)
+ *   -DREF_SHIM         the PRODUCT's drop-in shim (pwnfps_b200/host/pwn_screen.h) replaces
+ *                      trace.h + screen.h: the reference host driving libpwntrace.so
  *   -DREF_WIDE         the including TU is the build-time *widened* copy
  *                      (LV_DIM x LV_DIM grid, PM_MAX portals)
  *
@@ -112,8 +114,14 @@ static ref_ids *orc_ids = NULL;      /* [rwidth*rheight][3] */
 #endif
 
 #include "util.h"
+#ifdef REF_SHIM
+/* the reference host with trace.h + screen.h swapped for the drop-in shim:
+ * everything else -- defs.h, util.h, level.h and this harness -- is unchanged */
+#include "pwn_screen.h"
+#else
 #include "trace.h"
 #include "screen.h"
+#endif
 #include "level.h"
 
 /* ---------------------------------------------------------------------------- */
