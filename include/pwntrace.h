@@ -132,6 +132,21 @@ int pwn_math_tables_from_host(pwn_ctx *ctx);
 /* same dump without a context (host-only, no GPU needed); tables may be NULL to query bits */
 int pwn_host_math_probe(int *rcp_bits, int *rsqrt_bits, uint32_t *rcp_tab, size_t rcp_cap, uint32_t *rsqrt_tab, size_t rsqrt_cap);
 
+/*
+ * libm on the bounce-shading path: sinf/cosf/sincosf (trace.h:42-46) and expf (trace.h:97) come
+ * from the host's glibc in the reference.  The device restates glibc 2.39's algorithms bit for
+ * bit (csrc/pwn_libm.h) in both of the builds x86-64 glibc selects between at load time.
+ * pwn_host_libm_probe asks THIS host's libm which one it runs (*fma_build 1 = "_fma", 0 =
+ * "_sse2"; *exact = 0 if it is neither); pwn_math_tables_from_host applies the answer,
+ * pwn_libm_config overrides it.
+ */
+int pwn_host_libm_probe(int *fma_build, int *exact);
+int pwn_libm_config(pwn_ctx *ctx, int fma_build);
+/* test hook (host only, no GPU): the restatement itself over an array */
+void pwn_host_libm_eval(const float *in, float *s, float *c, float *e, size_t n, int fma_build);
+/* test hook: sin, cos, exp of n floats evaluated by the device functions K1 uses */
+int pwn_debug_libm(pwn_ctx *ctx, const float *in, float *sin_out, float *cos_out, float *exp_out, int n);
+
 /* ---- level: once per level (grid and portals are immutable after load, script.h:65-69) ---- */
 /*
  * Flattens the reference's level (defs.h:96-111) into the device layout:

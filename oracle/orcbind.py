@@ -46,6 +46,7 @@ class Oracle:
         lib.orc_kat_rcp.argtypes = [C.c_float]
         lib.orc_kat_rsqrt.restype = C.c_float
         lib.orc_kat_rsqrt.argtypes = [C.c_float]
+        lib.orc_kat_libm.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_size_t]
         self.dims = None
 
     def level_set(self, cells, portals):
@@ -110,6 +111,13 @@ class Oracle:
         zb = np.ascontiguousarray(zbuf, dtype=np.float32)
         self.lib.orc_blur(w, h, rwidth, y0, y1, out.ctypes.data, zb.ctypes.data, ts.ctypes.data, nthreads)
         return out
+
+    def libm(self, x):
+        """the host's glibc sinf, cosf, expf (what the reference calls, trace.h:42-46,97)"""
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+        s, c, e = np.empty_like(x), np.empty_like(x), np.empty_like(x)
+        self.lib.orc_kat_libm(x, s, c, e, x.size)
+        return s, c, e
 
     def randfs_seq(self, seed, n):
         s = C.c_uint32(seed)

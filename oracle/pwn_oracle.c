@@ -824,6 +824,11 @@ int orc_blur(int dimx, int dimy, int rwidth, int y0, int y1, uint32_t *sbuf, con
 }
 
 /* known-answer helpers */
+void orc_kat_libm(const float *in, float *s, float *c, float *e, size_t n)
+{
+	size_t i;
+	for(i = 0; i < n; i++) { s[i] = sinf(in[i]); c[i] = cosf(in[i]); e[i] = expf(in[i]); }
+}
 float orc_kat_randfs(uint32_t *seed) { return orc_randfs(seed); }
 uint32_t orc_kat_col_ftoint(const float *v4) { return orc_col_ftoint(v4); }
 float orc_kat_rcp(float x) { return cpu_rcp(x); }

@@ -52,6 +52,7 @@ _host = None
 ABI_SYMBOLS = [
     "pwn_abi_version", "pwn_last_error", "pwn_create", "pwn_destroy",
     "pwn_math_tables", "pwn_math_tables_from_host", "pwn_host_math_probe",
+    "pwn_host_libm_probe", "pwn_libm_config", "pwn_host_libm_eval", "pwn_debug_libm",
     "pwn_level_upload", "pwn_parts_upload", "pwn_frame_config", "pwn_frame_clear",
     "pwn_shard_config", "pwn_trace_frame", "pwn_blur_frame", "pwn_trace_cam", "pwn_ray_setup",
     "pwn_sync", "pwn_read_frame", "pwn_trace_screen", "pwn_trace_poses",
@@ -76,6 +77,11 @@ def lib():
     L.pwn_math_tables.argtypes = [vp, vp, i, vp, i]
     L.pwn_math_tables_from_host.argtypes = [vp]
     L.pwn_host_math_probe.argtypes = [C.POINTER(i), C.POINTER(i), vp, C.c_size_t, vp, C.c_size_t]
+    L.pwn_host_libm_probe.argtypes = [C.POINTER(i), C.POINTER(i)]
+    L.pwn_libm_config.argtypes = [vp, i]
+    L.pwn_host_libm_eval.argtypes = [vp, vp, vp, vp, C.c_size_t, i]
+    L.pwn_host_libm_eval.restype = None
+    L.pwn_debug_libm.argtypes = [vp, vp, vp, vp, vp, i]
     L.pwn_level_upload.argtypes = [vp, i, i, vp, i, vp]
     L.pwn_parts_upload.argtypes = [vp, i, vp]
     L.pwn_frame_config.argtypes = [vp, i, i, i]
@@ -279,6 +285,21 @@ def host_math_probe():
     return rb.value, sb.value, rt, st
 
 
+def host_libm_probe():
+    """(fma_build, exact): which glibc build of sinf/cosf/expf this host runs. No GPU needed."""
+    a, b = C.c_int(), C.c_int()
+    lib().pwn_host_libm_probe(C.byref(a), C.byref(b))
+    return a.value, bool(b.value)
+
+
+def host_libm_eval(x, fma_build):
+    """sin, cos, exp of x through the host build of csrc/pwn_libm.h (the device runs the same text)."""
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+    s, c, e = np.empty_like(x), np.empty_like(x), np.empty_like(x)
+    lib().pwn_host_libm_eval(x.ctypes.data, s.ctypes.data, c.ctypes.data, e.ctypes.data, x.size, int(fma_build))
+    return s, c, e
+
+
 class PinnedBuffer:
     """cudaHostAlloc'd memory viewed as a numpy array."""
 
@@ -312,8 +333,10 @@ class Tracer:
         if math_tables == "host":
             _check(self.L.pwn_math_tables_from_host(self.h))
         elif math_tables is not None:
-            rb, sb, rt, st = math_tables
+            rb, sb, rt, st = math_tables[:4]
             _check(self.L.pwn_math_tables(self.h, rt.ctypes.data, rb, st.ctypes.data, sb))
+            if len(math_tables) > 4:
+                self.libm_config(math_tables[4])
 
     def close(self):
         if self.h:
@@ -338,6 +361,15 @@ class Tracer:
         lv = lv or self.level
         sp = np.ascontiguousarray(lv.spheres, dtype=SPHERE_DTYPE)
         _check(self.L.pwn_parts_upload(self.h, len(sp), sp.ctypes.data if len(sp) else None))
+
+    def libm_config(self, fma_build):
+        _check(self.L.pwn_libm_config(self.h, int(fma_build)))
+
+    def debug_libm(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+        s, c, e = np.empty_like(x), np.empty_like(x), np.empty_like(x)
+        _check(self.L.pwn_debug_libm(self.h, x.ctypes.data, s.ctypes.data, c.ctypes.data, e.ctypes.data, x.size))
+        return s, c, e
 
     def frame_config(self, rwidth, rheight, want_ids=False):
         _check(self.L.pwn_frame_config(self.h, rwidth, rheight, 1 if want_ids else 0))

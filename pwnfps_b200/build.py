@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
 ]
-GCC_FLAGS = ["-O2", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wextra"]
+GCC_FLAGS = ["-O2", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wextra", "-Wno-unused-function"]
 
 
 def _newer(target, sources):
@@ -73,7 +73,7 @@ def build(force=False, verbose=False):
     os.makedirs(obj_dir, exist_ok=True)
     o_host = os.path.join(obj_dir, "pwn_hostmath.o")
     o_cu = os.path.join(obj_dir, "pwntrace.o")
-    subprocess.run([gcc] + GCC_FLAGS + ["-I", INC, "-c", os.path.join(CSRC, "pwn_hostmath.c"), "-o", o_host], check=True)
+    subprocess.run([gcc] + GCC_FLAGS + ["-I", INC, "-I", CSRC, "-c", os.path.join(CSRC, "pwn_hostmath.c"), "-o", o_host], check=True)
     r = subprocess.run([nvcc, "-ccbin", gxx] + NVCC_FLAGS + ["-I", INC, "-I", CSRC, "-c",
                         os.path.join(CSRC, "pwntrace.cu"), "-o", o_cu],
                        check=False, capture_output=True, text=True)

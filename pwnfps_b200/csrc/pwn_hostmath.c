@@ -18,7 +18,10 @@
 #include <string.h>
 #include <xmmintrin.h>
 
+#include <math.h>
+
 #include "pwntrace.h"
+#include "pwn_libm.h"
 
 static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
@@ -130,5 +133,56 @@ void pwn_ray_setup(const float cam[16], int dimx, int dimy, float rayb[4], float
 		rayb[i] = cam[8+i] + ((-xrat)*cam[0+i] + (-yrat)*cam[4+i]);
 		rdx[i] = xsrat*cam[0+i];
 		rdy[i] = ysrat*cam[4+i];
+	}
+}
+
+/*
+ * Which glibc build of sinf/cosf/expf is this host running (the "_fma" or the "_sse2" one, see
+ * pwn_libm.h)?  Asked of the host libm itself: first on the inputs where the two builds round
+ * differently (found by an exhaustive search over |x| < 2^20), then on a spread of 2^18 inputs
+ * over the ranges the trace produces.  *exact = 1 when every sample agrees with the chosen
+ * restatement, 0 when the host's libm is something else (parity of the bounce shading is then
+ * only as good as 1-2 ulp).
+ */
+int pwn_host_libm_probe(int *fma_build, int *exact)
+{
+	static const uint64_t tab[32] = PWN_EXP2F_TAB;
+	/* volatile: the compiler must not fold sinf(constant) with its own (correctly rounded) arithmetic */
+	static volatile uint32_t disc_sin[] = {0x4255b0a9u}, disc_cos[] = {0x418a3adbu}, disc_exp[] = {0xc27c65d9u};
+	int votes[2] = {0, 0}, v, ok = 1;
+	uint32_t i;
+	for(v = 0; v < 2; v++)
+	{
+		float x, s, c;
+		x = u2f(disc_sin[0]); pwn_sincosf(x, &s, &c, v); votes[v] += (f2u(s) == f2u(sinf(x)));
+		x = u2f(disc_cos[0]); pwn_sincosf(x, &s, &c, v); votes[v] += (f2u(c) == f2u(cosf(x)));
+		x = u2f(disc_exp[0]); votes[v] += (f2u(pwn_expf(x, tab, v)) == f2u(expf(x)));
+	}
+	v = votes[1] >= votes[0] ? 1 : 0;
+	if(votes[v] != 3) ok = 0;
+	/* a spread: multiplicative-hash walk over [0, 2^18) mapped to (-400, 400) and (-87, 0] */
+	for(i = 0; i < (1u << 18) && ok; i++)
+	{
+		const uint32_t h = i*2654435761u;
+		const float x = ((float)(h >> 8)/16777216.0f - 0.5f)*800.0f;
+		const float e = -((float)(h >> 8)/16777216.0f)*87.0f;
+		float s, c;
+		pwn_sincosf(x, &s, &c, v);
+		if(f2u(s) != f2u(sinf(x)) || f2u(c) != f2u(cosf(x)) || f2u(pwn_expf(e, tab, v)) != f2u(expf(e))) ok = 0;
+	}
+	if(fma_build) *fma_build = v;
+	if(exact) *exact = ok;
+	return PWN_OK;
+}
+
+/* test hook (host only): the restatement of pwn_libm.h over an array, build `fma_build` */
+void pwn_host_libm_eval(const float *in, float *s, float *c, float *e, size_t n, int fma_build)
+{
+	static const uint64_t tab[32] = PWN_EXP2F_TAB;
+	size_t i;
+	for(i = 0; i < n; i++)
+	{
+		pwn_sincosf(in[i], &s[i], &c[i], fma_build);
+		e[i] = pwn_expf(in[i], tab, fma_build);
 	}
 }

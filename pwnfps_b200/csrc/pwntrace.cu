@@ -83,6 +83,7 @@ struct pwn_ctx
 	unsigned long long *d_opcount = nullptr;
 
 	int nshards = 1, shard = 0;
+	int libm_fma = 1;          // glibc build the reference host would run: 1 "_fma", 0 "_sse2"
 	unsigned long long launches = 0;
 	bool timed = false;        // events of the last trace are valid
 	bool timed_blur = false;
@@ -190,7 +191,37 @@ extern "C" int pwn_math_tables_from_host(pwn_ctx *ctx)
 	std::vector<uint32_t> rt((size_t)1 << rb), st((size_t)2 << sb);
 	rc = pwn_host_math_probe(&rb, &sb, rt.data(), rt.size(), st.data(), st.size());
 	if(rc != PWN_OK) return fail(rc, "host math probe failed");
+	int fma_build = 1, exact = 0;
+	pwn_host_libm_probe(&fma_build, &exact);
+	ctx->libm_fma = fma_build;
 	return pwn_math_tables(ctx, rt.data(), rb, st.data(), sb);
+}
+
+extern "C" int pwn_libm_config(pwn_ctx *ctx, int fma_build)
+{
+	if(ctx == nullptr) return fail(PWN_E_ARG, "null context");
+	if(fma_build != 0 && fma_build != 1) return fail(PWN_E_ARG, "pwn_libm_config: variant %d", fma_build);
+	ctx->libm_fma = fma_build;
+	return PWN_OK;
+}
+
+extern "C" int pwn_debug_libm(pwn_ctx *ctx, const float *in, float *sin_out, float *cos_out, float *exp_out, int n)
+{
+	CTX_ENTER(ctx);
+	if(in == nullptr || sin_out == nullptr || cos_out == nullptr || exp_out == nullptr || n <= 0) return fail(PWN_E_ARG, "pwn_debug_libm: bad arguments");
+	float *d = nullptr;
+	CU(cudaMalloc(&d, sizeof(float)*4*(size_t)n));
+	CU(cudaMemcpyAsync(d, in, sizeof(float)*n, cudaMemcpyHostToDevice, ctx->stream));
+	if(ctx->libm_fma) k_libm_eval<true><<<(n + 255)/256, 256, 0, ctx->stream>>>(d, d + n, d + 2*(size_t)n, d + 3*(size_t)n, n);
+	else k_libm_eval<false><<<(n + 255)/256, 256, 0, ctx->stream>>>(d, d + n, d + 2*(size_t)n, d + 3*(size_t)n, n);
+	CU(cudaGetLastError());
+	ctx->launches++;
+	CU(cudaMemcpyAsync(sin_out, d + n, sizeof(float)*n, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(cos_out, d + 2*(size_t)n, sizeof(float)*n, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(exp_out, d + 3*(size_t)n, sizeof(float)*n, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	cudaFree(d);
+	return PWN_OK;
 }
 
 // ---- level ---------------------------------------------------------------------------------
@@ -226,7 +257,9 @@ extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells
 		return fail(PWN_E_ARG, "pwn_level_upload: bad arguments");
 	if(w > 16384 || h > 16384) return fail(PWN_E_LIMIT, "level %dx%d exceeds 16384 cells per axis", w, h);
 
-	std::vector<uint16_t> map((size_t)w*h);
+	// padded map: one border cell of CL_OOB all round, so the walk needs no bounds checks
+	const int wp = w + 2, hp = h + 2;
+	std::vector<uint16_t> map((size_t)wp*hp, (uint16_t)CL_OOB);
 	std::vector<PortalRec> recs;
 	for(int z = 0; z < h; z++)
 	for(int x = 0; x < w; x++)
@@ -246,28 +279,34 @@ extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells
 			int32_t xcell = c;
 			if(pm.x1 == x && pm.z1 == z) xcell = pm.c2;
 			else if(pm.x2 == x && pm.z2 == z) xcell = pm.c1;
-			r.peek = peek_of(xcell);
-			if(pm.x2 == -1) r.kind = PR_UNPAIRED;                    // trace.h:512-526
+			uint32_t kind, rot = 0;
+			int dcx = 0, dcz = 0, dx = 0, dz = 0;
+			if(pm.x2 == -1) kind = PR_UNPAIRED;                      // trace.h:512-526
 			else if(pm.x1 == x && pm.z1 == z)                        // 1 -> 2, trace.h:530-537
 			{
-				r.kind = PR_OK;
-				r.dcx = (int16_t)pm.x2; r.dcz = (int16_t)pm.z2;
-				r.dx = (int16_t)(pm.x2 - pm.x1); r.dz = (int16_t)(pm.z2 - pm.z1);
-				r.rot = (uint8_t)((-pm.rot12) & 3);
+				kind = PR_OK; dcx = pm.x2; dcz = pm.z2;
+				dx = pm.x2 - pm.x1; dz = pm.z2 - pm.z1;
+				rot = (uint32_t)((-pm.rot12) & 3);
 			}
 			else if(pm.x2 == x && pm.z2 == z)                        // 2 -> 1, trace.h:539-545
 			{
-				r.kind = PR_OK;
-				r.dcx = (int16_t)pm.x1; r.dcz = (int16_t)pm.z1;
-				r.dx = (int16_t)(-(pm.x2 - pm.x1)); r.dz = (int16_t)(-(pm.z2 - pm.z1));
-				r.rot = (uint8_t)(pm.rot12 & 3);
+				kind = PR_OK; dcx = pm.x1; dcz = pm.z1;
+				dx = -(pm.x2 - pm.x1); dz = -(pm.z2 - pm.z1);
+				rot = (uint32_t)(pm.rot12 & 3);
 			}
-			else r.kind = PR_STRAY;                                  // trace.h:547-559
+			else kind = PR_STRAY;                                    // trace.h:547-559
+			if(kind == PR_OK && (dcx < 0 || dcx >= w || dcz < 0 || dcz >= h))
+				return fail(PWN_E_ARG, "portal %d: end (%d,%d) lies outside the %dx%d grid", pi, dcx, dcz, w, h);
+			r.dci = (dcz + 1)*wp + dcx + 1;
+			r.dx = (float)dx; r.dz = (float)dz;
+			r.flags = rot | (kind << 8) | ((uint32_t)peek_of(xcell) << 16);
+			r.ccx = (float)dcx + 0.5f; r.ccz = (float)dcz + 0.5f;   // (cx + 0.5f), trace.h:584
+			r.dcx = dcx; r.dcz = dcz;
 			if(recs.size() >= 4096) return fail(PWN_E_LIMIT, "more than 4096 portal cells");
 			entry |= (uint32_t)recs.size() << 4;
 			recs.push_back(r);
 		}
-		map[(size_t)z*w + x] = (uint16_t)entry;
+		map[(size_t)(z + 1)*wp + x + 1] = (uint16_t)entry;
 	}
 	if(recs.empty()) { PortalRec r; memset(&r, 0, sizeof(r)); recs.push_back(r); }
 
@@ -282,6 +321,7 @@ extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells
 	ctx->w = w; ctx->h = h;
 	ctx->have_level = true;
 	ctx->nsph = 0;
+	cudaFree(ctx->d_parts_off); ctx->d_parts_off = nullptr;   // sized for the previous level
 	return PWN_OK;
 }
 
@@ -303,8 +343,8 @@ extern "C" int pwn_parts_upload(pwn_ctx *ctx, int nsph, const pwn_sphere *sph)
 	ctx->sph_w = sph[0].pos[3];
 
 	// level_prepare_render + level_part_add_bbox (level.h:1-39,64-81): objs[] order per cell
-	const int w = ctx->w, h = ctx->h;
-	const size_t ncell = (size_t)w*h;
+	const int w = ctx->w, h = ctx->h, wp = w + 2;
+	const size_t ncell = (size_t)wp*(h + 2);   // CSR over the padded map, indexed like the cell map
 	std::vector<uint32_t> off(ncell + 1, 0), idx, cur;
 	for(int pass = 0; pass < 2; pass++)
 	{
@@ -317,8 +357,9 @@ extern "C" int pwn_parts_upload(pwn_ctx *ctx, int nsph, const pwn_sphere *sph)
 			for(int x = cx1; x <= cx2; x++)
 			{
 				if(x < 0 || x >= w || z < 0 || z >= h) continue;   // the reference writes out of bounds here
-				if(pass == 0) off[(size_t)z*w + x + 1]++;
-				else idx[cur[(size_t)z*w + x]++] = (uint32_t)i;
+				const size_t ci = (size_t)(z + 1)*wp + x + 1;
+				if(pass == 0) off[ci + 1]++;
+				else idx[cur[ci]++] = (uint32_t)i;
 			}
 		}
 		if(pass == 0) for(size_t c = 0; c < ncell; c++) off[c+1] += off[c];
@@ -432,7 +473,7 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 
 	TraceParams P;
 	memset(&P, 0, sizeof(P));
-	P.lv.cellmap = ctx->d_cellmap; P.lv.portals = ctx->d_portals; P.lv.w = ctx->w; P.lv.h = ctx->h;
+	P.lv.cellmap = ctx->d_cellmap; P.lv.portals = ctx->d_portals; P.lv.w = ctx->w; P.lv.h = ctx->h; P.lv.wp = ctx->w + 2;
 	P.lv.rcp_tab = ctx->d_rcp; P.lv.rsqrt_tab = ctx->d_rsqrt;
 	P.lv.rcp_shift = 23 - ctx->rcp_bits; P.lv.rsqrt_shift = 23 - ctx->rsqrt_bits;
 	P.lv.sph_pos = ctx->d_sph_pos; P.lv.sph_col = ctx->d_sph_col; P.lv.sph_rr = ctx->d_sph_rr;
@@ -462,9 +503,18 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 	{
 		dim3 grid((dimx + 31)/32, P.nbands_local*4), block(256);
 		if(timing) CU(cudaEventRecord(ctx->ev_k1a, ctx->stream));
-		const bool sph = ctx->nsph > 0, ids = P.ids != nullptr;
-		if(sph) { if(ids) k_trace<true, true><<<grid, block, 0, ctx->stream>>>(P); else k_trace<true, false><<<grid, block, 0, ctx->stream>>>(P); }
-		else { if(ids) k_trace<false, true><<<grid, block, 0, ctx->stream>>>(P); else k_trace<false, false><<<grid, block, 0, ctx->stream>>>(P); }
+		const int variant = (ctx->nsph > 0 ? 4 : 0) | (P.ids != nullptr ? 2 : 0) | (ctx->libm_fma ? 1 : 0);
+		switch(variant)
+		{
+			case 0: k_trace<false, false, false><<<grid, block, 0, ctx->stream>>>(P); break;
+			case 1: k_trace<false, false, true><<<grid, block, 0, ctx->stream>>>(P); break;
+			case 2: k_trace<false, true, false><<<grid, block, 0, ctx->stream>>>(P); break;
+			case 3: k_trace<false, true, true><<<grid, block, 0, ctx->stream>>>(P); break;
+			case 4: k_trace<true, false, false><<<grid, block, 0, ctx->stream>>>(P); break;
+			case 5: k_trace<true, false, true><<<grid, block, 0, ctx->stream>>>(P); break;
+			case 6: k_trace<true, true, false><<<grid, block, 0, ctx->stream>>>(P); break;
+			default: k_trace<true, true, true><<<grid, block, 0, ctx->stream>>>(P); break;
+		}
 		CU(cudaGetLastError());
 		ctx->launches++;
 		if(timing) { CU(cudaEventRecord(ctx->ev_k1b, ctx->stream)); ctx->timed = true; }

@@ -11,6 +11,12 @@
 // the reference's source order with explicit round-to-nearest intrinsics
 // (__fmul_rn/__fadd_rn never contract into FMA); rcpps/rsqrtps come from the
 // host-dumped tables; float->int uses the reference's truncation / RN-even.
+//
+// The kernel is instruction-issue bound (profiles/), so the walk is written to
+// minimise instructions per cell step: the ray carries ONE linear index into a
+// padded cell map (no per-step bounds checks or cz*w+cx), the face code of the
+// last step is a select between two per-segment registers, and everything rare
+// (raised floors, leaving the grid, portals) sits behind one predicate.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,7 +39,8 @@ enum : uint32_t
 	CL_RAMP_LT = 7,    // '<'
 	CL_RAMP_COMMA = 8, // ','
 	CL_RAMP_CARET = 9, // '^'
-	CL_PORTAL = 10     // letter cell; bits 4..15 of the map entry index PortalRec
+	CL_PORTAL = 10,    // letter cell; bits 4..15 of the map entry index PortalRec
+	CL_OOB = 15        // the one-cell border around the map: the ray is leaving the grid
 };
 
 enum : uint32_t { PK_WALL = 0, PK_PASS = 1, PK_RAISED = 2 };   // what a 2-high room sees through a cell (trace.h:404-440)
@@ -41,33 +48,31 @@ enum : uint32_t { PR_OK = 0, PR_UNPAIRED = 1, PR_STRAY = 2 };  // trace.h:512-52
 
 // One record per portal CELL (not per letter): the crossing transform of
 // trace.h:528-647 for a ray standing on this cell, precomputed.  It is the
-// 3x4 affine map {R(rot*90deg) about (dcx+.5, dcz+.5), translate (dx,dz)} in
-// factored form -- the reference evaluates it in a fixed association order
+// 3x4 affine map {R(rot*90deg) about (ccx, ccz), translate (dx,dz)} in factored
+// form -- the reference evaluates it in a fixed association order
 // (trace.h:583-616) that a generic matrix product would not reproduce bit for bit.
 struct __align__(16) PortalRec
 {
-	int16_t dcx, dcz;   // destination portal cell
-	int16_t dx, dz;     // pos.xz += (dx,dz) before rotating
-	uint8_t rot;        // quarter turns 0..3
-	uint8_t kind;       // PR_*
-	uint8_t peek;       // PK_* of the cell in front of the other end (pm->c2 / c1)
-	uint8_t pad;
-	uint32_t pad2;
+	int32_t dci;        // destination portal cell, index into the padded map
+	float dx, dz;       // pos.xz += (dx,dz) before rotating        (trace.h:535-536,543-544)
+	uint32_t flags;     // rot | kind<<8 | peek<<16
+	float ccx, ccz;     // (float)dcx + 0.5f, (float)dcz + 0.5f     (trace.h:584-607)
+	int32_t dcx, dcz;   // destination cell coordinates (ids only)
 };
 
 struct LevelDev
 {
-	const uint16_t *cellmap;   // h*w entries: class | rec<<4
+	const uint16_t *cellmap;   // (h+2)*(w+2) entries: class | rec<<4, border = CL_OOB
 	const PortalRec *portals;
-	int w, h;
+	int w, h, wp;              // wp = w + 2: row stride of the padded map
 	const uint32_t *rcp_tab;   // 1<<rcp_bits
 	const uint32_t *rsqrt_tab; // 2<<rsqrt_bits
 	int rcp_shift, rsqrt_shift;   // 23 - bits
-	// spheres (pwn_parts_upload)
+	// spheres (pwn_parts_upload); CSR over the padded map
 	const float4 *sph_pos;     // x y z w
 	const float4 *sph_col;     // b g r a
 	const float2 *sph_rr;      // r, refl
-	const uint32_t *parts_off; // h*w+1
+	const uint32_t *parts_off; // (h+2)*(w+2)+1
 	const uint32_t *parts_idx;
 	int nsph;
 };
@@ -111,7 +116,7 @@ __device__ __forceinline__ float rcp_emul(const LevelDev &L, float x)
 {
 	uint32_t u = __float_as_uint(x);
 	uint32_t t = __ldg(&L.rcp_tab[(u & 0x7FFFFFu) >> L.rcp_shift]);
-	return __uint_as_float(t - (((u >> 23) - 127u) << 23));
+	return __uint_as_float(t - (u & 0x7F800000u) + 0x3F800000u);
 }
 
 // rsqrtps(x), x > 0 normal
@@ -143,24 +148,8 @@ __device__ __forceinline__ uint32_t pack_lane(float v)
 	return (uint32_t)min(max(q, 0), 255);
 }
 
-__device__ __forceinline__ uint16_t get_cell(const LevelDev &L, int cx, int cz)
-{
-	// util.h:151-158: out-of-range coordinates fold to index 0 on that axis
-	if((unsigned)cx >= (unsigned)L.w) cx = 0;
-	if((unsigned)cz >= (unsigned)L.h) cz = 0;
-	return __ldg(&L.cellmap[cz*L.w + cx]);
-}
-
 // surface colours, lanes b g r a (defs.h:17-19, trace.h:558)
 enum : int { SF_CEIL = 0, SF_FLOOR = 1, SF_WALL = 2, SF_STRAY = 3 };
-
-struct Hit
-{
-	int kind;        // 0 wall/floor/ceiling, 1 sphere, 2 exhausted
-	int ldir;
-	int surf;
-	float dist;      // value the reference stores to *dist
-};
 
 struct Aux   // nearest sphere so far (trace.h:196-200)
 {
@@ -170,35 +159,40 @@ struct Aux   // nearest sphere so far (trace.h:196-200)
 	float cb, cg, cr, ca;
 };
 
-template <bool SPH, bool IDS>
+template <bool SPH, bool IDS, bool LFMA>
 __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TraceParams P)
 {
 	const LevelDev &L = P.lv;
+	__shared__ float s_ray[3][8][32];
 
 	// ---- pixel of this thread: CTA = 32x8 pixels, warp = 8x4 ----------------------
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int x = blockIdx.x*32 + (warp & 3)*8 + (lane & 7);
-	const int lrow = blockIdx.y*8 + (warp >> 2)*4 + (lane >> 3);
-	// local row -> global row through the band interleave
-	const int y = ((lrow >> 5)*P.nshards + P.shard)*32 + (lrow & 31);
-	if(x >= P.dimx || y >= P.dimy) return;
-	const size_t pix = (size_t)y*P.rwidth + x;
+	const int tx = (warp & 3)*8 + (lane & 7), ty = (warp >> 2)*4 + (lane >> 3);
+	const int x = blockIdx.x*32 + tx;
+	const int lrow0 = blockIdx.y*8;
+	// local row -> global row through the band interleave (8 | 32: a CTA never straddles bands)
+	const int y0 = ((lrow0 >> 5)*P.nshards + P.shard)*32 + (lrow0 & 31);
+	const int y = y0 + ty;
 
-	// ---- screen.h:12-13,18: rayl = ((rayb + y*rdy) + cx*rdx) + rdx + ... + rdx ----
-	float irx, iry, irz;
+	// ---- screen.h:12-13,18: rayl = ((rayb + y*rdy) + cx*rdx) + rdx + ... + rdx --------
+	// The x+1 adds are sequential by definition; the CTA computes each of its 8 rows once
+	// (warp w = row w, lanes 0..2 = the three components) and shares them through smem.
+	if(lane < 3)
 	{
-		const float fy = (float)y, fcx = (float)(x & ~31);
-		irx = __fadd_rn(__fadd_rn(P.rayb[0], __fmul_rn(fy, P.rdy[0])), __fmul_rn(fcx, P.rdx[0]));
-		iry = __fadd_rn(__fadd_rn(P.rayb[1], __fmul_rn(fy, P.rdy[1])), __fmul_rn(fcx, P.rdx[1]));
-		irz = __fadd_rn(__fadd_rn(P.rayb[2], __fmul_rn(fy, P.rdy[2])), __fmul_rn(fcx, P.rdx[2]));
-		const int nadd = (x & 31) + 1;
-		for(int k = 0; k < nadd; k++)
+		const float fy = (float)(y0 + warp), fcx = (float)(blockIdx.x*32);
+		const float d = P.rdx[lane];
+		float v = __fadd_rn(__fadd_rn(P.rayb[lane], __fmul_rn(fy, P.rdy[lane])), __fmul_rn(fcx, d));
+		#pragma unroll
+		for(int k = 0; k < 32; k++)
 		{
-			irx = __fadd_rn(irx, P.rdx[0]);
-			iry = __fadd_rn(iry, P.rdx[1]);
-			irz = __fadd_rn(irz, P.rdx[2]);
+			v = __fadd_rn(v, d);
+			s_ray[lane][warp][k] = v;
 		}
 	}
+	__syncthreads();
+	if(x >= P.dimx || y >= P.dimy) return;
+	const size_t pix = (size_t)y*P.rwidth + x;
+	float irx = s_ray[0][ty][tx], iry = s_ray[1][ty][tx], irz = s_ray[2][ty][tx];
 
 	// screen.h:19-21 (uint32 wrap)
 	uint32_t ops = W_PIXEL;
@@ -215,6 +209,8 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 	float ob, og, orr, oa;   // colour coming back from the deepest segment
 	int depth = 0;           // bounce levels to unwind
 
+	const int W = L.w, H = L.h, WP = L.wp;
+
 	#pragma unroll 1
 	for(int seg = 0; ; seg++)
 	{
@@ -226,13 +222,13 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 			const float s = rsqrt_emul(L, d);
 			rx = __fmul_rn(irx, s); ry = __fmul_rn(iry, s); rz = __fmul_rn(irz, s);
 		}
-		int cx = __float2int_rz(fx), cz = __float2int_rz(fz);
+		int cx = __float2int_rz(fx), cz = __float2int_rz(fz);   // real cell coordinates (IDS builds keep them current)
 		const float EPS = 0.0000000000001f;
-		if(rx > -EPS && rx < EPS) rx = (rx < 0.0f ? -EPS : EPS);
-		if(ry > -EPS && ry < EPS) ry = (ry < 0.0f ? -EPS : EPS);
-		if(rz > -EPS && rz < EPS) rz = (rz < 0.0f ? -EPS : EPS);
+		if(fabsf(rx) < EPS) rx = (rx < 0.0f ? -EPS : EPS);
+		if(fabsf(ry) < EPS) ry = (ry < 0.0f ? -EPS : EPS);
+		if(fabsf(rz) < EPS) rz = (rz < 0.0f ? -EPS : EPS);
 		int gx = (irx < 0.0f ? -1 : 1), gz = (irz < 0.0f ? -1 : 1);
-		const int gy = (iry < 0.0f ? -1 : 1);
+		const bool up = !(iry < 0.0f);                          // gy > 0
 		float iax = rcp_emul(L, fabsf(rx)), iaz = rcp_emul(L, fabsf(rz));
 		const float iay = rcp_emul(L, fabsf(ry));
 		float px = fx, py = fy, pz = fz;
@@ -242,53 +238,54 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 		if(rz >= 0.0f) wz = __fsub_rn(1.0f, wz);
 		wx = __fmul_rn(wx, iax); wy = __fmul_rn(wy, iay); wz = __fmul_rn(wz, iaz);
 
-		uint32_t cell = get_cell(L, cx, cz);
+		// linear index into the padded map; a coordinate outside the grid looks up index 0 on
+		// that axis for good (util.h:151-158) and stops moving the index on that axis
+		int stepx = gx, stepz = gz*WP;
+		bool oob = false;
+		int ci;
+		{
+			int lx = cx, lz = cz;
+			if((unsigned)cx >= (unsigned)W) { lx = 0; stepx = 0; oob = true; }
+			if((unsigned)cz >= (unsigned)H) { lz = 0; stepz = 0; oob = true; }
+			ci = (lz + 1)*WP + lx + 1;
+		}
+		int ldx = (gx < 0 ? PWN_FXN : PWN_FXP), ldz = (gz < 0 ? PWN_FZN : PWN_FZP);
+		uint32_t cell = __ldg(&L.cellmap[ci]);
 		int ldir = PWN_FYN;
-		float cdist = 0.0f, fog = 0.0f, fogbeg = 0.0f;
+		float cdist = 0.0f, fog = 0.0f;
 		int nstep = 0, nport = 0;
 		Aux aux;
 		aux.dist = -1.0f; aux.refl = 0.25f;
 		aux.px = aux.py = aux.pz = 0.0f; aux.nx = aux.ny = aux.nz = 0.0f;
 		aux.cb = aux.cg = aux.cr = aux.ca = 1.0f;
 
-		Hit hit;
-		hit.kind = 2; hit.ldir = PWN_FYN; hit.surf = SF_WALL; hit.dist = 0.0f;
+		int hkind = 2, hsurf = SF_WALL;   // 0 wall/floor/ceiling, 1 sphere, 2 exhausted
+		float hdist = 0.0f;               // what the reference stores to *dist
 
-// trace.h:156-184
-#define PWN_THROUGH(GX, GY, GZ) do { \
-		float t_; \
-		if(wy < wx && wy < wz) { t_ = wy; ldir = ((GY) < 0 ? PWN_FYN : PWN_FYP); } \
-		else if(wx < wz) { t_ = wx; ldir = ((GX) < 0 ? PWN_FXN : PWN_FXP); } \
-		else { t_ = wz; ldir = ((GZ) < 0 ? PWN_FZN : PWN_FZP); } \
-		cdist = __fadd_rn(cdist, t_); \
-		px = __fadd_rn(__fmul_rn(t_, rx), px); \
-		py = __fadd_rn(__fmul_rn(t_, ry), py); \
-		pz = __fadd_rn(__fmul_rn(t_, rz), pz); } while(0)
 // the "sphere nearer than where we got to" exits (trace.h:313-319 and friends)
-#define PWN_SPHERE_EXIT(FOGC) \
+#define PWN_SPHERE_EXIT(FOGC, FOGBEG) \
 		if(SPH && aux.dist != -1.0f && cdist > aux.dist) { \
-			hit.kind = 1; hit.ldir = -1; hit.dist = aux.dist; \
-			if((FOGC) && aux.dist > fogbeg) fog = __fadd_rn(fog, __fsub_rn(aux.dist, fogbeg)); \
+			hkind = 1; ldir = -1; hdist = aux.dist; \
+			if((FOGC) && aux.dist > (FOGBEG)) fog = __fadd_rn(fog, __fsub_rn(aux.dist, (FOGBEG))); \
 			break; }
-#define PWN_WALL_EXIT(SURF) { hit.kind = 0; hit.ldir = ldir; hit.surf = (SURF); hit.dist = cdist; break; }
-// X/Z cell advance (trace.h:331-340)
-#define PWN_STEP_XZ() do { \
-		if(ldir == PWN_FXN || ldir == PWN_FXP) { \
-			wy = __fsub_rn(wy, wx); wz = __fsub_rn(wz, wx); wx = iax; cx += gx; \
-		} else { \
-			wy = __fsub_rn(wy, wz); wx = __fsub_rn(wx, wz); wz = iaz; cz += gz; } } while(0)
+#define PWN_WALL_EXIT(SURF) { hkind = 0; hsurf = (SURF); hdist = cdist; break; }
+// the ray stepped onto the border of the padded map: it left the grid along the axis of ldir
+#define PWN_LEFT_GRID() do { \
+		const int row_ = ci / WP, col_ = ci - row_*WP; \
+		if(ldir & 1) { ci = WP + col_; stepz = 0; } else { ci = row_*WP + 1; stepx = 0; } \
+		oob = true; \
+		cell = __ldg(&L.cellmap[ci]); } while(0)
 
 		// ================= trace.h:250-675: the walk =================
 		#pragma unroll 1
 		for(int maxsteps = 1000; maxsteps > 0; maxsteps--)
 		{
-			nstep++;
+			if(IDS) nstep++;
 
 			if(SPH)   // trace.h:252-296
 			{
-				if((unsigned)cx < (unsigned)L.w && (unsigned)cz < (unsigned)L.h)
+				if(!oob)
 				{
-					const int ci = cz*L.w + cx;
 					const uint32_t e = __ldg(&L.parts_off[ci + 1]);
 					for(uint32_t i = __ldg(&L.parts_off[ci]); i < e; i++)
 					{
@@ -337,56 +334,86 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 
 			const uint32_t cls = cell & 15u;
 
-			if(cls >= CL_ONE && cls <= CL_TWO_FOG)
+			if(cls - CL_ONE <= CL_TWO_FOG - CL_ONE)
 			{
 				// 1-high (trace.h:302-352) and 2-high (trace.h:354-441) rooms share the step
 				const bool two = cls >= CL_TWO;
+				const bool fogc = (cls == CL_ONE_FOG) | (cls == CL_TWO_FOG);
+				const bool up2 = two & up;
 				if(IDS) ops += two ? W_TWO : W_ONE;
-				const bool fogc = (cls == CL_ONE_FOG) || (cls == CL_TWO_FOG);
-				const bool up2 = two && gy > 0;
 				if(up2) wy = __fadd_rn(wy, iay);   // ceiling one unit further (trace.h:357)
-				if(fogc) fogbeg = cdist;
-				PWN_THROUGH(gx, gy, gz);
-				PWN_SPHERE_EXIT(fogc)
+				const float fogbeg = cdist;        // trace.h:309,359 (read only when fogc)
+
+				// trace_ray_through (trace.h:156-184)
+				const bool yfirst = (wy < wx) & (wy < wz);
+				const bool xfirst = wx < wz;
+				const float t = yfirst ? wy : (xfirst ? wx : wz);
+				cdist = __fadd_rn(cdist, t);
+				px = __fadd_rn(__fmul_rn(t, rx), px);
+				py = __fadd_rn(__fmul_rn(t, ry), py);
+				pz = __fadd_rn(__fmul_rn(t, rz), pz);
+
+				PWN_SPHERE_EXIT(fogc, fogbeg)
 				if(fogc) fog = __fadd_rn(fog, __fsub_rn(cdist, fogbeg));
-				if(ldir >= PWN_FYP) PWN_WALL_EXIT(gy > 0 ? SF_CEIL : SF_FLOOR)
-				PWN_STEP_XZ();
-				if(up2) wy = __fsub_rn(wy, iay);   // trace.h:392
-				cell = get_cell(L, cx, cz);
-				const uint32_t ncls = cell & 15u;
-				if(!two)
+				if(yfirst)
 				{
-					if(cls == CL_RAISED && (ncls == CL_TWO || ncls == CL_TWO_FOG))   // trace.h:343-351
-					{
-						py = __fadd_rn(py, 1.0f);
-						wy = (gy < 0) ? __fadd_rn(wy, iay) : __fsub_rn(wy, iay);
-					}
+					ldir = up ? PWN_FYP : PWN_FYN;
+					PWN_WALL_EXIT(up ? SF_CEIL : SF_FLOOR)
 				}
-				else
+				// X/Z cell advance (trace.h:331-340): all lanes minus t, the stepped lane reloads
 				{
-					if(ncls == CL_RAISED)   // trace.h:395-402
+					const float ax = __fsub_rn(wx, t), az = __fsub_rn(wz, t);
+					wy = __fsub_rn(wy, t);
+					wx = xfirst ? iax : ax;
+					wz = xfirst ? az : iaz;
+					ci += xfirst ? stepx : stepz;
+					ldir = xfirst ? ldx : ldz;
+					if(IDS) { if(xfirst) cx += gx; else cz += gz; }
+				}
+				if(up2) wy = __fsub_rn(wy, iay);   // trace.h:392
+				cell = __ldg(&L.cellmap[ci]);
+				uint32_t ncls = cell & 15u;
+
+				// everything below is rare: leaving the grid, raised floors, 2-high rooms seen
+				// from outside [0,1]
+				const bool yout = two & ((py < 0.0f) | (py > 1.0f));
+				if((ncls == CL_OOB) | (ncls == CL_RAISED) | (cls == CL_RAISED) | yout)
+				{
+					if(ncls == CL_OOB) { PWN_LEFT_GRID(); ncls = cell & 15u; }
+					if(!two)
 					{
-						py = __fsub_rn(py, 1.0f);
-						wy = (gy > 0) ? __fadd_rn(wy, iay) : __fsub_rn(wy, iay);
-					}
-					if(py < 0.0f || py > 1.0f)   // trace.h:404-440
-					{
-						uint32_t pk;
-						if(ncls == CL_PORTAL) pk = (__ldg(&reinterpret_cast<const uint32_t *>(L.portals)[(cell >> 4)*4 + 2]) >> 16) & 255u;
-						else pk = (ncls == CL_TWO || ncls == CL_TWO_FOG) ? PK_PASS : (ncls == CL_RAISED ? PK_RAISED : PK_WALL);
-						if(pk != PK_PASS)
+						if(cls == CL_RAISED && (ncls == CL_TWO || ncls == CL_TWO_FOG))   // trace.h:343-351
 						{
-							if(pk == PK_RAISED)   // revert (trace.h:422-431)
+							py = __fadd_rn(py, 1.0f);
+							wy = up ? __fsub_rn(wy, iay) : __fadd_rn(wy, iay);
+						}
+					}
+					else
+					{
+						if(ncls == CL_RAISED)   // trace.h:395-402
+						{
+							py = __fsub_rn(py, 1.0f);
+							wy = up ? __fadd_rn(wy, iay) : __fsub_rn(wy, iay);
+						}
+						if(py < 0.0f || py > 1.0f)   // trace.h:404-440
+						{
+							uint32_t pk;
+							if(ncls == CL_PORTAL) pk = oob ? PK_WALL : ((__ldg(&L.portals[cell >> 4].flags) >> 16) & 255u);
+							else pk = (ncls == CL_TWO || ncls == CL_TWO_FOG) ? PK_PASS : (ncls == CL_RAISED ? PK_RAISED : PK_WALL);
+							if(pk != PK_PASS)
 							{
-								py = __fadd_rn(py, 1.0f);
-								wy = (gy > 0) ? __fsub_rn(wy, iay) : __fadd_rn(wy, iay);
+								if(pk == PK_RAISED)   // revert (trace.h:422-431)
+								{
+									py = __fadd_rn(py, 1.0f);
+									wy = up ? __fsub_rn(wy, iay) : __fadd_rn(wy, iay);
+								}
+								PWN_WALL_EXIT(SF_WALL)
 							}
-							PWN_WALL_EXIT(SF_WALL)
 						}
 					}
 				}
 			}
-			else if(cls >= CL_RAMP_GT && cls <= CL_RAMP_CARET)
+			else if(cls - CL_RAMP_GT <= CL_RAMP_CARET - CL_RAMP_GT)
 			{
 				// trace.h:443-505
 				if(IDS) ops += W_RAMP;
@@ -396,48 +423,56 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 				wy = py;
 				if(ry >= 0.0f) wy = __fsub_rn(1.0f, wy);
 				wy = __fmul_rn(wy, __fdiv_rn(1.0f, (ry < 0.0f ? -ry : ry)));
-				PWN_SPHERE_EXIT(false)
-				PWN_THROUGH(gy, gy, gz);   // sic: gy stands in for gx (trace.h:470)
-				if(ldir >= PWN_FYP)
+				PWN_SPHERE_EXIT(false, 0.0f)
+				// trace_ray_through(..., gy, gy, gz): gy stands in for gx (trace.h:470); the face is
+				// then re-derived from the ray's own signs (trace.h:474,481,487)
+				const bool yfirst = (wy < wx) & (wy < wz);
+				const bool xfirst = wx < wz;
+				const float t = yfirst ? wy : (xfirst ? wx : wz);
+				cdist = __fadd_rn(cdist, t);
+				px = __fadd_rn(__fmul_rn(t, rx), px);
+				py = __fadd_rn(__fmul_rn(t, ry), py);
+				pz = __fadd_rn(__fmul_rn(t, rz), pz);
+				if(yfirst)
 				{
 					ldir = (ry < 0.0f ? PWN_FYN : PWN_FYP);
 					PWN_WALL_EXIT(ry >= 0.0f ? SF_CEIL : SF_FLOOR)
 				}
-				else if(ldir == PWN_FXN || ldir == PWN_FXP)
 				{
-					ldir = (rx < 0.0f ? PWN_FXN : PWN_FXP);
-					wy = __fsub_rn(wy, wx); wz = __fsub_rn(wz, wx); wx = iax; cx += gx;
-				}
-				else
-				{
-					ldir = (rz < 0.0f ? PWN_FZN : PWN_FZP);
-					wy = __fsub_rn(wy, wz); wx = __fsub_rn(wx, wz); wz = iaz; cz += gz;
+					const float ax = __fsub_rn(wx, t), az = __fsub_rn(wz, t);
+					wx = xfirst ? iax : ax;
+					wz = xfirst ? az : iaz;
+					ci += xfirst ? stepx : stepz;
+					ldir = xfirst ? (rx < 0.0f ? PWN_FXN : PWN_FXP) : (rz < 0.0f ? PWN_FZN : PWN_FZP);
+					if(IDS) { if(xfirst) cx += gx; else cz += gz; }
 				}
 				// un-tilt: the product is recomputed from the (unchanged) rx/rz, as the source does
 				ry = minus ? __fadd_rn(ry, tilt) : __fsub_rn(ry, tilt);
 				wy = py;
 				if(ry >= 0.0f) wy = __fsub_rn(1.0f, wy);
 				wy = __fmul_rn(wy, iay);
-				cell = get_cell(L, cx, cz);
+				cell = __ldg(&L.cellmap[ci]);
+				if((cell & 15u) == CL_OOB) PWN_LEFT_GRID();
 			}
 			else if(cls == CL_PORTAL)
 			{
 				// trace.h:508-650
-				const uint4 pr = __ldg(reinterpret_cast<const uint4 *>(&L.portals[cell >> 4]));
-				const uint32_t pkind = (pr.z >> 8) & 255u;
+				const uint4 pa = __ldg(reinterpret_cast<const uint4 *>(&L.portals[cell >> 4]));
+				uint32_t pkind = (pa.w >> 8) & 255u;
+				if(oob && pkind == PR_OK) pkind = PR_STRAY;   // outside the grid no end matches (trace.h:530,539)
 				if(pkind != PR_OK)
 				{
-					PWN_SPHERE_EXIT(false)
+					PWN_SPHERE_EXIT(false, 0.0f)
 					PWN_WALL_EXIT(pkind == PR_UNPAIRED ? SF_WALL : SF_STRAY)
 				}
-				cx = (int)(int16_t)(pr.x & 0xFFFFu); cz = (int)(int16_t)(pr.x >> 16);
-				px = __fadd_rn(px, (float)(int)(int16_t)(pr.y & 0xFFFFu));
-				pz = __fadd_rn(pz, (float)(int)(int16_t)(pr.y >> 16));
-				const int rot = (int)(pr.z & 255u);
+				const uint4 pb = __ldg(reinterpret_cast<const uint4 *>(&L.portals[cell >> 4]) + 1);
+				ci = (int)pa.x;
+				if(IDS) { cx = (int)pb.z; cz = (int)pb.w; ops += W_PORTAL; nport++; }
+				px = __fadd_rn(px, __uint_as_float(pa.y));
+				pz = __fadd_rn(pz, __uint_as_float(pa.z));
+				const int rot = (int)(pa.w & 255u);
 				ldir = (ldir - rot) & 3;
-				nport++;
-				if(IDS) ops += W_PORTAL;
-				const float ccx = __fadd_rn((float)cx, 0.5f), ccz = __fadd_rn((float)cz, 0.5f);
+				const float ccx = __uint_as_float(pb.x), ccz = __uint_as_float(pb.y);
 				if(rot == 1)
 				{
 					const float trx = px, trz = pz, trvx = rx;
@@ -445,8 +480,8 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 					pz = __fsub_rn(ccz, __fsub_rn(trx, ccx));
 					rx = rz; rz = -trvx;
 					const int tg = gx; gx = gz; gz = -tg;
-					float t = wx; wx = wz; wz = t;
-					t = iax; iax = iaz; iaz = t;
+					float tt = wx; wx = wz; wz = tt;
+					tt = iax; iax = iaz; iaz = tt;
 				}
 				else if(rot == 2)
 				{
@@ -462,43 +497,45 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 					pz = __fadd_rn(ccz, __fsub_rn(trx, ccx));
 					rx = -rz; rz = trvx;
 					const int tg = gx; gx = -gz; gz = tg;
-					float t = wx; wx = wz; wz = t;
-					t = iax; iax = iaz; iaz = t;
+					float tt = wx; wx = wz; wz = tt;
+					tt = iax; iax = iaz; iaz = tt;
 				}
+				stepx = gx; stepz = gz*WP;
+				ldx = (gx < 0 ? PWN_FXN : PWN_FXP); ldz = (gz < 0 ? PWN_FZN : PWN_FZP);
 				// step out of the destination portal cell (trace.h:624-647)
-				if(ldir == PWN_FXP) { cx++; px = __fadd_rn(px, 1.0f); }
-				else if(ldir == PWN_FZP) { cz++; pz = __fadd_rn(pz, 1.0f); }
-				else if(ldir == PWN_FXN) { cx--; px = __fsub_rn(px, 1.0f); }
-				else { cz--; pz = __fsub_rn(pz, 1.0f); }
-				cell = get_cell(L, cx, cz);
+				if(ldir == PWN_FXP) { ci++; px = __fadd_rn(px, 1.0f); if(IDS) cx++; }
+				else if(ldir == PWN_FZP) { ci += WP; pz = __fadd_rn(pz, 1.0f); if(IDS) cz++; }
+				else if(ldir == PWN_FXN) { ci--; px = __fsub_rn(px, 1.0f); if(IDS) cx--; }
+				else { ci -= WP; pz = __fsub_rn(pz, 1.0f); if(IDS) cz--; }
+				cell = __ldg(&L.cellmap[ci]);
+				if((cell & 15u) == CL_OOB) PWN_LEFT_GRID();
 			}
 			else
 			{
 				// solid (trace.h:651-664)
-				PWN_SPHERE_EXIT(false)
+				PWN_SPHERE_EXIT(false, 0.0f)
 				PWN_WALL_EXIT(ldir == PWN_FYP ? SF_CEIL : SF_WALL)
 			}
 
-			PWN_SPHERE_EXIT(false)   // trace.h:668-673
+			PWN_SPHERE_EXIT(false, 0.0f)   // trace.h:668-673
 		}
-#undef PWN_THROUGH
 #undef PWN_SPHERE_EXIT
 #undef PWN_WALL_EXIT
-#undef PWN_STEP_XZ
+#undef PWN_LEFT_GRID
 
 		if(IDS && P.ids != nullptr)
 		{
 			pwn_ids rec;
-			rec.cell = cz*L.w + cx; rec.ldir = (int16_t)hit.ldir; rec.kind = (int16_t)hit.kind;
+			rec.cell = cz*W + cx; rec.ldir = (int16_t)ldir; rec.kind = (int16_t)hkind;
 			rec.nstep = nstep; rec.nportal = nport;
 			P.ids[pix*3 + seg] = rec;
 		}
 
 		// zbuf keeps the PRIMARY distance: bounces save/zero/restore *dist (trace.h:86-87,103);
 		// an exhausted walk leaves it untouched (trace.h:677-678)
-		if(seg == 0 && hit.kind != 2) P.zbuf[pix] = hit.dist;
+		if(seg == 0 && hkind != 2) P.zbuf[pix] = hdist;
 
-		if(hit.kind == 2)
+		if(hkind == 2)
 		{
 			ob = rx; og = ry; orr = rz; oa = 0.0f;   // the ray comes back as the colour
 			break;
@@ -506,31 +543,23 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 
 		// ================= shading =================
 		float cb, cg, cr, ca, refl;
-		if(hit.kind == 0)
+		if(!SPH || hkind == 0)
 		{
 			// trace_hit_wall, trace.h:108-154
 			if(IDS) ops += W_WALL;
 			float sb, sg, sr;
-			if(hit.surf == SF_CEIL) { sb = 30.0f; sg = 30.0f; sr = 0.0f; }
-			else if(hit.surf == SF_FLOOR) { sb = 1.0f; sg = 1.0f; sr = 1.0f; }
-			else if(hit.surf == SF_WALL) { sb = 0.8f; sg = 0.8f; sr = 1.0f; }
+			if(hsurf == SF_CEIL) { sb = 30.0f; sg = 30.0f; sr = 0.0f; }
+			else if(hsurf == SF_FLOOR) { sb = 1.0f; sg = 1.0f; sr = 1.0f; }
+			else if(hsurf == SF_WALL) { sb = 0.8f; sg = 0.8f; sr = 1.0f; }
 			else { sb = 5.0f; sg = 0.0f; sr = 5.0f; }
 			cb = __fmul_rn(icb, sb); cg = __fmul_rn(icg, sg); cr = __fmul_rn(icr, sr); ca = __fmul_rn(ica, 0.0f);
-			float diffuse;
-			switch(hit.ldir)
-			{
-				default:
-				case PWN_FXP: diffuse = rx; break;
-				case PWN_FYP: diffuse = ry; break;
-				case PWN_FZP: diffuse = rz; break;
-				case PWN_FXN: diffuse = -rx; break;
-				case PWN_FYN: diffuse = -ry; break;
-				case PWN_FZN: diffuse = -rz; break;
-			}
+			// diffuse = +-ray[axis(ldir)]: FXP FZP FXN FZN FYP FYN = 0..5
+			float diffuse = (ldir >= PWN_FYP) ? ry : ((ldir & 1) ? rz : rx);
+			if(ldir == PWN_FXN || ldir == PWN_FZN || ldir == PWN_FYN) diffuse = -diffuse;
 			if(diffuse < 0.0f) diffuse = 0.0f;
 			diffuse = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, 0.1f), diffuse), 0.1f);
 			cb = __fmul_rn(cb, diffuse); cg = __fmul_rn(cg, diffuse); cr = __fmul_rn(cr, diffuse); ca = __fmul_rn(ca, diffuse);
-			refl = (hit.ldir == PWN_FYN ? 0.7f : 0.25f);
+			refl = (ldir == PWN_FYN ? 0.7f : 0.25f);
 		}
 		else
 		{
@@ -545,31 +574,31 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 			break;
 		}
 
-		if(IDS) ops += W_BOUNCE + (hit.ldir == PWN_FYN ? W_FLOOR : 0u) + (fog != 0.0f ? W_FOG : 0u);
+		if(IDS) ops += W_BOUNCE + (ldir == PWN_FYN ? W_FLOOR : 0u) + (fog != 0.0f ? W_FOG : 0u);
 		float nrx = rx, nry = ry, nrz = rz;
 		float npx, npy, npz;
-		if(hit.kind == 1) { npx = aux.px; npy = aux.py; npz = aux.pz; }
+		if(SPH && hkind == 1) { npx = aux.px; npy = aux.py; npz = aux.pz; }
 		else { npx = px; npy = py; npz = pz; }
 
-		if(hit.ldir == PWN_FXP) { nrx = -nrx; npx = __fsub_rn(npx, 0.001f); }
-		else if(hit.ldir == PWN_FXN) { nrx = -nrx; npx = __fadd_rn(npx, 0.001f); }
-		else if(hit.ldir == PWN_FZP) { nrz = -nrz; npz = __fsub_rn(npz, 0.001f); }
-		else if(hit.ldir == PWN_FZN) { nrz = -nrz; npz = __fadd_rn(npz, 0.001f); }
-		else if(hit.ldir == PWN_FYP) { nry = -nry; npy = __fsub_rn(npy, 0.001f); }
+		if(ldir == PWN_FXP) { nrx = -nrx; npx = __fsub_rn(npx, 0.001f); }
+		else if(ldir == PWN_FXN) { nrx = -nrx; npx = __fadd_rn(npx, 0.001f); }
+		else if(ldir == PWN_FZP) { nrz = -nrz; npz = __fsub_rn(npz, 0.001f); }
+		else if(ldir == PWN_FZN) { nrz = -nrz; npz = __fadd_rn(npz, 0.001f); }
+		else if(ldir == PWN_FYP) { nry = -nry; npy = __fsub_rn(npy, 0.001f); }
 		else
 		{
 			float nx, ny, nz;
-			if(hit.ldir == PWN_FYN)
+			if(!SPH || ldir == PWN_FYN)
 			{
 				// wavy floor normal (trace.h:39-46)
 				npy = __fsub_rn(npy, 0.001f);
 				const float HPI = __uint_as_float(0x3FC90FDBu);   // (float)M_PI*0.5f
 				const float TPI = __uint_as_float(0x40C90FDBu);   // (float)M_PI*2.0f
-				const float a0 = libm_sinf(__fmul_rn(HPI, npx));
-				const float a1 = libm_cosf(__fmul_rn(HPI, npz));
+				const float a0 = libm_sinf<LFMA>(__fmul_rn(HPI, npx));
+				const float a1 = libm_cosf<LFMA>(__fmul_rn(HPI, npz));
 				const float ang = __fmul_rn(TPI, __fadd_rn(__fadd_rn(a0, a1), P.sec_current));
 				float s, c;
-				libm_sincosf(ang, &s, &c);
+				libm_sincosf<LFMA>(ang, &s, &c);
 				// v_normalise(sin, 38, cos, 0): (x^2 + z^2) + (y^2 + 0)
 				const float nd = __fadd_rn(__fadd_rn(__fmul_rn(s, s), __fmul_rn(c, c)), __fmul_rn(38.0f, 38.0f));
 				const float ns = rsqrt_emul(L, nd);
@@ -597,9 +626,9 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 		{
 			nrx = __fadd_rn(nrx, __fmul_rn(randfs(seed), 0.03f));
 			nry = __fadd_rn(nry, __fmul_rn(randfs(seed), 0.03f));
-			randfs(seed);
+			seed = (seed * 25739u + 4u) & 0x7FFFFFFFu;
 			nrz = __fadd_rn(nrz, __fmul_rn(randfs(seed), 0.03f));
-			randfs(seed);
+			seed = (seed * 25739u + 4u) & 0x7FFFFFFFu;
 		}
 
 		if(seg == 0) { b0b = cb; b0g = cg; b0r = cr; b0a = ca; refl0 = refl; fog0 = fog; }
@@ -622,7 +651,7 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 		oa = __fadd_rn(__fmul_rn(refl1, oa), __fmul_rn(k, b1a));
 		if(fog1 != 0.0f)
 		{
-			const float f = libm_expf(__fmul_rn(-0.6f, fog1)), g = __fsub_rn(1.0f, f);
+			const float f = libm_expf<LFMA>(__fmul_rn(-0.6f, fog1)), g = __fsub_rn(1.0f, f);
 			ob = __fadd_rn(__fmul_rn(f, ob), g); og = __fadd_rn(__fmul_rn(f, og), g);
 			orr = __fadd_rn(__fmul_rn(f, orr), g); oa = __fadd_rn(__fmul_rn(f, oa), g);
 		}
@@ -636,7 +665,7 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 		oa = __fadd_rn(__fmul_rn(refl0, oa), __fmul_rn(k, b0a));
 		if(fog0 != 0.0f)
 		{
-			const float f = libm_expf(__fmul_rn(-0.6f, fog0)), g = __fsub_rn(1.0f, f);
+			const float f = libm_expf<LFMA>(__fmul_rn(-0.6f, fog0)), g = __fsub_rn(1.0f, f);
 			ob = __fadd_rn(__fmul_rn(f, ob), g); og = __fadd_rn(__fmul_rn(f, og), g);
 			orr = __fadd_rn(__fmul_rn(f, orr), g); oa = __fadd_rn(__fmul_rn(f, oa), g);
 		}

@@ -91,6 +91,21 @@ def mirror_hall(nrooms=17):
     return api.Level.from_grid(g, 26, sx, sz)
 
 
+def open_border():
+    """A 64x64 level whose rooms are open to the edge of the grid: rays leave the map and the
+    lookup folds to index 0 on that axis (get_cell, util.h:151-158), for good."""
+    g = _grid(64, 64)
+    g[0:8, 0:8] = ord(";")
+    g[2:5, 3:6] = ord("#")
+    g[5, 0:3] = ord("$")
+    g[56:64, 56:64] = ord(";")
+    g[58:61, 60:64] = ord("&")
+    g[0:8, 30:34] = ord(";")          # a corridor open to the top edge only
+    g[3, 8] = api.portal_code(0)      # links the two corner rooms
+    g[59, 55] = api.portal_code(0)
+    return api.Level.from_grid(g, 26, 4, 6)
+
+
 def maze(dim=128, seed=1, target_cells=10000, portal_pairs=1000):
     """C4/C5: a `dim` x `dim` level carved by a seeded randomised DFS to about `target_cells`
     walkable cells of mixed types, dead ends capped with portal cells paired by a seeded

@@ -83,3 +83,31 @@ def test_ray_setup_matches_oracle(oracle):
         want = oracle.ray_setup(cam.reshape(16), w, h)
         for g, x in zip(got, want):
             assert (g.view(np.uint32) == x.view(np.uint32)).all()
+
+
+def libm_samples():
+    rng = np.random.RandomState(11)
+    x = np.concatenate([rng.uniform(-130, 130, 400000), rng.uniform(-3e4, 3e4, 200000), rng.uniform(-0.9, 0.9, 100000),
+                        np.exp(rng.uniform(-12, 14, 100000)) * rng.choice([-1, 1], 100000), -rng.uniform(0, 100, 200000),
+                        [0.0, -0.0, 1e-6, -1e-6, 0.78539816, 120.0, -120.0, 119.99999, 2.0**20, -87.0, -88.5, -103.0, -104.5]]).astype(np.float32)
+    # plus the inputs on which the two glibc builds round differently
+    d = np.array([0x4255b0a9, 0x418a3adb, 0xc27c65d9], np.uint32).view(np.float32)
+    return np.concatenate([x, d])
+
+
+def test_libm_restatement_matches_host_glibc(oracle):
+    """csrc/pwn_libm.h (host build of the text the device runs) == this host's sinf/cosf/expf."""
+    fma_build, exact = api.host_libm_probe()
+    assert exact, "host libm is neither glibc build restated in pwn_libm.h"
+    x = libm_samples()
+    s, c, e = api.host_libm_eval(x, fma_build)
+    hs, hc, he = oracle.libm(x)
+    assert (s.view(np.uint32) == hs.view(np.uint32)).all()
+    assert (c.view(np.uint32) == hc.view(np.uint32)).all()
+    neg = (x <= 0) & (x >= -87)          # the trace passes -0.6*fog; below -88 every result blends to 1
+    assert (e.view(np.uint32)[neg] == he.view(np.uint32)[neg]).all()
+    tiny = x < -88
+    assert (e[tiny] < 1e-37).all() and (he[tiny] < 1e-37).all()
+    # the other build differs on the discriminating inputs, so the probe is meaningful
+    s2, c2, e2 = api.host_libm_eval(x[-3:], 1 - fma_build)
+    assert (s2.view(np.uint32)[0] != hs.view(np.uint32)[-3]) or (c2.view(np.uint32)[1] != hc.view(np.uint32)[-2])

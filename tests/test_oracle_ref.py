@@ -203,3 +203,26 @@ def test_maze_vs_wide_reference(oracle, refs):
         _, _, ids = oracle.trace_frame(pz["cam"], float(pz["sec_current"]), 64, 36, want_ids=True)
         crossed += int(ids["nportal"].sum())
     assert crossed > 0
+
+
+def test_open_border_level_vs_reference(oracle, refs, tmp_path):
+    """rays that leave the grid: get_cell folds the lookup to index 0 on that axis (util.h:151-158)"""
+    lv = levels.open_border()
+    ref, strict = refs("libref_ids.so"), refs("libref_strict.so")
+    p = str(tmp_path / "open.txt")
+    lv.save_txt(p)
+    ref.level_load(p)
+    strict.level_load(p)
+    oracle_set_level(oracle, lv)
+    outside = 0
+    for (x, z, yaw) in [(4.5, 6.5, 0.0), (4.5, 6.5, 1.6), (4.5, 6.5, 3.1), (4.5, 6.5, 4.7), (60.5, 62.5, 0.3),
+                        (60.5, 57.5, 2.0), (31.5, 2.5, 3.14), (31.5, 2.5, 0.5)]:
+        cam = np.eye(4, dtype=np.float32)
+        cam[3, :3] = (x, 0.5, z)
+        cam = api.mat4_roty(cam.reshape(16), yaw)
+        _compare(oracle, ref, strict, cam, 0.25, 320, 180)
+        _, _, ids = oracle.trace_frame(cam, 0.25, 320, 180, want_ids=True)
+        c = ids["cell"]
+        cx, cz = c % 64, c // 64
+        outside += int(((c < 0) | (cx >= 64)).sum())   # cz*64+cx with cx or cz outside the grid
+    assert outside > 1000

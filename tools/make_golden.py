@@ -42,7 +42,10 @@ def main():
                         cells=cells.astype(np.int16), portals=pm.astype(np.int32), spawn=np.array([sx, sz], np.int32))
 
     rb, sb, rt, st = api.host_math_probe()
-    np.savez_compressed(os.path.join(gold, "host_tables.npz"), rcp_bits=rb, rsqrt_bits=sb, rcp_tab=rt, rsqrt_tab=st)
+    fma_build, exact = api.host_libm_probe()
+    assert exact
+    np.savez_compressed(os.path.join(gold, "host_tables.npz"), rcp_bits=rb, rsqrt_bits=sb, rcp_tab=rt, rsqrt_tab=st,
+                        libm_fma=fma_build)
 
     # util.h known answers
     seeds = [1, 12345, 0x7FFFFFFF, 415135, 0xDEADBEEF]
