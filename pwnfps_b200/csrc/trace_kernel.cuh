@@ -238,17 +238,12 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 		if(rz >= 0.0f) wz = __fsub_rn(1.0f, wz);
 		wx = __fmul_rn(wx, iax); wy = __fmul_rn(wy, iay); wz = __fmul_rn(wz, iaz);
 
-		// linear index into the padded map; a coordinate outside the grid looks up index 0 on
-		// that axis for good (util.h:151-158) and stops moving the index on that axis
+		// linear index into the padded map.  While a coordinate is outside the grid the lookup
+		// folds to index 0 on that axis (util.h:151-158): `oob` rays take the rare path of every
+		// step, which tracks the real (cx, cz) and recomputes the index from them
 		int stepx = gx, stepz = gz*WP;
-		bool oob = false;
-		int ci;
-		{
-			int lx = cx, lz = cz;
-			if((unsigned)cx >= (unsigned)W) { lx = 0; stepx = 0; oob = true; }
-			if((unsigned)cz >= (unsigned)H) { lz = 0; stepz = 0; oob = true; }
-			ci = (lz + 1)*WP + lx + 1;
-		}
+		bool oob = ((unsigned)cx >= (unsigned)W) | ((unsigned)cz >= (unsigned)H);
+		int ci = (((unsigned)cz >= (unsigned)H ? 0 : cz) + 1)*WP + ((unsigned)cx >= (unsigned)W ? 0 : cx) + 1;
 		int ldx = (gx < 0 ? PWN_FXN : PWN_FXP), ldz = (gz < 0 ? PWN_FZN : PWN_FZP);
 		uint32_t cell = __ldg(&L.cellmap[ci]);
 		int ldir = PWN_FYN;
@@ -269,11 +264,14 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 			if((FOGC) && aux.dist > (FOGBEG)) fog = __fadd_rn(fog, __fsub_rn(aux.dist, (FOGBEG))); \
 			break; }
 #define PWN_WALL_EXIT(SURF) { hkind = 0; hsurf = (SURF); hdist = cdist; break; }
-// the ray stepped onto the border of the padded map: it left the grid along the axis of ldir
-#define PWN_LEFT_GRID() do { \
-		const int row_ = ci / WP, col_ = ci - row_*WP; \
-		if(ldir & 1) { ci = WP + col_; stepz = 0; } else { ci = row_*WP + 1; stepx = 0; } \
-		oob = true; \
+// The step just taken (along x if XSTEP) put the ray on the border of the padded map, or the ray
+// already was outside the grid: bring the real cell coordinates up to date and look the cell up
+// the way get_cell does (util.h:151-158).  Builds with IDS keep cx/cz current themselves.
+#define PWN_OOB_FIX(XSTEP) do { \
+		if(!oob) { const int row_ = ci / WP; if(!IDS) { cx = ci - row_*WP - 1; cz = row_ - 1; } } \
+		else if(!IDS) { if(XSTEP) cx += gx; else cz += gz; } \
+		oob = ((unsigned)cx >= (unsigned)W) | ((unsigned)cz >= (unsigned)H); \
+		ci = (((unsigned)cz >= (unsigned)H ? 0 : cz) + 1)*WP + ((unsigned)cx >= (unsigned)W ? 0 : cx) + 1; \
 		cell = __ldg(&L.cellmap[ci]); } while(0)
 
 		// ================= trace.h:250-675: the walk =================
@@ -377,9 +375,9 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 				// everything below is rare: leaving the grid, raised floors, 2-high rooms seen
 				// from outside [0,1]
 				const bool yout = two & ((py < 0.0f) | (py > 1.0f));
-				if((ncls == CL_OOB) | (ncls == CL_RAISED) | (cls == CL_RAISED) | yout)
+				if((ncls == CL_OOB) | oob | (ncls == CL_RAISED) | (cls == CL_RAISED) | yout)
 				{
-					if(ncls == CL_OOB) { PWN_LEFT_GRID(); ncls = cell & 15u; }
+					if((ncls == CL_OOB) | oob) { PWN_OOB_FIX(xfirst); ncls = cell & 15u; }
 					if(!two)
 					{
 						if(cls == CL_RAISED && (ncls == CL_TWO || ncls == CL_TWO_FOG))   // trace.h:343-351
@@ -452,7 +450,7 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 				if(ry >= 0.0f) wy = __fsub_rn(1.0f, wy);
 				wy = __fmul_rn(wy, iay);
 				cell = __ldg(&L.cellmap[ci]);
-				if((cell & 15u) == CL_OOB) PWN_LEFT_GRID();
+				if(((cell & 15u) == CL_OOB) | oob) PWN_OOB_FIX(xfirst);
 			}
 			else if(cls == CL_PORTAL)
 			{
@@ -508,7 +506,7 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 				else if(ldir == PWN_FXN) { ci--; px = __fsub_rn(px, 1.0f); if(IDS) cx--; }
 				else { ci -= WP; pz = __fsub_rn(pz, 1.0f); if(IDS) cz--; }
 				cell = __ldg(&L.cellmap[ci]);
-				if((cell & 15u) == CL_OOB) PWN_LEFT_GRID();
+				if((cell & 15u) == CL_OOB) PWN_OOB_FIX(false);   // a portal on the rim: never outside before the step
 			}
 			else
 			{
@@ -521,7 +519,7 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 		}
 #undef PWN_SPHERE_EXIT
 #undef PWN_WALL_EXIT
-#undef PWN_LEFT_GRID
+#undef PWN_OOB_FIX
 
 		if(IDS && P.ids != nullptr)
 		{

@@ -58,8 +58,10 @@ def check_frame(tracer, oracle, cam, sec, w, h, exact_rgb=None, label=""):
     # bounce segments: count mismatching pixels ("grazing", reported)
     bad = np.zeros((h, w), bool)
     for seg in (1, 2):
+        ran_d, ran_o = ids[..., seg]["kind"] != -1, io[..., seg]["kind"] != -1   # a segment that never ran keeps its cleared record
+        bad |= ran_d != ran_o
         for f in IDF:
-            bad |= ids[..., seg][f] != io[..., seg][f]
+            bad |= ran_o & (ids[..., seg][f] != io[..., seg][f])
     d = rgb_diff(s, so)
     frac_ok = (d <= RGB_LSB).mean()
     assert frac_ok >= RGB_FRACTION, (label, frac_ok)
