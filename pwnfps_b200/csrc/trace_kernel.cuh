@@ -372,9 +372,9 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 				cell = __ldg(&L.cellmap[ci]);
 				uint32_t ncls = cell & 15u;
 
-				// everything below is rare: leaving the grid, raised floors, 2-high rooms seen
-				// from outside [0,1]
-				const bool yout = two & ((py < 0.0f) | (py > 1.0f));
+				// everything below is rare: leaving the grid, raised floors, and a 2-high room left
+				// above y = 1 into anything but another 2-high room (the common case passes: trace.h:418-420)
+				const bool yout = two & ((py < 0.0f) | (py > 1.0f)) & (ncls - CL_TWO > CL_TWO_FOG - CL_TWO);
 				if((ncls == CL_OOB) | oob | (ncls == CL_RAISED) | (cls == CL_RAISED) | yout)
 				{
 					if((ncls == CL_OOB) | oob) { PWN_OOB_FIX(xfirst); ncls = cell & 15u; }
