@@ -110,28 +110,40 @@ def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), fr
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # single-GPU time of the same frames, for the speed-up
+    # single-GPU time of the same frames, for the speed-up; rank 0 keeps their checksums
     tr.shard_config(1, 0)
     one = 0.0
     for p in poses:
         tr.trace_cam(p["cam"], w, h, float(p["sec_current"]), 0)
         one += tr.last_kernel_ms()[0]
     one = allmax(one) / frames
+    want = tr.trace_poses(poses, w, h, 0, want_sums=True) if rank == 0 else None
 
     # fused: K1 stores into GPU 0's frame over NVLink
     tr.shard_config(world, rank)
     fused = None
     try:
         base = open_peer_frame(tr, rank, dist)
+        got = []
         for it in range(2):
             tot = 0.0
             for p in poses:
+                if rank == 0 and it == 1:
+                    tr.frame_clear()
+                    tr.sync()
                 dist.barrier()
                 tr.trace_cam(p["cam"], w, h, float(p["sec_current"]), 0)
                 tot += tr.last_kernel_ms()[0]
+                if it == 1:
+                    dist.barrier()      # every rank's stores have landed in GPU 0's frame
+                    if rank == 0:
+                        s0, _, _ = tr.read_frame(want_z=False)
+                        got.append(int(api.checksum_ref(s0, w, h)))
             fused = allmax(tot) / frames
         dist.barrier()
         close_peer_frame(tr, base)
+        if rank == 0:
+            out["fused_frames_equal_one_gpu"] = bool(got == [int(v) for v in want])
     except api.PwnError as e:
         out["fused_error"] = str(e)
         tr.frame_redirect(0, 0, 0)

@@ -213,6 +213,46 @@ def test_row_band_sharding_stitches(tracer, default_level):
     tracer.shard_config(1, 0)
 
 
+def test_redirected_shards_assemble_in_one_frame(tracer, default_level):
+    """The fused trace+gather path in one process: a second context traces its bands straight into
+    the first context's frame (pwn_frame_redirect; across GPUs the pointer comes from CUDA IPC)."""
+    a = tracer
+    b = api.Tracer(0)
+    try:
+        w, h = 640, 361
+        cam = api.mat4_roty(api.cam_spawn(default_level), 2.0)
+        for t in (a, b):
+            t.level_upload(default_level)
+            t.level_prepare_render()
+            t.frame_config(w, h)
+        a.shard_config(1, 0)
+        a.frame_clear()
+        a.trace_cam(cam, w, h, 0.0, 0)
+        full, zfull, _ = a.read_frame()
+        sb, zb, tsb = a.device_ptrs()
+        a.frame_clear()
+        a.shard_config(2, 0)
+        b.shard_config(2, 1)
+        b.frame_redirect(sb, zb, tsb)
+        a.trace_cam(cam, w, h, 0.0, 0)
+        b.trace_cam(cam, w, h, 0.0, 0)
+        a.sync()
+        b.sync()
+        got, zgot, _ = a.read_frame()
+        assert (got == full).all() and (zgot.view(np.uint32) == zfull.view(np.uint32)).all()
+        # the blur pass then runs on the assembled frame
+        a.blur_frame(w, h)
+        blurred, _, _ = a.read_frame(want_z=False)
+        a.shard_config(1, 0)
+        a.trace_cam(cam, w, h, 0.0, api.PWN_F_BLUR)
+        want, _, _ = a.read_frame(want_z=False)
+        assert (blurred == want).all()
+    finally:
+        b.frame_redirect(0, 0, 0)
+        b.close()
+        a.shard_config(1, 0)
+
+
 def test_trace_screen_centred_and_poses(tracer, oracle, default_level):
     """The drop-in call and the batched fly-through: host buffers, checksums."""
     tracer.level_upload(default_level)
