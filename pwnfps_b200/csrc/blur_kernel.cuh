@@ -2,8 +2,10 @@
 //
 // The reference walks each row left to right with ONE sequential LCG stream
 // (seed = cy*cy + 415135, 32 draws per 4-pixel group, screen.h:82,95-109).  The LCG
-// is affine mod 2^31, so a thread reaches its own draws by composing precomputed
-// power-of-two jumps; one thread = one output pixel, gathers go through L2.
+// is affine mod 2^31, so a thread reaches its own draws through a per-frame table of
+// the composed map for each 4-pixel group (built by pwn_frame_config); one thread =
+// one output pixel.  In pose batches the blur of frame i-1 rides in the trace launch
+// of frame i (k_trace<..., BLURP>): its scattered gathers hide under the trace's ALU work.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -15,14 +17,16 @@ struct BlurParams
 	const uint32_t *src;   // pre-blur frame (the reference's tsbuf copy, screen.h:75)
 	const float *zbuf;
 	uint32_t *dst;         // sbuf
+	const uint2 *jump;     // per 4-pixel group g: the affine map (A, C) that advances a row's stream by 32*g draws
 	int dimx, dimy, rwidth;
 	int y0, y1;            // rows to produce
 	float fstr;            // 0.002f * dimy (screen.h:86), computed on the host in float
 };
 
-// s -> A*s + C (mod 2^31) composed 2^k times: jumpA[k], jumpC[k]
-__constant__ uint32_t c_jumpA[32];
-__constant__ uint32_t c_jumpC[32];
+// s -> A*s + C (mod 2^31) composed n times for n = 0, 2, 4, 6 (a pixel's offset inside its group)
+// and for n = 6 (from one sample of a pixel to its next)
+__constant__ uint32_t c_jumpA[8];
+__constant__ uint32_t c_jumpC[8];
 
 __device__ __forceinline__ float blur_randfs(uint32_t &seed)
 {
@@ -38,31 +42,26 @@ __device__ __forceinline__ int cvtt(float v)
 	return __float2int_rz(v);
 }
 
-__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ BlurParams P)
+// one output pixel of the blur pass (screen.h:91-117)
+__device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 {
-	const int x = blockIdx.x*blockDim.x + threadIdx.x;
-	const int y = P.y0 + blockIdx.y;
-	if(x >= P.dimx || y >= P.y1) return;
 	const size_t pix = (size_t)y*P.rwidth + x;
-	const int cx = x & ~3, j = x & 3;
-	if(cx >= P.dimx - 3)
+	const int g = x >> 2, j = x & 3;
+	if((x & ~3) >= P.dimx - 3)
 	{
 		// the last dimx%4 pixels are not blurred (screen.h:88-91)
 		P.dst[pix] = P.src[pix];
 		return;
 	}
-
-	// jump the row's stream to draw number 32*(cx/4) + 2*j
-	uint32_t n = 8u*(uint32_t)cx + 2u*(uint32_t)j;
-	uint32_t a = 1u, c = 0u;
-	for(int k = 0; n != 0u; k++, n >>= 1)
-		if(n & 1u) { a = c_jumpA[k]*a; c = c_jumpA[k]*c + c_jumpC[k]; }
-	uint32_t seed = (a*((uint32_t)y*(uint32_t)y + 415135u) + c) & 0x7FFFFFFFu;
+	// the row's stream (seed = cy*cy + 415135, screen.h:82) advanced to draw 32*g + 2*j
+	const uint2 jg = __ldg(&P.jump[g]);
+	uint32_t seed = jg.x*((uint32_t)y*(uint32_t)y + 415135u) + jg.y;
+	seed = (c_jumpA[j]*seed + c_jumpC[j]) & 0x7FFFFFFFu;
 
 	const float z = __fsub_rn(P.zbuf[pix], 1.0f);
 	const float fbx = (float)x, fby = (float)y;
 	// six draws separate this pixel's pair in sample i from its pair in sample i+1
-	const uint32_t a6 = c_jumpA[1]*c_jumpA[2], c6 = c_jumpA[2]*c_jumpC[1] + c_jumpC[2];
+	const uint32_t a6 = c_jumpA[3], c6 = c_jumpC[3];
 	uint32_t s[4];
 	#pragma unroll
 	for(int i = 0; i < 4; i++)
@@ -78,6 +77,14 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ BlurParams
 	}
 	// pavgb: per byte (a+b+1)>>1 (screen.h:112-115)
 	P.dst[pix] = __vavgu4(__vavgu4(s[0], s[1]), __vavgu4(s[2], s[3]));
+}
+
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ BlurParams P)
+{
+	const int x = blockIdx.x*blockDim.x + threadIdx.x;
+	const int y = P.y0 + blockIdx.y;
+	if(x >= P.dimx || y >= P.y1) return;
+	blur_pixel(P, x, y);
 }
 
 // ---- order-independent frame checksum: sum_i mix64(i<<32 | word_i) mod 2^64 ----------

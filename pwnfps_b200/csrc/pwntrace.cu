@@ -15,7 +15,6 @@
 
 #include "pwntrace.h"
 #include "trace_kernel.cuh"
-#include "blur_kernel.cuh"
 
 using namespace pwn;
 
@@ -76,6 +75,7 @@ struct pwn_ctx
 	int rwidth = 0, rheight = 0;
 	FrameSet fs[2];
 	pwn_ids *d_ids = nullptr;
+	uint2 *d_jump = nullptr;   // per 4-pixel group: the LCG map composed 32*g times (K2)
 	uint32_t *r_sbuf = nullptr, *r_tsbuf = nullptr;   // redirect targets (peer frame) or null
 	float *r_zbuf = nullptr;
 	unsigned long long *d_sums = nullptr;
@@ -126,10 +126,14 @@ extern "C" int pwn_create(pwn_ctx **out, int device)
 		CU(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
 	}
 
-	// LCG jump table for K2: s -> A s + C composed 2^k times (util.h:1-6)
-	uint32_t ja[32], jc[32];
-	ja[0] = 25739u; jc[0] = 4u;
-	for(int k = 1; k < 32; k++) { ja[k] = ja[k-1]*ja[k-1]; jc[k] = ja[k-1]*jc[k-1] + jc[k-1]; }
+	// LCG jumps for K2 (util.h:1-6: s -> 25739 s + 4): entries 0..3 = the map composed 0, 2, 4, 6 times
+	uint32_t ja[8] = {1u, 0, 0, 0, 0, 0, 0, 0}, jc[8] = {0u, 0, 0, 0, 0, 0, 0, 0};
+	for(int k = 1; k < 4; k++)
+	{
+		uint32_t a = ja[k-1], c = jc[k-1];
+		for(int r = 0; r < 2; r++) { c = 25739u*c + 4u; a = 25739u*a; }
+		ja[k] = a; jc[k] = c;
+	}
 	CU(cudaMemcpyToSymbol(c_jumpA, ja, sizeof(ja)));
 	CU(cudaMemcpyToSymbol(c_jumpC, jc, sizeof(jc)));
 
@@ -141,6 +145,7 @@ static void free_frames(pwn_ctx *ctx)
 {
 	for(int i = 0; i < 2; i++) { cudaFree(ctx->fs[i].base); ctx->fs[i] = FrameSet(); }
 	cudaFree(ctx->d_ids); ctx->d_ids = nullptr;
+	cudaFree(ctx->d_jump); ctx->d_jump = nullptr;
 	ctx->rwidth = ctx->rheight = 0;
 }
 
@@ -424,6 +429,15 @@ extern "C" int pwn_frame_config(pwn_ctx *ctx, int rwidth, int rheight, int want_
 			f.zbuf = (float *)((char *)f.base + f.off_zbuf);
 			CU(cudaMemset(f.base, 0, f.bytes));
 		}
+		// the blur's stream position of every 4-pixel group: 32 draws per group (screen.h:95-109)
+		const int ngroups = rwidth/4 + 1;
+		std::vector<uint2> jt(ngroups);
+		uint32_t a32 = 1u, c32 = 0u;
+		for(int r = 0; r < 32; r++) { c32 = 25739u*c32 + 4u; a32 = 25739u*a32; }
+		uint32_t a = 1u, c = 0u;
+		for(int g = 0; g < ngroups; g++) { jt[g] = make_uint2(a, c); c = a32*c + c32; a = a32*a; }
+		CU(cudaMalloc(&ctx->d_jump, ngroups*sizeof(uint2)));
+		CU(cudaMemcpy(ctx->d_jump, jt.data(), ngroups*sizeof(uint2), cudaMemcpyHostToDevice));
 		ctx->rwidth = rwidth; ctx->rheight = rheight;
 	}
 	if(want_ids && ctx->d_ids == nullptr)
@@ -453,8 +467,36 @@ extern "C" int pwn_shard_config(pwn_ctx *ctx, int nshards, int shard)
 }
 
 // ---- the hot path ----------------------------------------------------------------------------------
+static BlurParams blur_params(pwn_ctx *ctx, const uint32_t *src, const float *z, uint32_t *dst, int dimx, int dimy)
+{
+	BlurParams B;
+	B.src = src; B.zbuf = z; B.dst = dst; B.jump = ctx->d_jump;
+	B.dimx = dimx; B.dimy = dimy; B.rwidth = ctx->rwidth; B.y0 = 0; B.y1 = dimy;
+	B.fstr = 0.002f * (float)dimy;   // screen.h:86
+	return B;
+}
+
+static int launch_blur(pwn_ctx *ctx, const BlurParams &B)
+{
+	dim3 grid((B.dimx + 255)/256, B.dimy), block(256);
+	k_blur<<<grid, block, 0, ctx->stream>>>(B);
+	CU(cudaGetLastError());
+	ctx->launches++;
+	return PWN_OK;
+}
+
+template <bool SPH, bool LFMA>
+static void launch_k1(const TraceParams &P, dim3 grid, cudaStream_t st, bool ids, bool blurp)
+{
+	if(ids) k_trace<SPH, true, LFMA, false><<<grid, 256, 0, st>>>(P);
+	else if(blurp) k_trace<SPH, false, LFMA, true><<<grid, 256, 0, st>>>(P);
+	else k_trace<SPH, false, LFMA, false><<<grid, 256, 0, st>>>(P);
+}
+
+// K1 for one frame into frame set f (+ the blur of `prev`'s frame riding along, pose batches),
+// then, for a single blurred frame, K2
 static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], const float rayb[4], const float rdx[4], const float rdy[4],
-	int dimx, int dimy, float sec, unsigned flags, bool timing)
+	int dimx, int dimy, float sec, unsigned flags, bool timing, const FrameSet *prev = nullptr, bool defer_blur = false)
 {
 	if(!ctx->have_level) return fail(PWN_E_STATE, "trace before pwn_level_upload");
 	if(!ctx->have_tables) return fail(PWN_E_STATE, "trace before pwn_math_tables");
@@ -497,38 +539,25 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 		P.opcount = ctx->d_opcount;
 	}
 	P.reflect_blur = (flags & PWN_F_NO_REFLECT_BLUR) ? 0 : 1;
+	const bool blurp = blur && prev != nullptr && P.ids == nullptr;
+	if(blurp) P.prev = blur_params(ctx, prev->tsbuf, prev->zbuf, prev->sbuf, dimx, dimy);
 
 	ctx->timed = ctx->timed_blur = false;
 	if(P.nbands_local > 0)
 	{
-		dim3 grid((dimx + 31)/32, P.nbands_local*4), block(256);
+		dim3 grid((dimx + 31)/32, P.nbands_local*4);
 		if(timing) CU(cudaEventRecord(ctx->ev_k1a, ctx->stream));
-		const int variant = (ctx->nsph > 0 ? 4 : 0) | (P.ids != nullptr ? 2 : 0) | (ctx->libm_fma ? 1 : 0);
-		switch(variant)
-		{
-			case 0: k_trace<false, false, false><<<grid, block, 0, ctx->stream>>>(P); break;
-			case 1: k_trace<false, false, true><<<grid, block, 0, ctx->stream>>>(P); break;
-			case 2: k_trace<false, true, false><<<grid, block, 0, ctx->stream>>>(P); break;
-			case 3: k_trace<false, true, true><<<grid, block, 0, ctx->stream>>>(P); break;
-			case 4: k_trace<true, false, false><<<grid, block, 0, ctx->stream>>>(P); break;
-			case 5: k_trace<true, false, true><<<grid, block, 0, ctx->stream>>>(P); break;
-			case 6: k_trace<true, true, false><<<grid, block, 0, ctx->stream>>>(P); break;
-			default: k_trace<true, true, true><<<grid, block, 0, ctx->stream>>>(P); break;
-		}
+		const bool ids = P.ids != nullptr;
+		if(ctx->nsph > 0) { if(ctx->libm_fma) launch_k1<true, true>(P, grid, ctx->stream, ids, blurp); else launch_k1<true, false>(P, grid, ctx->stream, ids, blurp); }
+		else { if(ctx->libm_fma) launch_k1<false, true>(P, grid, ctx->stream, ids, blurp); else launch_k1<false, false>(P, grid, ctx->stream, ids, blurp); }
 		CU(cudaGetLastError());
 		ctx->launches++;
 		if(timing) { CU(cudaEventRecord(ctx->ev_k1b, ctx->stream)); ctx->timed = true; }
 	}
-	if(blur)
+	if(blur && !defer_blur)
 	{
-		BlurParams B;
-		B.src = tsb; B.zbuf = P.zbuf; B.dst = sb;
-		B.dimx = dimx; B.dimy = dimy; B.rwidth = ctx->rwidth; B.y0 = 0; B.y1 = dimy;
-		B.fstr = 0.002f * (float)dimy;
-		dim3 grid((dimx + 255)/256, dimy), block(256);
-		k_blur<<<grid, block, 0, ctx->stream>>>(B);
-		CU(cudaGetLastError());
-		ctx->launches++;
+		int rc = launch_blur(ctx, blur_params(ctx, tsb, P.zbuf, sb, dimx, dimy));
+		if(rc != PWN_OK) return rc;
 		if(timing) { CU(cudaEventRecord(ctx->ev_k2b, ctx->stream)); ctx->timed_blur = true; }
 	}
 	return PWN_OK;
@@ -550,14 +579,8 @@ extern "C" int pwn_blur_frame(pwn_ctx *ctx, int dimx, int dimy)
 	const FrameSet &f = ctx->fs[0];
 	// the traced (pre-blur) frame is in sbuf: it becomes the gather source, as memcpy(tsbuf, sbuf) does (screen.h:75)
 	CU(cudaMemcpyAsync(f.tsbuf, f.sbuf, (size_t)ctx->rwidth*ctx->rheight*4, cudaMemcpyDeviceToDevice, ctx->stream));
-	BlurParams B;
-	B.src = f.tsbuf; B.zbuf = f.zbuf; B.dst = f.sbuf;
-	B.dimx = dimx; B.dimy = dimy; B.rwidth = ctx->rwidth; B.y0 = 0; B.y1 = dimy;
-	B.fstr = 0.002f * (float)dimy;
-	dim3 grid((dimx + 255)/256, dimy), block(256);
-	k_blur<<<grid, block, 0, ctx->stream>>>(B);
-	CU(cudaGetLastError());
-	ctx->launches++;
+	int rc = launch_blur(ctx, blur_params(ctx, f.tsbuf, f.zbuf, f.sbuf, dimx, dimy));
+	if(rc != PWN_OK) return rc;
 	return PWN_OK;
 }
 
@@ -630,18 +653,15 @@ extern "C" int pwn_trace_poses(pwn_ctx *ctx, int n, const pwn_pose *poses, int d
 		}
 		CU(cudaMemsetAsync(ctx->d_sums, 0, (size_t)n*sizeof(unsigned long long), ctx->stream));
 	}
-	for(int i = 0; i < n; i++)
-	{
-		const int s = i & 1;
-		float rayb[4], rdx[4], rdy[4];
-		pwn_ray_setup(poses[i].cam, dimx, dimy, rayb, rdx, rdy);
-		// frame set s is free again once the copy of pose i-2 has drained
-		if(sbuf_host != nullptr && i >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[s], 0));
-		int rc = launch_trace(ctx, ctx->fs[s], poses[i].cam + 12, rayb, rdx, rdy, dimx, dimy, poses[i].sec_current, flags, false);
-		if(rc != PWN_OK) return rc;
+	// Blurred batches are software-pipelined across frames: launch i traces pose i into set i&1
+	// and, in the same kernel, blurs frame i-1 in the other set; a plain K2 finishes the last
+	// frame.  Frame j is final (and is checksummed / copied out) after launch j+1.
+	const bool pipelined = (flags & PWN_F_BLUR) != 0 && ctx->nshards == 1 && n > 1;
+	auto finish = [&](int j) -> int {
+		const int s = j & 1;
 		if(sums != nullptr)
 		{
-			k_checksum<<<296, 256, 0, ctx->stream>>>(ctx->fs[s].sbuf, dimx, dimy, ctx->rwidth, ctx->d_sums + i);
+			k_checksum<<<296, 256, 0, ctx->stream>>>(ctx->fs[s].sbuf, dimx, dimy, ctx->rwidth, ctx->d_sums + j);
 			CU(cudaGetLastError());
 			ctx->launches++;
 		}
@@ -649,9 +669,38 @@ extern "C" int pwn_trace_poses(pwn_ctx *ctx, int n, const pwn_pose *poses, int d
 		{
 			CU(cudaEventRecord(ctx->ev_done[s], ctx->stream));
 			CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[s], 0));
-			CU(cudaMemcpyAsync(sbuf_host + (size_t)i*fpix, ctx->fs[s].sbuf, fpix*4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+			CU(cudaMemcpyAsync(sbuf_host + (size_t)j*fpix, ctx->fs[s].sbuf, fpix*4, cudaMemcpyDeviceToHost, ctx->copy_stream));
 			CU(cudaEventRecord(ctx->ev_copied[s], ctx->copy_stream));
 		}
+		return PWN_OK;
+	};
+	for(int i = 0; i < n; i++)
+	{
+		const int s = i & 1;
+		float rayb[4], rdx[4], rdy[4];
+		pwn_ray_setup(poses[i].cam, dimx, dimy, rayb, rdx, rdy);
+		// Before a frame set's sbuf is rewritten, the copy of the frame it still holds must have
+		// drained.  Unpipelined: this launch rewrites set s, which holds frame i-2.  Pipelined: the
+		// blur riding in this launch rewrites set s^1, which holds frame i-3.
+		if(sbuf_host != nullptr)
+		{
+			if(!pipelined && i >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[s], 0));
+			if(pipelined && i >= 3) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[s ^ 1], 0));
+		}
+		int rc = launch_trace(ctx, ctx->fs[s], poses[i].cam + 12, rayb, rdx, rdy, dimx, dimy, poses[i].sec_current, flags, false,
+			(pipelined && i > 0) ? &ctx->fs[s ^ 1] : nullptr, pipelined);
+		if(rc != PWN_OK) return rc;
+		if(pipelined) { if(i > 0) { rc = finish(i - 1); if(rc != PWN_OK) return rc; } }
+		else { rc = finish(i); if(rc != PWN_OK) return rc; }
+	}
+	if(pipelined)
+	{
+		const FrameSet &f = ctx->fs[(n - 1) & 1];
+		if(sbuf_host != nullptr && n >= 3) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[(n - 1) & 1], 0));
+		int rc = launch_blur(ctx, blur_params(ctx, f.tsbuf, f.zbuf, f.sbuf, dimx, dimy));
+		if(rc != PWN_OK) return rc;
+		rc = finish(n - 1);
+		if(rc != PWN_OK) return rc;
 	}
 	if(sums != nullptr && n > 0)
 		CU(cudaMemcpyAsync(sums, ctx->d_sums, (size_t)n*sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));

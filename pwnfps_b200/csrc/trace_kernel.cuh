@@ -23,6 +23,7 @@
 
 #include "pwntrace.h"
 #include "pwn_libm.cuh"
+#include "blur_kernel.cuh"
 
 namespace pwn {
 
@@ -90,6 +91,7 @@ struct TraceParams
 	pwn_ids *ids;              // [rwidth*rheight][3] or null
 	unsigned long long *opcount; // IDS builds: sum of algorithmic FP32 lane-ops (DESIGN.md "Work model")
 	int reflect_blur;
+	BlurParams prev;           // BLURP builds: the blur pass of the PREVIOUS frame of a pose batch
 };
 
 // Algorithmic FP32 lane-ops per event (counted from the reference source: mul, add,
@@ -159,7 +161,7 @@ struct Aux   // nearest sphere so far (trace.h:196-200)
 	float cb, cg, cr, ca;
 };
 
-template <bool SPH, bool IDS, bool LFMA>
+template <bool SPH, bool IDS, bool LFMA, bool BLURP>
 __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TraceParams P)
 {
 	const LevelDev &L = P.lv;
@@ -683,6 +685,10 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 
 	// ---- col_ftoint (util.h:48-59): B | G<<8 | R<<16 | A<<24 ------------------------------
 	P.sbuf[pix] = pack_lane(ob) | (pack_lane(og) << 8) | (pack_lane(orr) << 16) | (pack_lane(oa) << 24);
+
+	// ---- pose batches: this thread also blurs its pixel of the previous frame (screen.h:69-123),
+	// whose trace finished in the previous launch
+	if(BLURP) blur_pixel(P.prev, x, y);
 }
 
 } // namespace pwn

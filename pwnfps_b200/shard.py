@@ -127,14 +127,15 @@ def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), fr
         got = []
         for it in range(2):
             tot = 0.0
-            for p in poses:
-                if rank == 0 and it == 1:
+            for k, p in enumerate(poses):
+                check = it == 1 and k % 4 == 0      # every 4th frame is read back and compared
+                if rank == 0 and check:
                     tr.frame_clear()
                     tr.sync()
                 dist.barrier()
                 tr.trace_cam(p["cam"], w, h, float(p["sec_current"]), 0)
                 tot += tr.last_kernel_ms()[0]
-                if it == 1:
+                if check:
                     dist.barrier()      # every rank's stores have landed in GPU 0's frame
                     if rank == 0:
                         s0, _, _ = tr.read_frame(want_z=False)
@@ -143,7 +144,7 @@ def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), fr
         dist.barrier()
         close_peer_frame(tr, base)
         if rank == 0:
-            out["fused_frames_equal_one_gpu"] = bool(got == [int(v) for v in want])
+            out["fused_frames_equal_one_gpu"] = bool(got == [int(v) for v in want[::4]])
     except api.PwnError as e:
         out["fused_error"] = str(e)
         tr.frame_redirect(0, 0, 0)

@@ -278,6 +278,32 @@ def test_trace_screen_centred_and_poses(tracer, oracle, default_level):
     assert (sums == sums2).all()
 
 
+def test_blurred_pose_batches_are_pipelined_bit_exact(tracer, oracle, default_level):
+    """pwn_trace_poses with PWN_F_BLUR blurs frame i-1 inside the trace launch of frame i: every
+    frame must equal the single-frame path (K1 then K2) and the oracle, for every batch length."""
+    tracer.level_upload(default_level)
+    tracer.level_prepare_render()
+    oracle_set_level(oracle, default_level)
+    w, h = 320, 200
+    tracer.frame_config(w, h)
+    poses = api.flythrough(default_level, 130)[::10][:9]
+    single = []
+    for pz in poses:
+        tracer.trace_cam(pz["cam"], w, h, float(pz["sec_current"]), api.PWN_F_BLUR)
+        s, _, _ = tracer.read_frame(want_z=False)
+        single.append(s)
+    so, zo, _ = oracle.trace_frame(poses["cam"][4], float(poses["sec_current"][4]), w, h)
+    assert (single[4] == oracle.blur(so, zo, w, h)).all()
+    for n in (1, 2, 3, 4, 9):
+        out = np.zeros((n, h, w), np.uint32)
+        sums = tracer.trace_poses(poses[:n], w, h, api.PWN_F_BLUR, out=out, want_sums=True)
+        for i in range(n):
+            assert (out[i] == single[i]).all(), (n, i)
+            assert int(sums[i]) == int(api.checksum_ref(single[i], w, h))
+        sums2 = tracer.trace_poses(poses[:n], w, h, api.PWN_F_BLUR, want_sums=True)
+        assert (sums2 == sums).all()
+
+
 def test_full_size_properties(tracer, default_level):
     """BASELINE sizes (4K, 8K): determinism, band-stitch equality by checksum, zbuf sanity."""
     tracer.level_upload(default_level)
