@@ -53,7 +53,7 @@ struct pwn_ctx
 	cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
 
 	// level
-	uint16_t *d_cellmap = nullptr;
+	uint32_t *d_cellmap = nullptr;
 	PortalRec *d_portals = nullptr;
 	int w = 0, h = 0;
 	bool have_level = false;
@@ -264,7 +264,7 @@ extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells
 
 	// padded map: one border cell of CL_OOB all round, so the walk needs no bounds checks
 	const int wp = w + 2, hp = h + 2;
-	std::vector<uint16_t> map((size_t)wp*hp, (uint16_t)CL_OOB);
+	std::vector<uint32_t> map((size_t)wp*hp, (uint32_t)CL_OOB);
 	std::vector<PortalRec> recs;
 	for(int z = 0; z < h; z++)
 	for(int x = 0; x < w; x++)
@@ -307,11 +307,30 @@ extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells
 			r.flags = rot | (kind << 8) | ((uint32_t)peek_of(xcell) << 16);
 			r.ccx = (float)dcx + 0.5f; r.ccz = (float)dcz + 0.5f;   // (cx + 0.5f), trace.h:584
 			r.dcx = dcx; r.dcz = dcz;
-			if(recs.size() >= 4096) return fail(PWN_E_LIMIT, "more than 4096 portal cells");
-			entry |= (uint32_t)recs.size() << 4;
+			if(recs.size() >= (1u << 24)) return fail(PWN_E_LIMIT, "more than 2^24 portal cells");
+			entry |= (uint32_t)recs.size() << CM_REC_SHIFT;
 			recs.push_back(r);
 		}
-		map[(size_t)(z + 1)*wp + x + 1] = (uint16_t)entry;
+		map[(size_t)(z + 1)*wp + x + 1] = entry;
+	}
+	// slow-transition bits of the room cells (see CM_SLOW_SHIFT in trace_kernel.cuh)
+	for(int z = 0; z < h; z++)
+	for(int x = 0; x < w; x++)
+	{
+		const size_t ci = (size_t)(z + 1)*wp + x + 1;
+		const uint32_t c = map[ci] & 15u;
+		if(c < CL_ONE || c > CL_TWO_FOG) continue;
+		const long nb[4] = {1, wp, -1, -wp};   // FXP FZP FXN FZN (defs.h:25-33)
+		for(int d = 0; d < 4; d++)
+		{
+			const uint32_t n = map[ci + nb[d]] & 15u;
+			const bool ntwo = (n == CL_TWO) || (n == CL_TWO_FOG);
+			bool slow;
+			if(c == CL_TWO || c == CL_TWO_FOG) slow = !ntwo;
+			else if(c == CL_RAISED) slow = ntwo || n == CL_OOB;
+			else slow = n == CL_OOB;
+			if(slow) map[ci] |= 1u << (CM_SLOW_SHIFT + d);
+		}
 	}
 	if(recs.empty()) { PortalRec r; memset(&r, 0, sizeof(r)); recs.push_back(r); }
 
@@ -319,9 +338,9 @@ extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells
 	cudaFree(ctx->d_cellmap); cudaFree(ctx->d_portals);
 	ctx->d_cellmap = nullptr; ctx->d_portals = nullptr;
 	ctx->have_level = false;
-	CU(cudaMalloc(&ctx->d_cellmap, map.size()*sizeof(uint16_t)));
+	CU(cudaMalloc(&ctx->d_cellmap, map.size()*sizeof(uint32_t)));
 	CU(cudaMalloc(&ctx->d_portals, recs.size()*sizeof(PortalRec)));
-	CU(cudaMemcpy(ctx->d_cellmap, map.data(), map.size()*sizeof(uint16_t), cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(ctx->d_cellmap, map.data(), map.size()*sizeof(uint32_t), cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(ctx->d_portals, recs.data(), recs.size()*sizeof(PortalRec), cudaMemcpyHostToDevice));
 	ctx->w = w; ctx->h = h;
 	ctx->have_level = true;

@@ -40,8 +40,15 @@ enum : uint32_t
 	CL_RAMP_LT = 7,    // '<'
 	CL_RAMP_COMMA = 8, // ','
 	CL_RAMP_CARET = 9, // '^'
-	CL_PORTAL = 10,    // letter cell; bits 4..15 of the map entry index PortalRec
-	CL_OOB = 15        // the one-cell border around the map: the ray is leaving the grid
+	CL_PORTAL = 10,    // letter cell; bits 8.. of the map entry index PortalRec
+	CL_OOB = 15,       // the one-cell border around the map: the ray is leaving the grid
+
+	// Map entry = class | slow[4] << 4 | portal record << 8.  slow[d] (d = FXP, FZP, FXN, FZN) is set
+	// on a room cell when stepping out of it through face d can need more than the plain advance:
+	// the neighbour is the border, a raised cell steps into a 2-high room (trace.h:343-351), or a
+	// 2-high room steps into anything but another 2-high room (trace.h:395-440).  The flattening
+	// (pwn_level_upload) derives the bits; the room step tests one of them instead of the classes.
+	CM_SLOW_SHIFT = 4, CM_REC_SHIFT = 8
 };
 
 enum : uint32_t { PK_WALL = 0, PK_PASS = 1, PK_RAISED = 2 };   // what a 2-high room sees through a cell (trace.h:404-440)
@@ -63,7 +70,7 @@ struct __align__(16) PortalRec
 
 struct LevelDev
 {
-	const uint16_t *cellmap;   // (h+2)*(w+2) entries: class | rec<<4, border = CL_OOB
+	const uint32_t *cellmap;   // (h+2)*(w+2) entries: class | slow<<4 | rec<<8, border = CL_OOB
 	const PortalRec *portals;
 	int w, h, wp;              // wp = w + 2: row stride of the padded map
 	const uint32_t *rcp_tab;   // 1<<rcp_bits
@@ -241,11 +248,16 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 		wx = __fmul_rn(wx, iax); wy = __fmul_rn(wy, iay); wz = __fmul_rn(wz, iaz);
 
 		// linear index into the padded map.  While a coordinate is outside the grid the lookup
-		// folds to index 0 on that axis (util.h:151-158): `oob` rays take the rare path of every
-		// step, which tracks the real (cx, cz) and recomputes the index from them
+		// folds to index 0 on that axis (util.h:151-158): such rays (oobm != 0) take the slow path
+		// of every step, which tracks the real (cx, cz) and recomputes the index from them
 		int stepx = gx, stepz = gz*WP;
-		bool oob = ((unsigned)cx >= (unsigned)W) | ((unsigned)cz >= (unsigned)H);
-		int ci = (((unsigned)cz >= (unsigned)H ? 0 : cz) + 1)*WP + ((unsigned)cx >= (unsigned)W ? 0 : cx) + 1;
+		uint32_t oobm = 0u;
+		int ci = (cz + 1)*WP + cx + 1;
+		if(((unsigned)cx >= (unsigned)W) | ((unsigned)cz >= (unsigned)H))
+		{
+			oobm = 1u << CM_SLOW_SHIFT;
+			ci = (((unsigned)cz >= (unsigned)H ? 0 : cz) + 1)*WP + ((unsigned)cx >= (unsigned)W ? 0 : cx) + 1;
+		}
 		int ldx = (gx < 0 ? PWN_FXN : PWN_FXP), ldz = (gz < 0 ? PWN_FZN : PWN_FZP);
 		uint32_t cell = __ldg(&L.cellmap[ci]);
 		int ldir = PWN_FYN;
@@ -270,9 +282,9 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 // already was outside the grid: bring the real cell coordinates up to date and look the cell up
 // the way get_cell does (util.h:151-158).  Builds with IDS keep cx/cz current themselves.
 #define PWN_OOB_FIX(XSTEP) do { \
-		if(!oob) { const int row_ = ci / WP; if(!IDS) { cx = ci - row_*WP - 1; cz = row_ - 1; } } \
+		if(!oobm) { const int row_ = ci / WP; if(!IDS) { cx = ci - row_*WP - 1; cz = row_ - 1; } } \
 		else if(!IDS) { if(XSTEP) cx += gx; else cz += gz; } \
-		oob = ((unsigned)cx >= (unsigned)W) | ((unsigned)cz >= (unsigned)H); \
+		oobm = (((unsigned)cx >= (unsigned)W) | ((unsigned)cz >= (unsigned)H)) ? (1u << CM_SLOW_SHIFT) : 0u; \
 		ci = (((unsigned)cz >= (unsigned)H ? 0 : cz) + 1)*WP + ((unsigned)cx >= (unsigned)W ? 0 : cx) + 1; \
 		cell = __ldg(&L.cellmap[ci]); } while(0)
 
@@ -284,7 +296,7 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 
 			if(SPH)   // trace.h:252-296
 			{
-				if(!oob)
+				if(!oobm)
 				{
 					const uint32_t e = __ldg(&L.parts_off[ci + 1]);
 					for(uint32_t i = __ldg(&L.parts_off[ci]); i < e; i++)
@@ -371,15 +383,15 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 					if(IDS) { if(xfirst) cx += gx; else cz += gz; }
 				}
 				if(up2) wy = __fsub_rn(wy, iay);   // trace.h:392
+				const uint32_t cur = cell;
 				cell = __ldg(&L.cellmap[ci]);
-				uint32_t ncls = cell & 15u;
 
-				// everything below is rare: leaving the grid, raised floors, and a 2-high room left
-				// above y = 1 into anything but another 2-high room (the common case passes: trace.h:418-420)
-				const bool yout = two & ((py < 0.0f) | (py > 1.0f)) & (ncls - CL_TWO > CL_TWO_FOG - CL_TWO);
-				if((ncls == CL_OOB) | oob | (ncls == CL_RAISED) | (cls == CL_RAISED) | yout)
+				// slow transitions only (the cell's slow bit for the face just crossed, or a ray
+				// outside the grid): leaving the grid, raised floors, 2-high room into anything else
+				if(((cur >> ldir) | oobm) & (1u << CM_SLOW_SHIFT))
 				{
-					if((ncls == CL_OOB) | oob) { PWN_OOB_FIX(xfirst); ncls = cell & 15u; }
+					if(((cell & 15u) == CL_OOB) | (oobm != 0u)) PWN_OOB_FIX(xfirst);
+					const uint32_t ncls = cell & 15u;
 					if(!two)
 					{
 						if(cls == CL_RAISED && (ncls == CL_TWO || ncls == CL_TWO_FOG))   // trace.h:343-351
@@ -398,7 +410,7 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 						if(py < 0.0f || py > 1.0f)   // trace.h:404-440
 						{
 							uint32_t pk;
-							if(ncls == CL_PORTAL) pk = oob ? PK_WALL : ((__ldg(&L.portals[cell >> 4].flags) >> 16) & 255u);
+							if(ncls == CL_PORTAL) pk = oobm ? PK_WALL : ((__ldg(&L.portals[cell >> CM_REC_SHIFT].flags) >> 16) & 255u);
 							else pk = (ncls == CL_TWO || ncls == CL_TWO_FOG) ? PK_PASS : (ncls == CL_RAISED ? PK_RAISED : PK_WALL);
 							if(pk != PK_PASS)
 							{
@@ -452,20 +464,20 @@ __global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TracePara
 				if(ry >= 0.0f) wy = __fsub_rn(1.0f, wy);
 				wy = __fmul_rn(wy, iay);
 				cell = __ldg(&L.cellmap[ci]);
-				if(((cell & 15u) == CL_OOB) | oob) PWN_OOB_FIX(xfirst);
+				if(((cell & 15u) == CL_OOB) | (oobm != 0u)) PWN_OOB_FIX(xfirst);
 			}
 			else if(cls == CL_PORTAL)
 			{
 				// trace.h:508-650
-				const uint4 pa = __ldg(reinterpret_cast<const uint4 *>(&L.portals[cell >> 4]));
+				const uint4 pa = __ldg(reinterpret_cast<const uint4 *>(&L.portals[cell >> CM_REC_SHIFT]));
 				uint32_t pkind = (pa.w >> 8) & 255u;
-				if(oob && pkind == PR_OK) pkind = PR_STRAY;   // outside the grid no end matches (trace.h:530,539)
+				if(oobm && pkind == PR_OK) pkind = PR_STRAY;   // outside the grid no end matches (trace.h:530,539)
 				if(pkind != PR_OK)
 				{
 					PWN_SPHERE_EXIT(false, 0.0f)
 					PWN_WALL_EXIT(pkind == PR_UNPAIRED ? SF_WALL : SF_STRAY)
 				}
-				const uint4 pb = __ldg(reinterpret_cast<const uint4 *>(&L.portals[cell >> 4]) + 1);
+				const uint4 pb = __ldg(reinterpret_cast<const uint4 *>(&L.portals[cell >> CM_REC_SHIFT]) + 1);
 				ci = (int)pa.x;
 				if(IDS) { cx = (int)pb.z; cz = (int)pb.w; ops += W_PORTAL; nport++; }
 				px = __fadd_rn(px, __uint_as_float(pa.y));
