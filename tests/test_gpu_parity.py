@@ -186,6 +186,38 @@ def test_maze_wide_level(tracer, oracle):
         check_frame(tracer, oracle, pz["cam"], float(pz["sec_current"]), 480, 270, label="maze")
 
 
+def test_large_arguments_and_flags(tracer, oracle, default_level):
+    """sec_current in the thousands drives sinf/cosf through glibc's 192-bit reduction (|x| >= 120);
+    REFLECT_BLUR off (defs.h:6) removes the five RNG draws per bounce."""
+    tracer.level_upload(default_level)
+    tracer.level_prepare_render()
+    oracle_set_level(oracle, default_level)
+    cam = api.mat4_roty(api.cam_spawn(default_level), 0.8)
+    for sec in (19.5, 1234.567, 1.0e6):
+        check_frame(tracer, oracle, cam, sec, 320, 240, label="sec %g" % sec)
+    w, h = 320, 240
+    tracer.frame_config(w, h)
+    tracer.frame_clear()
+    tracer.trace_cam(cam, w, h, 0.5, api.PWN_F_NO_REFLECT_BLUR)
+    s, z, _ = tracer.read_frame()
+    oracle.config(reflect=2, reflect_blur=False)
+    try:
+        so, zo, _ = oracle.trace_frame(cam, 0.5, w, h)
+    finally:
+        oracle.config(reflect=2, reflect_blur=True)
+    assert (s == so).all() and (z.view(np.uint32) == zo.view(np.uint32)).all()
+
+
+def test_flythrough_frames_vs_oracle(tracer, oracle, default_level):
+    """every 40th pose of the 600-frame script (BASELINE configs[1]) at quarter resolution"""
+    tracer.level_upload(default_level)
+    tracer.level_prepare_render()
+    oracle_set_level(oracle, default_level)
+    poses = api.flythrough(default_level, 600)
+    for i in range(0, 600, 40):
+        check_frame(tracer, oracle, poses["cam"][i], float(poses["sec_current"][i]), 480, 270, label="fly %d" % i)
+
+
 def test_row_band_sharding_stitches(tracer, default_level):
     """bands b % N == r traced separately land on exactly the 1-shard frame."""
     tracer.level_upload(default_level)
