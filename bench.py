@@ -325,6 +325,38 @@ def run_ours(args, rank, world, local_rank):
         except Exception as e:     # the baseline is a reported number, never a gate
             cpu = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
 
+    # ---- the other BASELINE configs, device-timed on rank 0 (reported, not the headline) --------
+    others = None
+    if rank == 0 and world == 1 and not args.no_others:
+        others = {}
+        for name, lvx, (ow, oh), nposes in (("mirror_hall_1080p (configs[2])", levels.mirror_hall(), (1920, 1080), 8),
+                                            ("maze_10k_4k (configs[3])", levels.maze(dim=128, seed=1), (3840, 2160), 16),
+                                            ("maze_10k_8k (configs[4], 1 GPU)", levels.maze(dim=128, seed=1), (7680, 4320), 16)):
+            tr.level_upload(lvx)
+            tr.level_prepare_render()
+            tr.frame_config(ow, oh)
+            if "hall" in name:
+                cam0 = api.cam_spawn(lvx)
+                px = np.zeros(nposes, api.POSE_DTYPE)
+                for k in range(nposes):
+                    px["cam"][k] = api.mat4_roty(cam0, 1.5707964 + 0.4 * k)
+                    px["sec_current"][k] = 0.25 * k
+            else:
+                px = levels.poses_random(lvx, nposes, seed=1)
+            tr.trace_poses(px, ow, oh, flags)                         # warm-up
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(3):
+                tr.trace_poses(px, ow, oh, flags)
+            b.record(stream)
+            b.synchronize()
+            msf = a.elapsed_time(b) / (3 * nposes)
+            others[name] = {"resolution": [ow, oh], "poses": nposes, "ms_per_frame": msf,
+                            "mrays_per_s": ow * oh / msf / 1e3, "frames_per_s": 1e3 / msf, "blur": bool(flags)}
+        tr.level_upload(lv)
+        tr.level_prepare_render()
+        tr.frame_config(w, h, want_ids=True)
+
     band = None
     if world > 1:
         from pwnfps_b200 import shard
@@ -347,6 +379,8 @@ def run_ours(args, rank, world, local_rank):
                     "how": "pwn_trace_poses into pinned host memory, %d-frame chunks; trace of frame i+1 overlaps the copy of frame i" % chunk},
             "gpu_launches": int(launches), "wall_s": wall,
         }
+        if others is not None:
+            line["other_configs"] = others
         if band is not None:
             line["band_gather"] = band
         print(json.dumps(line))
@@ -364,6 +398,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-blur", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_configs block")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

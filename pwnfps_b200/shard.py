@@ -164,6 +164,20 @@ def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), fr
         tot_g += a.elapsed_time(b)
     gk, gg = allmax(tot_k) / frames, allmax(tot_g) / frames
     tr.shard_config(1, 0)
+
+    # the 64-pose batch of configs[4]: sharded by pose (pose p -> rank p % N), no exchange at all
+    batch = levels.poses_random(lv, 64, seed=9)
+    mine = batch[rank::world].copy()
+    tr.trace_poses(mine[:2], w, h, api.PWN_F_BLUR)
+    dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    tr.trace_poses(mine, w, h, api.PWN_F_BLUR)
+    b.record(stream)
+    b.synchronize()
+    pb = allmax(a.elapsed_time(b))
+    out["pose_batch_64_ms"] = pb
+    out["pose_batch_64_mrays"] = 64 * w * h / pb / 1e3
     px = w * h / 1e3
     out.update({"one_gpu_ms": one, "one_gpu_mrays": px / one,
                 "fused_ms": fused, "fused_mrays": (px / fused) if fused else None,
