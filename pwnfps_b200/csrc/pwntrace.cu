@@ -507,9 +507,9 @@ static int launch_blur(pwn_ctx *ctx, const BlurParams &B)
 template <bool SPH, bool LFMA>
 static void launch_k1(const TraceParams &P, dim3 grid, cudaStream_t st, bool ids, bool blurp)
 {
-	if(ids) k_trace<SPH, true, LFMA, false><<<grid, 256, 0, st>>>(P);
-	else if(blurp) k_trace<SPH, false, LFMA, true><<<grid, 256, 0, st>>>(P);
-	else k_trace<SPH, false, LFMA, false><<<grid, 256, 0, st>>>(P);
+	if(ids) k_trace<SPH, true, LFMA, false><<<grid, K1_THREADS, 0, st>>>(P);
+	else if(blurp) k_trace<SPH, false, LFMA, true><<<grid, K1_THREADS, 0, st>>>(P);
+	else k_trace<SPH, false, LFMA, false><<<grid, K1_THREADS, 0, st>>>(P);
 }
 
 // K1 for one frame into frame set f (+ the blur of `prev`'s frame riding along, pose batches),
@@ -564,7 +564,7 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 	ctx->timed = ctx->timed_blur = false;
 	if(P.nbands_local > 0)
 	{
-		dim3 grid((dimx + 31)/32, P.nbands_local*4);
+		dim3 grid((dimx + 31)/32, P.nbands_local*(32/K1_ROWS));
 		if(timing) CU(cudaEventRecord(ctx->ev_k1a, ctx->stream));
 		const bool ids = P.ids != nullptr;
 		if(ctx->nsph > 0) { if(ctx->libm_fma) launch_k1<true, true>(P, grid, ctx->stream, ids, blurp); else launch_k1<true, false>(P, grid, ctx->stream, ids, blurp); }

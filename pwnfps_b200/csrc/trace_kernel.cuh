@@ -168,17 +168,21 @@ struct Aux   // nearest sphere so far (trace.h:196-200)
 	float cb, cg, cr, ca;
 };
 
+// CTA = 32 x K1_ROWS pixels, K1_ROWS/4 ... one warp per 8x4 pixels
+constexpr int K1_ROWS = 4;
+constexpr int K1_THREADS = 32*K1_ROWS;
+
 template <bool SPH, bool IDS, bool LFMA, bool BLURP>
-__global__ void __launch_bounds__(256) k_trace(const __grid_constant__ TraceParams P)
+__global__ void __launch_bounds__(K1_THREADS) k_trace(const __grid_constant__ TraceParams P)
 {
 	const LevelDev &L = P.lv;
-	__shared__ float s_ray[3][8][32];
+	__shared__ float s_ray[3][K1_ROWS][32];
 
 	// ---- pixel of this thread: CTA = 32x8 pixels, warp = 8x4 ----------------------
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int tx = (warp & 3)*8 + (lane & 7), ty = (warp >> 2)*4 + (lane >> 3);
 	const int x = blockIdx.x*32 + tx;
-	const int lrow0 = blockIdx.y*8;
+	const int lrow0 = blockIdx.y*K1_ROWS;
 	// local row -> global row through the band interleave (8 | 32: a CTA never straddles bands)
 	const int y0 = ((lrow0 >> 5)*P.nshards + P.shard)*32 + (lrow0 & 31);
 	const int y = y0 + ty;
