@@ -133,6 +133,9 @@ def host():
     H.pwn_level_link.argtypes = [C.POINTER(_CLevel)]
     H.pwn_level_derive.argtypes = [C.POINTER(_CLevel)]
     H.pwn_level_save_txt.argtypes = [C.POINTER(_CLevel), C.c_char_p]
+    H.pwn_level_save_bin.argtypes = [C.POINTER(_CLevel), C.c_char_p]
+    H.pwn_level_load_bin.restype = C.POINTER(_CLevel)
+    H.pwn_level_load_bin.argtypes = [C.c_char_p]
     H.pwn_cam_spawn.argtypes = [C.c_int, C.c_int, C.c_void_p]
     H.pwn_cam_spawn.restype = None
     H.pwn_mat4_roty.argtypes = [C.c_void_p, C.c_float]
@@ -207,6 +210,24 @@ class Level:
         s["col"][0] = (cb, cg, cr, 0.0)
         self.spheres = np.concatenate([self.spheres, s])
 
+    def _to_c(self):
+        H = host()
+        p = H.pwn_level_new(self.w, self.h, len(self.portals))
+        C.memmove(p.contents.cells, self.cells.ctypes.data, self.cells.nbytes)
+        if len(self.portals):
+            C.memmove(p.contents.portals, self.portals.ctypes.data, self.portals.nbytes)
+        p.contents.sx, p.contents.sz = self.sx, self.sz
+        return p
+
+    def save_bin(self, path):
+        """PWNLV001 binary file (pwn_level.h): any grid size, any number of portal pairs."""
+        H = host()
+        p = self._to_c()
+        rc = H.pwn_level_save_bin(p, os.fsencode(path))
+        H.pwn_level_free(p)
+        if rc != 0:
+            raise PwnError(-1, "cannot write %s" % path)
+
     def save_txt(self, path):
         H = host()
         p = H.pwn_level_new(self.w, self.h, len(self.portals))
@@ -221,6 +242,13 @@ class Level:
 def level_load(fname):
     """level_load (level.h:107-228) through the C host loader."""
     p = host().pwn_level_load(os.fsencode(fname))
+    if not p:
+        raise PwnError(-1, "err loading level: %s" % fname)
+    return Level._from_c(p)
+
+
+def level_load_bin(fname):
+    p = host().pwn_level_load_bin(os.fsencode(fname))
     if not p:
         raise PwnError(-1, "err loading level: %s" % fname)
     return Level._from_c(p)

@@ -218,3 +218,35 @@ int pwn_level_save_txt(const pwn_level *lv, const char *fname)
 	fclose(fp);
 	return 0;
 }
+
+int pwn_level_save_bin(const pwn_level *lv, const char *fname)
+{
+	FILE *fp = fopen(fname, "wb");
+	if(fp == NULL) return -1;
+	int32_t hdr[5] = {lv->w, lv->h, lv->nportals, lv->sx, lv->sz};
+	int ok = fwrite("PWNLV001", 1, 8, fp) == 8
+		&& fwrite(hdr, sizeof(int32_t), 5, fp) == 5
+		&& fwrite(lv->cells, sizeof(int32_t), (size_t)lv->w*lv->h, fp) == (size_t)lv->w*lv->h
+		&& fwrite(lv->portals, sizeof(pwn_portal), (size_t)lv->nportals, fp) == (size_t)lv->nportals;
+	fclose(fp);
+	return ok ? 0 : -1;
+}
+
+pwn_level *pwn_level_load_bin(const char *fname)
+{
+	FILE *fp = fopen(fname, "rb");
+	char magic[8];
+	int32_t hdr[5];
+	if(fp == NULL) return NULL;
+	if(fread(magic, 1, 8, fp) != 8 || memcmp(magic, "PWNLV001", 8) != 0 || fread(hdr, sizeof(int32_t), 5, fp) != 5
+		|| hdr[0] <= 0 || hdr[1] <= 0 || hdr[0] > 16384 || hdr[1] > 16384 || hdr[2] < 0 || hdr[2] > (1 << 24))
+	{ fclose(fp); return NULL; }
+	pwn_level *lv = pwn_level_new(hdr[0], hdr[1], hdr[2]);
+	if(lv == NULL) { fclose(fp); return NULL; }
+	lv->sx = hdr[3]; lv->sz = hdr[4];
+	if(fread(lv->cells, sizeof(int32_t), (size_t)lv->w*lv->h, fp) != (size_t)lv->w*lv->h
+		|| fread(lv->portals, sizeof(pwn_portal), (size_t)lv->nportals, fp) != (size_t)lv->nportals)
+	{ fclose(fp); pwn_level_free(lv); return NULL; }
+	fclose(fp);
+	return lv;
+}

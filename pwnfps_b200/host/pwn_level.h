@@ -51,6 +51,16 @@ int32_t pwn_level_get_cell(const pwn_level *lv, int cx, int cz);
 /* writes the level in level.txt format; fails (-1) if it does not fit 64x64 / 26 letters */
 int pwn_level_save_txt(const pwn_level *lv, const char *fname);
 
+/*
+ * Binary level file for levels beyond the reference's limits: little endian,
+ *   char magic[8] = "PWNLV001"; int32 w, h, nportals, sx, sz;
+ *   int32 cells[h*w]; pwn_portal portals[nportals] (as derived: rot12, c1, c2 included).
+ * A level that fits 64x64 / 26 letters should be kept as level.txt (pwn_level_save_txt), which
+ * the reference's own loader reads.
+ */
+int pwn_level_save_bin(const pwn_level *lv, const char *fname);
+pwn_level *pwn_level_load_bin(const char *fname);
+
 #ifdef __cplusplus
 }
 #endif

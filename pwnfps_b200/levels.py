@@ -227,3 +227,24 @@ def game_spheres(lv, sec=0.0):
         rx, rz = rc * x + rs * z, rc * z - rs * x
         lv.sphere_add(r, refl, obx + rx, oby + y, obz + rz, cb, cg, cr)
     return lv
+
+
+def scatter_spheres(lv, n, seed=1):
+    """n seeded spheres over the walkable cells of `lv` (radius 0.03-0.3, mixed reflectance, some
+    overlapping cell borders): exercises the per-cell lists at scale (OBJ_MAX is 10000, defs.h:4)."""
+    rnd = _Lcg(seed + 1234)
+    ok = np.argwhere(np.isin(lv.cells, [ord(c) for c in ";$#&"]))
+    lv.spheres = np.zeros(0, api.SPHERE_DTYPE)
+    sp = np.zeros(n, api.SPHERE_DTYPE)
+    for i in range(n):
+        z, x = ok[rnd.below(len(ok))]
+        r = 0.03 + rnd.below(28) / 100.0
+        sp["r"][i] = r
+        sp["refl"][i] = (0.0, 0.2, 0.4, 0.6)[rnd.below(4)]
+        sp["pos"][i] = (x + rnd.below(1000) / 1000.0, 0.05 + rnd.below(900) / 1000.0, z + rnd.below(1000) / 1000.0, 1.0)
+        sp["col"][i] = (rnd.below(100) / 80.0, rnd.below(100) / 80.0, rnd.below(100) / 80.0, 0.0)
+    # keep every bounding box inside the grid: the reference indexes its cell lists unchecked (level.h:6-17)
+    keep = ((sp["pos"][:, 0] - sp["r"] >= 1) & (sp["pos"][:, 0] + sp["r"] < lv.w - 1)
+            & (sp["pos"][:, 2] - sp["r"] >= 1) & (sp["pos"][:, 2] + sp["r"] < lv.h - 1))
+    lv.spheres = sp[keep]
+    return lv

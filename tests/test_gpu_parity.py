@@ -176,6 +176,23 @@ def test_spheres(tracer, oracle):
     tracer.level_prepare_render()
 
 
+def test_many_spheres_on_the_maze(tracer, oracle):
+    """3000 spheres binned per cell on the device side of pwn_parts_upload; sphere hits, sphere
+    bounces and spheres seen through portals, bit-exact"""
+    lv = levels.scatter_spheres(levels.maze(dim=128, seed=1), 3000, seed=2)
+    tracer.level_upload(lv)
+    tracer.level_prepare_render()
+    oracle_set_level(oracle, lv)
+    hits = 0
+    for pz in levels.poses_random(lv, 5, seed=3):
+        check_frame(tracer, oracle, pz["cam"], float(pz["sec_current"]), 480, 270, label="maze spheres")
+        _, _, ids = tracer.read_frame(want_ids=True)
+        hits += int((ids["kind"] == 1).sum())
+    assert hits > 2000
+    lv.spheres = lv.spheres[:0]
+    tracer.level_prepare_render()
+
+
 def test_maze_wide_level(tracer, oracle):
     """10k-sector level (beyond the reference's 64x64/26 limits), seeded poses."""
     lv = levels.maze(dim=128, seed=1)

@@ -85,3 +85,42 @@ def test_flythrough_is_deterministic(default_level):
     step = np.abs(np.diff(pos[:, [0, 2]], axis=0)).max(axis=1)
     assert (step > 2.0).any() and np.ptp(a["cam"][:, 8]) > 0.5
     assert abs(float(a["sec_current"][60]) - 1.0) < 1e-4
+
+
+def test_binary_level_roundtrip(tmp_path):
+    lv = levels.maze(dim=128, seed=3)
+    p = str(tmp_path / "maze.pwnlv")
+    lv.save_bin(p)
+    back = api.level_load_bin(p)
+    assert (back.cells == lv.cells).all() and (back.portals_i32() == lv.portals_i32()).all()
+    assert (back.sx, back.sz) == (lv.sx, lv.sz)
+    with open(p, "r+b") as f:
+        f.write(b"XXXX")
+    with pytest.raises(api.PwnError):
+        api.level_load_bin(p)
+    with pytest.raises(api.PwnError):
+        lv.save_txt(str(tmp_path / "maze.txt"))    # does not fit 64x64 / 26 letters
+
+
+def test_player_portal_traversal_keeps_the_view(oracle, default_level):
+    """The restated player physics (main.c:276-379) teleports and turns the camera through a portal
+    with the same quarter-turn maths as the rays: the frame after a crossing must look like the frame
+    before it (the portal is a window), unlike a frame from elsewhere on the path."""
+    from conftest import oracle_set_level
+    oracle_set_level(oracle, default_level)
+    poses = api.flythrough(default_level, 600)
+    pos = poses["cam"][:, [12, 14]]
+    jumps = np.nonzero(np.abs(np.diff(pos, axis=0)).max(axis=1) > 2.0)[0]
+    assert len(jumps) >= 2
+    w, h = 160, 90
+
+    def frame(i):
+        s, _, _ = oracle.trace_frame(poses["cam"][i], 0.0, w, h, nthreads=4)   # same sec: only the pose differs
+        return s.view(np.uint8).reshape(h, w, 4)[..., :3].astype(np.int32)
+
+    for j in jumps[:3]:
+        before, after = frame(j), frame(j + 1)
+        far = frame((j + 150) % 600)
+        d_cross = np.abs(before - after).mean()
+        d_far = np.abs(before - far).mean()
+        assert d_cross < 12.0 and d_cross < 0.5 * d_far, (j, d_cross, d_far)

@@ -226,3 +226,23 @@ def test_open_border_level_vs_reference(oracle, refs, tmp_path):
         cx, cz = c % 64, c // 64
         outside += int(((c < 0) | (cx >= 64)).sum())   # cz*64+cx with cx or cz outside the grid
     assert outside > 1000
+
+
+def test_many_spheres_vs_wide_reference(oracle, refs):
+    """per-cell sphere lists at scale (level_prepare_render, level.h:64-81) on the 10k-sector maze"""
+    lv = levels.scatter_spheres(levels.maze(dim=128, seed=1), 1500, seed=2)
+    wide = refs("libref_wide_ids.so")
+    wide.level_set(lv.cells, lv.portals_i32(), lv.sx, lv.sz)
+    wide.objs_clear()
+    for sp in lv.spheres:
+        wide.obj_sphere(sp["r"], sp["refl"], sp["pos"][0], sp["pos"][1], sp["pos"][2], sp["col"][0], sp["col"][1], sp["col"][2])
+    oracle_set_level(oracle, lv)
+    hits = 0
+    try:
+        for pz in levels.poses_random(lv, 4, seed=3):
+            _compare(oracle, wide, None, pz["cam"], float(pz["sec_current"]), 256, 144)
+            _, _, ids = oracle.trace_frame(pz["cam"], float(pz["sec_current"]), 256, 144, want_ids=True)
+            hits += int((ids["kind"] == 1).sum())
+    finally:
+        wide.objs_clear()
+    assert hits > 500
