@@ -171,9 +171,10 @@ struct Aux   // nearest sphere so far (trace.h:196-200)
 // CTA = 32 x K1_ROWS pixels, K1_ROWS/4 ... one warp per 8x4 pixels
 constexpr int K1_ROWS = 4;
 constexpr int K1_THREADS = 32*K1_ROWS;
+constexpr int K1_MIN_CTAS = 8;   // 8 CTAs x 4 warps per SM at 64 registers; 9 (56 regs) and 10 (48 regs) spill and are slower
 
 template <bool SPH, bool IDS, bool LFMA, bool BLURP>
-__global__ void __launch_bounds__(K1_THREADS) k_trace(const __grid_constant__ TraceParams P)
+__global__ void __launch_bounds__(K1_THREADS, K1_MIN_CTAS) k_trace(const __grid_constant__ TraceParams P)
 {
 	const LevelDev &L = P.lv;
 	__shared__ float s_ray[3][K1_ROWS][32];
