@@ -35,19 +35,29 @@ def max_owned_rows(dimy, nshards):
 
 def gather_frame(local_frame, dimy, rank, world, dist, device=None):
     """local_frame: (H, W) torch tensor in which this rank's owned rows are valid.
-    Returns the stitched (H, W) tensor on rank 0, None elsewhere.  One gather of padded row packs."""
+    Returns the stitched (H, W) tensor on rank 0, None elsewhere.  One gather of padded band packs;
+    whole bands move as strided views (band b of rank r is row block b*world + r)."""
     import torch
-    rows = torch.as_tensor(owned_rows(dimy, world, rank), device=local_frame.device)
-    nmax = max_owned_rows(dimy, world)
-    pack = torch.zeros((nmax, local_frame.shape[1]), dtype=local_frame.dtype, device=local_frame.device)
-    pack[:len(rows)] = local_frame[rows]
+    W = local_frame.shape[1]
+    nfull = dimy // BAND                      # whole bands; a ragged last band is handled below
+    tail_owner = nfull % world if dimy % BAND else -1
+    bands = local_frame[:nfull * BAND].view(nfull, BAND, W)
+    nmax = (nfull + world - 1) // world + (1 if tail_owner >= 0 else 0)
+    pack = torch.zeros((nmax, BAND, W), dtype=local_frame.dtype, device=local_frame.device)
+    mine = bands[rank::world]
+    pack[:mine.shape[0]] = mine
+    if rank == tail_owner:
+        pack[mine.shape[0], :dimy - nfull * BAND] = local_frame[nfull * BAND:dimy]
     if rank == 0:
         parts = [torch.empty_like(pack) for _ in range(world)]
         dist.gather(pack, parts, dst=0)
         out = torch.zeros_like(local_frame)
+        ob = out[:nfull * BAND].view(nfull, BAND, W)
         for r in range(world):
-            rr = torch.as_tensor(owned_rows(dimy, world, r), device=local_frame.device)
-            out[rr] = parts[r][:len(rr)]
+            n = ob[r::world].shape[0]
+            ob[r::world] = parts[r][:n]
+            if r == tail_owner:
+                out[nfull * BAND:dimy] = parts[r][n, :dimy - nfull * BAND]
         return out
     dist.gather(pack, None, dst=0)
     return None
@@ -70,8 +80,9 @@ def frame_tensors(tr):
     return s, z
 
 
-def open_peer_frame(tr, rank, dist):
-    """Fused path set-up: every rank > 0 redirects its K1 output into rank 0's frame."""
+def open_peer_frame(tr, rank, dist, with_z=True):
+    """Fused path set-up: every rank > 0 redirects its K1 output into rank 0's frame.  zbuf is only
+    needed on GPU 0 when the blur pass follows; without it half the NVLink bytes stay home."""
     objs = [None]
     if rank == 0:
         objs = [tr.ipc_export()]
@@ -80,7 +91,7 @@ def open_peer_frame(tr, rank, dist):
         return None
     handle, so, zo, to = objs[0]
     base = tr.ipc_import(handle)
-    tr.frame_redirect(base + so, base + zo, base + to)
+    tr.frame_redirect(base + so, (base + zo) if with_z else 0, base + to)
     return base
 
 
@@ -119,32 +130,38 @@ def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), fr
     one = allmax(one) / frames
     want = tr.trace_poses(poses, w, h, 0, want_sums=True) if rank == 0 else None
 
-    # fused: K1 stores into GPU 0's frame over NVLink
+    # fused: K1 stores into GPU 0's frame over NVLink.  Twice: sbuf + zbuf (what a blur on GPU 0
+    # needs), and sbuf alone (the frame the host reads; zbuf stays on the tracing GPU)
     tr.shard_config(world, rank)
-    fused = None
+    fused = fused_s = None
     try:
-        base = open_peer_frame(tr, rank, dist)
-        got = []
-        for it in range(2):
-            tot = 0.0
-            for k, p in enumerate(poses):
-                check = it == 1 and k % 4 == 0      # every 4th frame is read back and compared
-                if rank == 0 and check:
-                    tr.frame_clear()
-                    tr.sync()
-                dist.barrier()
-                tr.trace_cam(p["cam"], w, h, float(p["sec_current"]), 0)
-                tot += tr.last_kernel_ms()[0]
-                if check:
-                    dist.barrier()      # every rank's stores have landed in GPU 0's frame
-                    if rank == 0:
-                        s0, _, _ = tr.read_frame(want_z=False)
-                        got.append(int(api.checksum_ref(s0, w, h)))
-            fused = allmax(tot) / frames
-        dist.barrier()
-        close_peer_frame(tr, base)
-        if rank == 0:
-            out["fused_frames_equal_one_gpu"] = bool(got == [int(v) for v in want[::4]])
+        for with_z in (True, False):
+            base = open_peer_frame(tr, rank, dist, with_z=with_z)
+            got = []
+            for it in range(2):
+                tot = 0.0
+                for k, p in enumerate(poses):
+                    check = it == 1 and k % 4 == 0      # every 4th frame is read back and compared
+                    if rank == 0 and check:
+                        tr.frame_clear()
+                        tr.sync()
+                    dist.barrier()
+                    tr.trace_cam(p["cam"], w, h, float(p["sec_current"]), 0)
+                    tot += tr.last_kernel_ms()[0]
+                    if check:
+                        dist.barrier()      # every rank's stores have landed in GPU 0's frame
+                        if rank == 0:
+                            s0, _, _ = tr.read_frame(want_z=False)
+                            got.append(int(api.checksum_ref(s0, w, h)))
+                if with_z:
+                    fused = allmax(tot) / frames
+                else:
+                    fused_s = allmax(tot) / frames
+            dist.barrier()
+            close_peer_frame(tr, base)
+            if rank == 0:
+                key = "fused_frames_equal_one_gpu" if with_z else "fused_sbuf_only_frames_equal_one_gpu"
+                out[key] = bool(got == [int(v) for v in want[::4]])
     except api.PwnError as e:
         out["fused_error"] = str(e)
         tr.frame_redirect(0, 0, 0)
@@ -181,6 +198,7 @@ def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), fr
     px = w * h / 1e3
     out.update({"one_gpu_ms": one, "one_gpu_mrays": px / one,
                 "fused_ms": fused, "fused_mrays": (px / fused) if fused else None,
+                "fused_sbuf_only_ms": fused_s, "fused_sbuf_only_mrays": (px / fused_s) if fused_s else None,
                 "gather_trace_ms": gk, "gather_nccl_ms": gg, "gather_mrays": px / (gk + gg),
                 "sbuf_bytes": w * h * 4})
     return out
