@@ -537,6 +537,7 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 	P.lv.cellmap = ctx->d_cellmap; P.lv.portals = ctx->d_portals; P.lv.w = ctx->w; P.lv.h = ctx->h; P.lv.wp = ctx->w + 2;
 	P.lv.rcp_tab = ctx->d_rcp; P.lv.rsqrt_tab = ctx->d_rsqrt;
 	P.lv.rcp_shift = 23 - ctx->rcp_bits; P.lv.rsqrt_shift = 23 - ctx->rsqrt_bits;
+	P.lv.rsqrt_mask = (2u << ctx->rsqrt_bits) - 1u;
 	P.lv.sph_pos = ctx->d_sph_pos; P.lv.sph_col = ctx->d_sph_col; P.lv.sph_rr = ctx->d_sph_rr;
 	P.lv.parts_off = ctx->d_parts_off; P.lv.parts_idx = ctx->d_parts_idx; P.lv.nsph = ctx->nsph;
 	for(int i = 0; i < 4; i++) { P.from[i] = from[i]; P.rayb[i] = rayb[i]; P.rdx[i] = rdx[i]; P.rdy[i] = rdy[i]; }

@@ -76,6 +76,7 @@ struct LevelDev
 	const uint32_t *rcp_tab;   // 1<<rcp_bits
 	const uint32_t *rsqrt_tab; // 2<<rsqrt_bits
 	int rcp_shift, rsqrt_shift;   // 23 - bits
+	uint32_t rsqrt_mask;          // (2 << rsqrt_bits) - 1
 	// spheres (pwn_parts_upload); CSR over the padded map
 	const float4 *sph_pos;     // x y z w
 	const float4 *sph_col;     // b g r a
@@ -98,6 +99,7 @@ struct TraceParams
 	pwn_ids *ids;              // [rwidth*rheight][3] or null
 	unsigned long long *opcount; // IDS builds: sum of algorithmic FP32 lane-ops (DESIGN.md "Work model")
 	int reflect_blur;
+	uint32_t zero;             // always 0; opaque to the compiler (see xmov)
 	BlurParams prev;           // BLURP builds: the blur pass of the PREVIOUS frame of a pose batch
 };
 
@@ -128,15 +130,16 @@ __device__ __forceinline__ float rcp_emul(const LevelDev &L, float x)
 	return __uint_as_float(t - (u & 0x7F800000u) + 0x3F800000u);
 }
 
-// rsqrtps(x), x > 0 normal
+// rsqrtps(x), x > 0 normal.  The table index is [parity of the unbiased exponent | top mantissa
+// bits]; with E the biased exponent that parity is !(E & 1), so the index is read straight from
+// the bit pattern with the exponent's low bit flipped, and the result exponent is
+// floor((E - 127)/2) = ((E + 1) >> 1) - 64.
 __device__ __forceinline__ float rsqrt_emul(const LevelDev &L, float x)
 {
-	uint32_t u = __float_as_uint(x);
-	int e = (int)(u >> 23) - 127;
-	int p = e & 1;
-	uint32_t idx = ((u & 0x7FFFFFu) >> L.rsqrt_shift) + ((uint32_t)p << (23 - L.rsqrt_shift));
-	uint32_t t = __ldg(&L.rsqrt_tab[idx]);
-	return __uint_as_float(t - ((uint32_t)((e - p) >> 1) << 23));
+	const uint32_t u = __float_as_uint(x);
+	const uint32_t idx = ((u ^ 0x00800000u) >> L.rsqrt_shift) & L.rsqrt_mask;
+	const uint32_t t = __ldg(&L.rsqrt_tab[idx]);
+	return __uint_as_float(t - (((u + 0x00800000u) >> 1) & 0x7F800000u) + 0x20000000u);
 }
 
 // util.h:1-16 with the shipped -ffast-math folding of randfs: r*fl(2/3759) - 1
@@ -156,6 +159,17 @@ __device__ __forceinline__ uint32_t pack_lane(float v)
 	int q = __float2int_rn(s);
 	return (uint32_t)min(max(q, 0), 255);
 }
+
+// The portal rotation exchanges x and z quantities.  Written as plain copies the exchange becomes a
+// cyclic register copy that ptxas resolves with moves at the head of EVERY walk iteration; written
+// as integer arithmetic (xor swap, xor with an opaque zero) the rare portal path pays for it instead.
+__device__ __forceinline__ void xswap(float &a, float &b)
+{
+	uint32_t x = __float_as_uint(a), y = __float_as_uint(b);
+	x ^= y; y ^= x; x ^= y;
+	a = __uint_as_float(x); b = __uint_as_float(y);
+}
+__device__ __forceinline__ float xmov(float v, uint32_t zero) { return __uint_as_float(__float_as_uint(v) ^ zero); }
 
 // surface colours, lanes b g r a (defs.h:17-19, trace.h:558)
 enum : int { SF_CEIL = 0, SF_FLOOR = 1, SF_WALL = 2, SF_STRAY = 3 };
@@ -189,18 +203,20 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_CTAS) k_trace(const __grid_
 	const int y = y0 + ty;
 
 	// ---- screen.h:12-13,18: rayl = ((rayb + y*rdy) + cx*rdx) + rdx + ... + rdx --------
-	// The x+1 adds are sequential by definition; the CTA computes each of its 8 rows once
-	// (warp w = row w, lanes 0..2 = the three components) and shares them through smem.
-	if(lane < 3)
+	// The x+1 adds are sequential by definition; warp 0 computes each of the CTA's rows once
+	// (lane = 3*row + component, 32 chained adds) and shares them through smem.  The other warps
+	// wait at the barrier, which costs no issue slots -- the resource this kernel is short of.
+	if(warp == 0 && lane < 3*K1_ROWS)
 	{
-		const float fy = (float)(y0 + warp), fcx = (float)(blockIdx.x*32);
-		const float d = P.rdx[lane];
-		float v = __fadd_rn(__fadd_rn(P.rayb[lane], __fmul_rn(fy, P.rdy[lane])), __fmul_rn(fcx, d));
+		const int row = lane/3, comp = lane - 3*row;
+		const float fy = (float)(y0 + row), fcx = (float)(blockIdx.x*32);
+		const float d = P.rdx[comp];
+		float v = __fadd_rn(__fadd_rn(P.rayb[comp], __fmul_rn(fy, P.rdy[comp])), __fmul_rn(fcx, d));
 		#pragma unroll
 		for(int k = 0; k < 32; k++)
 		{
 			v = __fadd_rn(v, d);
-			s_ray[lane][warp][k] = v;
+			s_ray[comp][row][k] = v;
 		}
 	}
 	__syncthreads();
@@ -238,9 +254,12 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_CTAS) k_trace(const __grid_
 		}
 		int cx = __float2int_rz(fx), cz = __float2int_rz(fz);   // real cell coordinates (IDS builds keep them current)
 		const float EPS = 0.0000000000001f;
-		if(fabsf(rx) < EPS) rx = (rx < 0.0f ? -EPS : EPS);
-		if(fabsf(ry) < EPS) ry = (ry < 0.0f ? -EPS : EPS);
-		if(fabsf(rz) < EPS) rz = (rz < 0.0f ? -EPS : EPS);
+		if(fminf(fminf(fabsf(rx), fabsf(ry)), fabsf(rz)) < EPS)   // trace.h:220-222, almost never taken
+		{
+			if(fabsf(rx) < EPS) rx = (rx < 0.0f ? -EPS : EPS);
+			if(fabsf(ry) < EPS) ry = (ry < 0.0f ? -EPS : EPS);
+			if(fabsf(rz) < EPS) rz = (rz < 0.0f ? -EPS : EPS);
+		}
 		int gx = (irx < 0.0f ? -1 : 1), gz = (irz < 0.0f ? -1 : 1);
 		const bool up = !(iry < 0.0f);                          // gy > 0
 		float iax = rcp_emul(L, fabsf(rx)), iaz = rcp_emul(L, fabsf(rz));
@@ -255,7 +274,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_CTAS) k_trace(const __grid_
 		// linear index into the padded map.  While a coordinate is outside the grid the lookup
 		// folds to index 0 on that axis (util.h:151-158): such rays (oobm != 0) take the slow path
 		// of every step, which tracks the real (cx, cz) and recomputes the index from them
-		int stepx = gx, stepz = gz*WP;
+		int stepz = gz*WP;   // index step of a z move; an x move steps by gx
 		uint32_t oobm = 0u;
 		int ci = (cz + 1)*WP + cx + 1;
 		if(((unsigned)cx >= (unsigned)W) | ((unsigned)cz >= (unsigned)H))
@@ -383,7 +402,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_CTAS) k_trace(const __grid_
 					wy = __fsub_rn(wy, t);
 					wx = xfirst ? iax : ax;
 					wz = xfirst ? az : iaz;
-					ci += xfirst ? stepx : stepz;
+					ci += xfirst ? gx : stepz;
 					ldir = xfirst ? ldx : ldz;
 					if(IDS) { if(xfirst) cx += gx; else cz += gz; }
 				}
@@ -459,7 +478,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_CTAS) k_trace(const __grid_
 					const float ax = __fsub_rn(wx, t), az = __fsub_rn(wz, t);
 					wx = xfirst ? iax : ax;
 					wz = xfirst ? az : iaz;
-					ci += xfirst ? stepx : stepz;
+					ci += xfirst ? gx : stepz;
 					ldir = xfirst ? (rx < 0.0f ? PWN_FXN : PWN_FXP) : (rz < 0.0f ? PWN_FZN : PWN_FZP);
 					if(IDS) { if(xfirst) cx += gx; else cz += gz; }
 				}
@@ -495,10 +514,10 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_CTAS) k_trace(const __grid_
 					const float trx = px, trz = pz, trvx = rx;
 					px = __fadd_rn(ccx, __fsub_rn(trz, ccz));
 					pz = __fsub_rn(ccz, __fsub_rn(trx, ccx));
-					rx = rz; rz = -trvx;
-					const int tg = gx; gx = gz; gz = -tg;
-					float tt = wx; wx = wz; wz = tt;
-					tt = iax; iax = iaz; iaz = tt;
+					rx = xmov(rz, P.zero); rz = -trvx;
+					const int tg = gx; gx = gz ^ (int)P.zero; gz = -tg;
+					xswap(wx, wz);
+					xswap(iax, iaz);
 				}
 				else if(rot == 2)
 				{
@@ -512,12 +531,12 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_CTAS) k_trace(const __grid_
 					const float trx = px, trz = pz, trvx = rx;
 					px = __fsub_rn(ccx, __fsub_rn(trz, ccz));
 					pz = __fadd_rn(ccz, __fsub_rn(trx, ccx));
-					rx = -rz; rz = trvx;
-					const int tg = gx; gx = -gz; gz = tg;
-					float tt = wx; wx = wz; wz = tt;
-					tt = iax; iax = iaz; iaz = tt;
+					rx = -rz; rz = xmov(trvx, P.zero);
+					const int tg = gx; gx = -gz; gz = tg ^ (int)P.zero;
+					xswap(wx, wz);
+					xswap(iax, iaz);
 				}
-				stepx = gx; stepz = gz*WP;
+				stepz = gz*WP;
 				ldx = (gx < 0 ? PWN_FXN : PWN_FXP); ldz = (gz < 0 ? PWN_FZN : PWN_FZP);
 				// step out of the destination portal cell (trace.h:624-647)
 				if(ldir == PWN_FXP) { ci++; px = __fadd_rn(px, 1.0f); if(IDS) cx++; }
