@@ -50,7 +50,7 @@ struct pwn_ctx
 	int device = -1;
 	cudaStream_t stream = nullptr, copy_stream = nullptr;
 	cudaEvent_t ev_k1a = nullptr, ev_k1b = nullptr, ev_k2b = nullptr;
-	cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+	cudaEvent_t ev_done[3] = {nullptr, nullptr, nullptr}, ev_copied[3] = {nullptr, nullptr, nullptr};
 
 	// level
 	uint32_t *d_cellmap = nullptr;
@@ -73,7 +73,7 @@ struct pwn_ctx
 
 	// frame
 	int rwidth = 0, rheight = 0;
-	FrameSet fs[2];
+	FrameSet fs[3];            // three sets: the pose pipeline keeps trace(i), blur(i-1) and copy(i-2) apart
 	pwn_ids *d_ids = nullptr;
 	uint2 *d_jump = nullptr;   // per 4-pixel group: the LCG map composed 32*g times (K2)
 	uint32_t *r_sbuf = nullptr, *r_tsbuf = nullptr;   // redirect targets (peer frame) or null
@@ -120,7 +120,7 @@ extern "C" int pwn_create(pwn_ctx **out, int device)
 	CU(cudaEventCreate(&ctx->ev_k1a));
 	CU(cudaEventCreate(&ctx->ev_k1b));
 	CU(cudaEventCreate(&ctx->ev_k2b));
-	for(int i = 0; i < 2; i++)
+	for(int i = 0; i < 3; i++)
 	{
 		CU(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
@@ -143,7 +143,7 @@ extern "C" int pwn_create(pwn_ctx **out, int device)
 
 static void free_frames(pwn_ctx *ctx)
 {
-	for(int i = 0; i < 2; i++) { cudaFree(ctx->fs[i].base); ctx->fs[i] = FrameSet(); }
+	for(int i = 0; i < 3; i++) { cudaFree(ctx->fs[i].base); ctx->fs[i] = FrameSet(); }
 	cudaFree(ctx->d_ids); ctx->d_ids = nullptr;
 	cudaFree(ctx->d_jump); ctx->d_jump = nullptr;
 	ctx->rwidth = ctx->rheight = 0;
@@ -161,7 +161,7 @@ extern "C" int pwn_destroy(pwn_ctx *ctx)
 	cudaFree(ctx->d_parts_off); cudaFree(ctx->d_parts_idx);
 	cudaFree(ctx->d_sums); cudaFree(ctx->d_opcount);
 	cudaEventDestroy(ctx->ev_k1a); cudaEventDestroy(ctx->ev_k1b); cudaEventDestroy(ctx->ev_k2b);
-	for(int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_done[i]); cudaEventDestroy(ctx->ev_copied[i]); }
+	for(int i = 0; i < 3; i++) { cudaEventDestroy(ctx->ev_done[i]); cudaEventDestroy(ctx->ev_copied[i]); }
 	cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->copy_stream);
 	delete ctx;
 	return PWN_OK;
@@ -437,7 +437,7 @@ extern "C" int pwn_frame_config(pwn_ctx *ctx, int rwidth, int rheight, int want_
 	{
 		free_frames(ctx);
 		const size_t plane = align_up((size_t)rwidth*rheight*4, 512);
-		for(int i = 0; i < 2; i++)
+		for(int i = 0; i < 3; i++)
 		{
 			FrameSet &f = ctx->fs[i];
 			f.bytes = 3*plane;
@@ -472,7 +472,7 @@ extern "C" int pwn_frame_clear(pwn_ctx *ctx)
 {
 	CTX_ENTER(ctx);
 	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "pwn_frame_clear before pwn_frame_config");
-	for(int i = 0; i < 2; i++) CU(cudaMemsetAsync(ctx->fs[i].base, 0, ctx->fs[i].bytes, ctx->stream));
+	for(int i = 0; i < 3; i++) CU(cudaMemsetAsync(ctx->fs[i].base, 0, ctx->fs[i].bytes, ctx->stream));
 	if(ctx->d_ids) CU(cudaMemsetAsync(ctx->d_ids, 0xFF, (size_t)ctx->rwidth*ctx->rheight*3*sizeof(pwn_ids), ctx->stream));
 	return PWN_OK;
 }
@@ -508,7 +508,18 @@ template <bool SPH, bool LFMA>
 static void launch_k1(const TraceParams &P, dim3 grid, cudaStream_t st, bool ids, bool blurp)
 {
 	if(ids) k_trace<SPH, true, LFMA, false><<<grid, K1_THREADS, 0, st>>>(P);
-	else if(blurp) k_trace<SPH, false, LFMA, true><<<grid, K1_THREADS, 0, st>>>(P);
+	else if(blurp)
+	{
+		// programmatic dependent launch: this grid may begin before the previous one has drained
+		// (see the end of k_trace)
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = grid; cfg.blockDim = dim3(K1_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+		cudaLaunchAttribute at[1];
+		at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		at[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = at; cfg.numAttrs = 1;
+		cudaLaunchKernelEx(&cfg, k_trace<SPH, false, LFMA, true>, P);
+	}
 	else k_trace<SPH, false, LFMA, false><<<grid, K1_THREADS, 0, st>>>(P);
 }
 
@@ -673,12 +684,12 @@ extern "C" int pwn_trace_poses(pwn_ctx *ctx, int n, const pwn_pose *poses, int d
 		}
 		CU(cudaMemsetAsync(ctx->d_sums, 0, (size_t)n*sizeof(unsigned long long), ctx->stream));
 	}
-	// Blurred batches are software-pipelined across frames: launch i traces pose i into set i&1
-	// and, in the same kernel, blurs frame i-1 in the other set; a plain K2 finishes the last
-	// frame.  Frame j is final (and is checksummed / copied out) after launch j+1.
+	// Blurred batches are software-pipelined across frames: launch i traces pose i into set i%3
+	// and, in the same kernel, blurs frame i-1 in set (i-1)%3; a plain K2 finishes the last frame.
+	// Frame j is final (and is checksummed / copied out) after launch j+1.
 	const bool pipelined = (flags & PWN_F_BLUR) != 0 && ctx->nshards == 1 && n > 1;
 	auto finish = [&](int j) -> int {
-		const int s = j & 1;
+		const int s = j % 3;
 		if(sums != nullptr)
 		{
 			k_checksum<<<296, 256, 0, ctx->stream>>>(ctx->fs[s].sbuf, dimx, dimy, ctx->rwidth, ctx->d_sums + j);
@@ -696,27 +707,27 @@ extern "C" int pwn_trace_poses(pwn_ctx *ctx, int n, const pwn_pose *poses, int d
 	};
 	for(int i = 0; i < n; i++)
 	{
-		const int s = i & 1;
+		const int s = i % 3;
 		float rayb[4], rdx[4], rdy[4];
 		pwn_ray_setup(poses[i].cam, dimx, dimy, rayb, rdx, rdy);
 		// Before a frame set's sbuf is rewritten, the copy of the frame it still holds must have
-		// drained.  Unpipelined: this launch rewrites set s, which holds frame i-2.  Pipelined: the
-		// blur riding in this launch rewrites set s^1, which holds frame i-3.
+		// drained.  Unpipelined: this launch rewrites sbuf of set s, which holds frame i-3.
+		// Pipelined: the blur riding in this launch rewrites sbuf of set (i-1)%3, which holds frame i-4.
 		if(sbuf_host != nullptr)
 		{
-			if(!pipelined && i >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[s], 0));
-			if(pipelined && i >= 3) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[s ^ 1], 0));
+			if(!pipelined && i >= 3) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[s], 0));
+			if(pipelined && i >= 4) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[(i - 1) % 3], 0));
 		}
 		int rc = launch_trace(ctx, ctx->fs[s], poses[i].cam + 12, rayb, rdx, rdy, dimx, dimy, poses[i].sec_current, flags, false,
-			(pipelined && i > 0) ? &ctx->fs[s ^ 1] : nullptr, pipelined);
+			(pipelined && i > 0) ? &ctx->fs[(i - 1) % 3] : nullptr, pipelined);
 		if(rc != PWN_OK) return rc;
 		if(pipelined) { if(i > 0) { rc = finish(i - 1); if(rc != PWN_OK) return rc; } }
 		else { rc = finish(i); if(rc != PWN_OK) return rc; }
 	}
 	if(pipelined)
 	{
-		const FrameSet &f = ctx->fs[(n - 1) & 1];
-		if(sbuf_host != nullptr && n >= 3) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[(n - 1) & 1], 0));
+		const FrameSet &f = ctx->fs[(n - 1) % 3];
+		if(sbuf_host != nullptr && n >= 4) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[(n - 1) % 3], 0));
 		int rc = launch_blur(ctx, blur_params(ctx, f.tsbuf, f.zbuf, f.sbuf, dimx, dimy));
 		if(rc != PWN_OK) return rc;
 		rc = finish(n - 1);

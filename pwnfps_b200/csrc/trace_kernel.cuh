@@ -723,8 +723,16 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_CTAS) k_trace(const __grid_
 	P.sbuf[pix] = pack_lane(ob) | (pack_lane(og) << 8) | (pack_lane(orr) << 16) | (pack_lane(oa) << 24);
 
 	// ---- pose batches: this thread also blurs its pixel of the previous frame (screen.h:69-123),
-	// whose trace finished in the previous launch
-	if(BLURP) blur_pixel(P.prev, x, y);
+	// whose trace ran in the previous launch.  The launches are chained with programmatic dependent
+	// launch: the trace above needs nothing from the previous grid, so this grid may start while
+	// that one drains; only here does it wait for it (griddepcontrol.wait = previous grid complete
+	// and flushed), and only after that does it let the next grid in, so at most two grids overlap.
+	if(BLURP)
+	{
+		asm volatile("griddepcontrol.wait;" ::: "memory");
+		asm volatile("griddepcontrol.launch_dependents;");
+		blur_pixel(P.prev, x, y);
+	}
 }
 
 } // namespace pwn
