@@ -235,6 +235,39 @@ def test_flythrough_frames_vs_oracle(tracer, oracle, default_level):
         check_frame(tracer, oracle, poses["cam"][i], float(poses["sec_current"][i]), 480, 270, label="fly %d" % i)
 
 
+def test_ragged_and_tiny_frames(tracer, oracle, default_level):
+    """edge sizes: single pixel, single row/column, widths that are not multiples of 4 or 32, and a
+    trace window smaller than the frame (the reference indexes from (0,0) with stride rwidth,
+    screen.h:14-15; x1/y1 only enter through dimx/dimy)"""
+    tracer.level_upload(default_level)
+    tracer.level_prepare_render()
+    oracle_set_level(oracle, default_level)
+    cam = api.mat4_roty(api.cam_spawn(default_level), 1.3)
+    for (w, h) in [(1, 1), (1, 40), (40, 1), (3, 5), (33, 2), (31, 31), (65, 33), (130, 70)]:
+        check_frame(tracer, oracle, cam, 0.4, w, h, label="%dx%d" % (w, h))
+    # window smaller than the frame: rwidth 96 x rheight 64, trace 50 x 37 into it
+    rw, rh, w, h = 96, 64, 50, 37
+    tracer.frame_config(rw, rh)
+    tracer.frame_clear()
+    tracer.trace_cam(cam, w, h, 0.4, 0)
+    s, z, _ = tracer.read_frame()
+    so, zo, _ = oracle.trace_frame(cam, 0.4, w, h, rwidth=rw)
+    assert (s[:h] == so).all() and (z[:h].view(np.uint32) == zo.view(np.uint32)).all()
+    assert (s[h:] == 0).all() and (s[:, w:] == 0).all()          # nothing outside the window is touched
+    # blur on a window: only dimx-3 rounded down to groups of 4 is blurred, the tail keeps the traced pixels
+    tracer.trace_cam(cam, w, h, 0.4, api.PWN_F_BLUR)
+    sb, _, _ = tracer.read_frame(want_z=False)
+    want = so.copy()
+    tmp = oracle.blur(np.ascontiguousarray(so), np.ascontiguousarray(zo), w, h, rwidth=rw)
+    assert (sb[:h] == tmp).all()
+    assert (sb[:h, 48:50] == so[:, 48:50]).all()
+    # trace_screen_centred with an offset window: x1/y1 only shrink the window
+    tracer.frame_config(rw, rh)
+    tracer.frame_clear()
+    out = tracer.trace_screen_centred(default_level, 10, 7, 60, 44, cam, 0.4, blur=False)
+    assert (out[:h] == so).all()
+
+
 def test_row_band_sharding_stitches(tracer, default_level):
     """bands b % N == r traced separately land on exactly the 1-shard frame."""
     tracer.level_upload(default_level)
