@@ -87,7 +87,20 @@ def build(force=False, verbose=False):
         sys.stderr.write(log)
     subprocess.run([nvcc, "-ccbin", gxx, "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
                     "-o", LIB, o_cu, o_host, "-lcudart"], check=True)
+    build_pwnbench()
     return LIB
+
+
+BENCH_BIN = os.path.join(HERE, "pwnbench")
+
+
+def build_pwnbench():
+    """The headless C host (host/pwnbench.c): plain gcc against the two shared libraries."""
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    build_host()
+    subprocess.run([gcc, "-O2", "-Wall", "-I", INC, "-I", HOSTDIR, "-o", BENCH_BIN, os.path.join(HOSTDIR, "pwnbench.c"),
+                    "-L", HERE, "-lpwnhost", "-lpwntrace", "-Wl,-rpath,$ORIGIN", "-lm"], check=True)
+    return BENCH_BIN
 
 
 if __name__ == "__main__":

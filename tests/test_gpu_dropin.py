@@ -40,3 +40,37 @@ def test_reference_host_through_the_shim(refs, default_level, tmp_path):
                 assert (d <= 1).mean() >= (0.995 if shim.has_blur else 0.999)
         for r in (shim, ref):
             r.objs_clear()
+
+
+def test_pwnbench_c_host(tracer, default_level, tmp_path):
+    """The pure-C headless host (host/pwnbench.c: level.txt loader + camera script + C ABI) renders
+    the frames the Python client renders."""
+    import os
+    import re
+    import subprocess
+    from pwnfps_b200 import build
+    exe = build.BENCH_BIN
+    if not os.path.isfile(exe):
+        pytest.skip("pwnbench not built")
+    p = str(tmp_path / "level.txt")
+    default_level.save_txt(p)
+    w, h, n = 320, 200, 120
+    out = subprocess.run([exe, p, str(n), str(w), str(h), "1", "0"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    sums = {int(m.group(1)): int(m.group(2), 16) for m in re.finditer(r"frame\s+(\d+) fnv1a64 ([0-9a-f]{16})", out.stdout)}
+    assert 0 in sums and 100 in sums and "Mrays/s" in out.stdout
+    tracer.level_upload(default_level)
+    tracer.level_prepare_render()
+    tracer.frame_config(w, h)
+    poses = api.flythrough(default_level, n)
+
+    def fnv(a):
+        hsh = 0xcbf29ce484222325
+        for v in a.reshape(-1).tolist():
+            hsh = ((hsh ^ v) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+        return hsh
+
+    for f in (0, 100):
+        tracer.trace_cam(poses["cam"][f], w, h, float(poses["sec_current"][f]), api.PWN_F_BLUR)
+        s, _, _ = tracer.read_frame(want_z=False)
+        assert fnv(s) == sums[f], f
