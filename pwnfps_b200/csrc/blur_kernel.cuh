@@ -35,11 +35,21 @@ __device__ __forceinline__ float blur_randfs(uint32_t &seed)
 	return __fsub_rn(__fmul_rn((float)r, __uint_as_float(0x3A0B79B3u)), 1.0f);
 }
 
-// (int)float as cvttss2si does it: out of range and NaN give INT_MIN
-__device__ __forceinline__ int cvtt(float v)
+// (int)float as cvttss2si does it, FOLLOWED by the clamp to [0, hi] of screen.h:103-106.
+// cvttss2si gives INT_MIN for NaN and for anything outside int range, which the clamp turns into 0;
+// F2I.TRUNC saturates instead, so only v >= 2^31 needs a correction (NaN -> 0 and v < -2^31 ->
+// INT_MIN clamp to 0 either way).
+__device__ __forceinline__ int cvtt_clamp(float v, int hi)
 {
-	if(!(v < 2147483648.0f && v >= -2147483648.0f)) return (int)0x80000000;
-	return __float2int_rz(v);
+	int i = __float2int_rz(v);
+	if(v >= 2147483648.0f) i = 0;
+	return min(max(i, 0), hi);
+}
+
+// pavgb on four bytes at once: (a + b + 1) >> 1 per byte = (a | b) - (((a ^ b) >> 1) & 0x7f7f7f7f)
+__device__ __forceinline__ uint32_t pavgb4(uint32_t a, uint32_t b)
+{
+	return (a | b) - (((a ^ b) >> 1) & 0x7F7F7F7Fu);
 }
 
 // one output pixel of the blur pass (screen.h:91-117)
@@ -66,17 +76,13 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 	#pragma unroll
 	for(int i = 0; i < 4; i++)
 	{
-		int sx = cvtt(__fadd_rn(fbx, __fmul_rn(__fmul_rn(blur_randfs(seed), P.fstr), z)));
-		int sy = cvtt(__fadd_rn(fby, __fmul_rn(__fmul_rn(blur_randfs(seed), P.fstr), z)));
-		if(sx < 0) sx = 0;
-		if(sy < 0) sy = 0;
-		if(sx >= P.dimx) sx = P.dimx - 1;
-		if(sy >= P.dimy) sy = P.dimy - 1;
+		const int sx = cvtt_clamp(__fadd_rn(fbx, __fmul_rn(__fmul_rn(blur_randfs(seed), P.fstr), z)), P.dimx - 1);
+		const int sy = cvtt_clamp(__fadd_rn(fby, __fmul_rn(__fmul_rn(blur_randfs(seed), P.fstr), z)), P.dimy - 1);
 		s[i] = __ldg(&P.src[(size_t)sy*P.rwidth + sx]);
 		seed = (a6*seed + c6) & 0x7FFFFFFFu;
 	}
 	// pavgb: per byte (a+b+1)>>1 (screen.h:112-115)
-	P.dst[pix] = __vavgu4(__vavgu4(s[0], s[1]), __vavgu4(s[2], s[3]));
+	P.dst[pix] = pavgb4(pavgb4(s[0], s[1]), pavgb4(s[2], s[3]));
 }
 
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ BlurParams P)
