@@ -38,6 +38,51 @@ def run(name, lv, poses, w, h, tr, o):
     return len(bad)
 
 
+def vs_reference(tr, lv, poses, w, h):
+    """north_star acceptance against the REFERENCE ITSELF (oracle/_ref, shipped -ffast-math flags):
+    zbuf bit-exact; RGB within 1 LSB per channel on >= 99.9% of pixels."""
+    import tempfile
+    from oracle import refbind
+    from conftest import rgb_diff
+    if not refbind.available("libref.so"):
+        print("oracle/_ref not built: reference comparison skipped")
+        return 0
+    refs = {False: refbind.Ref("libref_noblur.so"), True: refbind.Ref("libref.so")}
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "level.txt")
+        lv.save_txt(p)
+        devnull, saved = os.open(os.devnull, os.O_WRONLY), os.dup(1)
+        os.dup2(devnull, 1)
+        try:
+            for r in refs.values():
+                r.level_load(p)
+        finally:
+            os.dup2(saved, 1)
+    tr.level_upload(lv)
+    tr.level_prepare_render()
+    tr.frame_config(w, h)
+    worst = {False: [1.0, 0, 0], True: [1.0, 0, 0]}
+    zbad = 0
+    for pz in poses:
+        for blur in (False, True):
+            tr.frame_clear()
+            tr.trace_cam(pz["cam"], w, h, float(pz["sec_current"]), api.PWN_F_BLUR if blur else 0)
+            s, z, _ = tr.read_frame()
+            rs, rz, _, _ = refs[blur].trace_frame(pz["cam"], float(pz["sec_current"]), w, h)
+            dd = rgb_diff(s, rs)
+            worst[blur][0] = min(worst[blur][0], float((dd <= 1).mean()))
+            worst[blur][1] += int((dd > 0).sum())
+            worst[blur][2] = max(worst[blur][2], int(dd.max()))
+            zbad += int((z.view(np.uint32) != rz.view(np.uint32)).sum())
+    n = len(poses) * w * h
+    for blur in (False, True):
+        print("vs reference (shipped flags), %d frames %dx%d, blur %s: worst frame has %.6f%% of pixels within 1 LSB; "
+              "%d of %d pixels differ at all (%.2e), max channel delta %d"
+              % (len(poses), w, h, "on" if blur else "off", 100 * worst[blur][0], worst[blur][1], n, worst[blur][1] / n, worst[blur][2]), flush=True)
+    print("vs reference: zbuf words that differ: %d" % zbad, flush=True)
+    return 0 if (zbad == 0 and worst[False][0] >= 0.999 and worst[True][0] >= 0.999) else 1
+
+
 def main():
     tr = api.Tracer(0)
     o = orcbind.Oracle()
@@ -52,6 +97,8 @@ def main():
         px["cam"][k] = api.mat4_roty(cam0, 1.5707964 + 0.4 * k)
         px["sec_current"][k] = 0.25 * k
     nbad += run("configs[2] mirror hall", hall, px, 1920, 1080, tr, o)
+    lv = levels.default_level()
+    nbad += vs_reference(tr, lv, api.flythrough(lv, 600)[::30], 1920, 1080)
     tr.close()
     return 1 if nbad else 0
 
