@@ -210,9 +210,11 @@ int pwn_trace_screen(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, floa
 
 /*
  * A scripted fly-through: n poses, frame i written to sbuf_host + i*rwidth*rheight
- * (pinned or pageable).  Trace of pose i+1 overlaps the device->host copy of
- * pose i (two device frames, two streams).  sbuf_host may be NULL: frames then
- * stay on the device.  sums, if non-NULL, receives one checksum per frame computed
+ * (pinned or pageable).  The batch is pipelined over three device frame sets and two
+ * streams: with PWN_F_BLUR the launch that traces pose i also blurs frame i-1 (chained by
+ * programmatic dependent launch), while frame i-2 is copied to the host.  sbuf_host may be
+ * NULL: frames then stay on the device (pwn_read_frame afterwards returns frame set 0, not
+ * necessarily the last pose).  sums, if non-NULL, receives one checksum per frame computed
  * on the device: sum over pixels i = y*dimx+x of mix64(i<<32 | sbuf[y][x]) mod 2^64,
  * mix64 = the splitmix64 finaliser (order independent, so it parallelises).
  */
