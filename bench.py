@@ -328,6 +328,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- the other BASELINE configs, device-timed on rank 0 (reported, not the headline) --------
     others = None
     if rank == 0 and world == 1 and not args.no_others:
+      try:
         others = {}
         for name, lvx, (ow, oh), nposes in (("mirror_hall_1080p (configs[2])", levels.mirror_hall(), (1920, 1080), 8),
                                             ("maze_10k_4k (configs[3])", levels.maze(dim=128, seed=1), (3840, 2160), 16),
@@ -356,11 +357,16 @@ def run_ours(args, rank, world, local_rank):
         tr.level_upload(lv)
         tr.level_prepare_render()
         tr.frame_config(w, h, want_ids=True)
+      except Exception as e:
+        others = {"error": "%s: %s" % (type(e).__name__, e)}
 
     band = None
     if world > 1:
         from pwnfps_b200 import shard
-        band = shard.bench_band_gather(tr, rank, world, local_rank, stream)
+        try:        # a side measurement must never take the headline line down with it
+            band = shard.bench_band_gather(tr, rank, world, local_rank, stream)
+        except Exception as e:
+            band = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank == 0:
         line = {
