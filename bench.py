@@ -330,13 +330,16 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_others:
       try:
         others = {}
-        for name, lvx, (ow, oh), nposes in (("mirror_hall_1080p (configs[2])", levels.mirror_hall(), (1920, 1080), 8),
+        for name, lvx, (ow, oh), nposes in (("default_level_14_spheres_1080p (game.lua:2-30)", levels.game_spheres(levels.default_level(), 0.3), (1920, 1080), 8),
+                                            ("mirror_hall_1080p (configs[2])", levels.mirror_hall(), (1920, 1080), 8),
                                             ("maze_10k_4k (configs[3])", levels.maze(dim=128, seed=1), (3840, 2160), 16),
                                             ("maze_10k_8k (configs[4], 1 GPU)", levels.maze(dim=128, seed=1), (7680, 4320), 16)):
             tr.level_upload(lvx)
             tr.level_prepare_render()
             tr.frame_config(ow, oh)
-            if "hall" in name:
+            if "spheres" in name:
+                px = api.flythrough(lvx, 8 * 20)[::20].copy()      # poses around the spawn, where the spheres are
+            elif "hall" in name:
                 cam0 = api.cam_spawn(lvx)
                 px = np.zeros(nposes, api.POSE_DTYPE)
                 for k in range(nposes):
