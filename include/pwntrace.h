@@ -252,6 +252,12 @@ int pwn_last_opcount(pwn_ctx *ctx, uint64_t *ops);
 int pwn_last_kernel_ms(pwn_ctx *ctx, float *k1_ms, float *k2_ms);
 /* run n frames of the same pose back to back on the device, return total K1(+K2) event time in ms */
 int pwn_time_frames(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags, int n, float *total_ms);
+/*
+ * Measured FP32 issue peak of this GPU in 10^12 lane-ops/s: a kernel of independent, non-fused
+ * FMUL/FADD chains (the trace may not use FMA: the reference build has none).  The denominator of
+ * the FP32 roofline, measured under the clocks of the moment.
+ */
+int pwn_fp32_peak(pwn_ctx *ctx, double *tlaneops);
 /* the CUDA stream the context launches on (cudaStream_t as an integer) */
 int pwn_stream(pwn_ctx *ctx, uint64_t *stream);
 

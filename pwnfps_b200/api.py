@@ -58,7 +58,7 @@ ABI_SYMBOLS = [
     "pwn_sync", "pwn_read_frame", "pwn_trace_screen", "pwn_trace_poses",
     "pwn_frame_device_ptrs", "pwn_frame_redirect", "pwn_frame_ipc_export",
     "pwn_frame_ipc_import", "pwn_frame_ipc_close", "pwn_host_alloc", "pwn_host_free",
-    "pwn_launch_count", "pwn_last_opcount", "pwn_last_kernel_ms", "pwn_time_frames", "pwn_stream",
+    "pwn_launch_count", "pwn_last_opcount", "pwn_last_kernel_ms", "pwn_time_frames", "pwn_fp32_peak", "pwn_stream",
 ]
 
 
@@ -107,6 +107,7 @@ def lib():
     L.pwn_last_opcount.argtypes = [vp, u64p]
     L.pwn_last_kernel_ms.argtypes = [vp, C.POINTER(f), C.POINTER(f)]
     L.pwn_time_frames.argtypes = [vp, vp, i, i, f, u, i, C.POINTER(f)]
+    L.pwn_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.pwn_stream.argtypes = [vp, u64p]
     _lib = L
     return L
@@ -483,6 +484,11 @@ class Tracer:
         t = C.c_float()
         _check(self.L.pwn_time_frames(self.h, cam.ctypes.data, dimx, dimy, float(sec_current), flags, n, C.byref(t)))
         return t.value
+
+    def fp32_peak(self):
+        v = C.c_double()
+        _check(self.L.pwn_fp32_peak(self.h, C.byref(v)))
+        return v.value
 
     def stream_ptr(self):
         s = C.c_uint64()

@@ -115,4 +115,24 @@ __global__ void __launch_bounds__(256) k_checksum(const uint32_t *buf, int dimx,
 	if((threadIdx.x & 31) == 0) atomicAdd(out, (unsigned long long)acc);
 }
 
+// ---- measured FP32 issue peak: 8 independent chains of non-fused FMUL/FADD per thread ----------
+// (the trace may not use FMA, so the relevant ceiling is one FP32 lane-op per lane per clock)
+__global__ void __launch_bounds__(256) k_fp32_peak(float *out, int iters, float a, float b)
+{
+	float v0 = threadIdx.x, v1 = v0 + 1.0f, v2 = v0 + 2.0f, v3 = v0 + 3.0f, v4 = v0 + 4.0f, v5 = v0 + 5.0f, v6 = v0 + 6.0f, v7 = v0 + 7.0f;
+	#pragma unroll 1
+	for(int i = 0; i < iters; i++)
+	{
+		#pragma unroll
+		for(int k = 0; k < 8; k++)
+		{
+			v0 = __fadd_rn(__fmul_rn(v0, a), b); v1 = __fadd_rn(__fmul_rn(v1, a), b);
+			v2 = __fadd_rn(__fmul_rn(v2, a), b); v3 = __fadd_rn(__fmul_rn(v3, a), b);
+			v4 = __fadd_rn(__fmul_rn(v4, a), b); v5 = __fadd_rn(__fmul_rn(v5, a), b);
+			v6 = __fadd_rn(__fmul_rn(v6, a), b); v7 = __fadd_rn(__fmul_rn(v7, a), b);
+		}
+	}
+	out[blockIdx.x*blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+}
+
 } // namespace pwn

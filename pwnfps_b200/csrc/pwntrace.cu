@@ -859,6 +859,37 @@ extern "C" int pwn_time_frames(pwn_ctx *ctx, const float cam[16], int dimx, int 
 	return PWN_OK;
 }
 
+extern "C" int pwn_fp32_peak(pwn_ctx *ctx, double *tlaneops)
+{
+	CTX_ENTER(ctx);
+	if(tlaneops == nullptr) return fail(PWN_E_ARG, "null pointer");
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, ctx->device));
+	const int blocks = prop.multiProcessorCount*8, threads = 256, iters = 4096;
+	float *d = nullptr;
+	CU(cudaMalloc(&d, sizeof(float)*(size_t)blocks*threads));
+	cudaEvent_t a, b;
+	CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+	float best = 1e30f;
+	for(int rep = 0; rep < 5; rep++)
+	{
+		CU(cudaEventRecord(a, ctx->stream));
+		k_fp32_peak<<<blocks, threads, 0, ctx->stream>>>(d, iters, 1.0000001f, 1e-7f);
+		CU(cudaGetLastError());
+		CU(cudaEventRecord(b, ctx->stream));
+		CU(cudaEventSynchronize(b));
+		float ms = 0.0f;
+		CU(cudaEventElapsedTime(&ms, a, b));
+		if(rep > 0 && ms < best) best = ms;
+		ctx->launches++;
+	}
+	cudaEventDestroy(a); cudaEventDestroy(b);
+	cudaFree(d);
+	const double ops = (double)blocks*threads*(double)iters*8.0*8.0*2.0;   // 8 unrolled x 8 chains x (mul + add)
+	*tlaneops = ops/((double)best*1e-3)/1e12;
+	return PWN_OK;
+}
+
 extern "C" int pwn_stream(pwn_ctx *ctx, uint64_t *stream)
 {
 	if(ctx == nullptr || stream == nullptr) return fail(PWN_E_ARG, "null pointer");
