@@ -137,6 +137,10 @@ def host():
     H.pwn_level_save_bin.argtypes = [C.POINTER(_CLevel), C.c_char_p]
     H.pwn_level_load_bin.restype = C.POINTER(_CLevel)
     H.pwn_level_load_bin.argtypes = [C.c_char_p]
+    H.pwn_game_init.argtypes = [C.c_void_p]
+    H.pwn_game_init.restype = None
+    H.pwn_game_tick.argtypes = [C.c_void_p, C.POINTER(_CLevel), C.c_double, C.c_double]
+    H.pwn_game_tick.restype = None
     H.pwn_cam_spawn.argtypes = [C.c_int, C.c_int, C.c_void_p]
     H.pwn_cam_spawn.restype = None
     H.pwn_mat4_roty.argtypes = [C.c_void_p, C.c_float]
@@ -289,6 +293,32 @@ def flythrough(lv, nframes):
     if rc != 0:
         raise PwnError(rc, "flythrough failed")
     return poses
+
+
+class Game:
+    """The reference's sphere script (game.lua) restated in C (host/pwn_game.c): 14 spheres that
+    rotate about a centre which walks through the level.  tick() returns SPHERE_DTYPE[14]."""
+    _SIZE = 14 * 8 * 8 + 5 * 8 + 14 * 40
+
+    def __init__(self, lv):
+        self.buf = (C.c_char * (self._SIZE + 64))()
+        self.lv = lv
+        self._clv = lv._to_c()
+        host().pwn_game_init(self.buf)
+
+    def spheres(self):
+        off = 14 * 8 * 8 + 5 * 8
+        return np.frombuffer(self.buf, dtype=SPHERE_DTYPE, count=14, offset=off).copy()
+
+    def tick(self, sec_current, sec_delta):
+        host().pwn_game_tick(self.buf, self._clv, float(sec_current), float(sec_delta))
+        return self.spheres()
+
+    def __del__(self):
+        try:
+            host().pwn_level_free(self._clv)
+        except Exception:
+            pass
 
 
 def ray_setup(cam, dimx, dimy):

@@ -4,11 +4,14 @@
  * (north_star item 4).  Pure C against the C ABI (include/pwntrace.h) and the host library
  * (pwn_level.h, pwn_camera.h); no Python, no torch.
  *
- *   pwnbench level.txt|level.pwnlv [frames=600] [width=1920] [height=1080] [blur=1] [device=0]
+ *   pwnbench level.txt|level.pwnlv [frames=600] [width=1920] [height=1080] [blur=1] [device=0] [spheres=0]
  *
  * Loads the level with the level.txt loader (level.h:107 restated in pwn_level.c), runs the
  * scripted fly-through (pwn_camera.c) through pwn_trace_poses into pinned host memory -- the
  * frame loop of main.c:93-109 -- and prints the throughput and one checksum per 100th frame.
+ * With spheres=1 the loop is the reference's frame by frame: on_tick moves the 14 spheres of
+ * game.lua (pwn_game.c), level_prepare_render becomes pwn_parts_upload, trace_screen_centred
+ * becomes pwn_trace_screen (main.c:95,107,127-140).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -18,6 +21,7 @@
 #include "pwntrace.h"
 #include "pwn_level.h"
 #include "pwn_camera.h"
+#include "pwn_game.h"
 
 #define CHECK(call) do { int rc_ = (call); if(rc_ != PWN_OK) { \
 	fprintf(stderr, "pwnbench: %s failed (%d): %s\n", #call, rc_, pwn_last_error()); return 2; } } while(0)
@@ -49,6 +53,7 @@ int main(int argc, char **argv)
 	int w = argc > 3 ? atoi(argv[3]) : 1920, h = argc > 4 ? atoi(argv[4]) : 1080;
 	unsigned flags = (argc > 5 ? atoi(argv[5]) : 1) ? PWN_F_BLUR : 0u;
 	int device = argc > 6 ? atoi(argv[6]) : 0;
+	int spheres = argc > 7 ? atoi(argv[7]) : 0;
 	size_t len = strlen(path);
 
 	pwn_level *lv = (len > 6 && strcmp(path + len - 6, ".pwnlv") == 0) ? pwn_level_load_bin(path) : pwn_level_load(path);
@@ -72,11 +77,26 @@ int main(int argc, char **argv)
 	CHECK(pwn_trace_poses(ctx, chunk < 8 ? chunk : 8, poses, w, h, flags, host, NULL));   /* warm-up */
 	double t0 = now_s();
 	int f;
-	for(f = 0; f < frames; f += chunk)
+	if(!spheres)
 	{
-		int n = frames - f < chunk ? frames - f : chunk;
-		CHECK(pwn_trace_poses(ctx, n, poses + f, w, h, flags, host, NULL));
-		printf("frame %4d fnv1a64 %016llx\n", f, (unsigned long long)fnv1a64(host, fpix));
+		for(f = 0; f < frames; f += chunk)
+		{
+			int n = frames - f < chunk ? frames - f : chunk;
+			CHECK(pwn_trace_poses(ctx, n, poses + f, w, h, flags, host, NULL));
+			printf("frame %4d fnv1a64 %016llx\n", f, (unsigned long long)fnv1a64(host, fpix));
+		}
+	}
+	else
+	{
+		pwn_game game;
+		pwn_game_init(&game);
+		for(f = 0; f < frames; f++)
+		{
+			CHECK(pwn_parts_upload(ctx, PWN_GAME_NSPH, game.sph));                       /* level_prepare_render, main.c:95 */
+			CHECK(pwn_trace_screen(ctx, poses[f].cam, w, h, poses[f].sec_current, flags, host, NULL));   /* main.c:107 */
+			if(f % 100 == 0) printf("frame %4d fnv1a64 %016llx\n", f, (unsigned long long)fnv1a64(host, fpix));
+			pwn_game_tick(&game, lv, poses[f].sec_current + 1.0/60.0, 1.0/60.0);         /* on_tick, main.c:127-140 */
+		}
 	}
 	double dt = now_s() - t0;
 	uint64_t launches = 0;

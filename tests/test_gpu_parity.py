@@ -176,6 +176,30 @@ def test_spheres(tracer, oracle):
     tracer.level_prepare_render()
 
 
+def test_game_script_spheres_frame_by_frame(tracer, oracle, default_level):
+    """the reference's frame loop with its sphere script (host/pwn_game.c restating game.lua):
+    on_tick, level_prepare_render (pwn_parts_upload), trace -- each frame bit-exact"""
+    lv = levels.default_level()
+    game = api.Game(lv)
+    tracer.level_upload(lv)
+    oracle.level_set(lv.cells, lv.portals_i32())
+    poses = api.flythrough(lv, 200)
+    hits = 0
+    for f in range(200):
+        sec = float(poses["sec_current"][f])
+        if f % 25 == 0:
+            lv.spheres = game.spheres()
+            tracer.level_prepare_render(lv)
+            oracle_set_level(oracle, lv)
+            check_frame(tracer, oracle, poses["cam"][f], sec, 320, 200, label="game %d" % f)
+            _, _, ids = tracer.read_frame(want_ids=True)
+            hits += int((ids["kind"] == 1).sum())
+        game.tick(sec + 1.0 / 60.0, 1.0 / 60.0)
+    assert hits > 500
+    lv.spheres = lv.spheres[:0]
+    tracer.level_prepare_render(lv)
+
+
 def test_many_spheres_on_the_maze(tracer, oracle):
     """3000 spheres binned per cell on the device side of pwn_parts_upload; sphere hits, sphere
     bounces and spheres seen through portals, bit-exact"""

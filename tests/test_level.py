@@ -124,3 +124,24 @@ def test_player_portal_traversal_keeps_the_view(oracle, default_level):
         d_cross = np.abs(before - after).mean()
         d_far = np.abs(before - far).mean()
         assert d_cross < 12.0 and d_cross < 0.5 * d_far, (j, d_cross, d_far)
+
+
+def test_game_script_spheres(default_level):
+    """host/pwn_game.c: the 14 spheres of game.lua start where the script creates them, keep their
+    radii, never enter a '.' cell (the script's only wall) and turn there."""
+    g = api.Game(default_level)
+    s0 = g.spheres()
+    assert len(s0) == 14
+    assert np.allclose(s0["pos"][0], (9.5, 0.3, 5.5, 1.0)) and np.isclose(s0["r"][0], 0.3) and np.isclose(s0["refl"][0], 0.6)
+    assert np.allclose(s0["pos"][2][:3], (9.8, 0.3, 5.5))
+    seen_cells = set()
+    sec = 0.0
+    for i in range(1200):
+        sp = g.tick(sec, 1.0 / 60.0)
+        sec += 1.0 / 60.0
+        cx, cz = int(np.floor(sp["pos"][0][0])), int(np.floor(sp["pos"][0][2]))
+        assert chr(default_level.cells[cz, cx]) != ".", (i, cx, cz)      # the script only turns at '.' (game.lua:70)
+        seen_cells.add((cx, cz))
+        assert np.isclose(np.hypot(sp["pos"][2][0] - sp["pos"][0][0], sp["pos"][2][2] - sp["pos"][0][2]), 0.3, atol=1e-5)
+    assert len(seen_cells) >= 5       # the cluster walks
+    assert set(np.round(g.spheres()["col"][1][:3].astype(np.float64), 3).tolist()) <= {0.3, 1.3}   # sphere 2 blinks (game.lua:36-40)
