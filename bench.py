@@ -363,6 +363,23 @@ def run_ours(args, rank, world, local_rank):
             msf = a.elapsed_time(b) / (3 * nposes)
             others[name] = {"resolution": [ow, oh], "poses": nposes, "ms_per_frame": msf,
                             "mrays_per_s": ow * oh / msf / 1e3, "frames_per_s": 1e3 / msf, "blur": bool(flags)}
+        # K3 = screen_upscale (screen.h:126-149) of the last 8K frame to a 16K surface and of a 4K frame
+        # to 8K: the one HBM-bound kernel of the path (4 B read + 4*rscale^2 B written per frame pixel)
+        for (ow, oh, rs) in ((7680, 4320, 2), (3840, 2160, 2), (1920, 1080, 4)):
+            tr.frame_config(ow, oh)
+            tr.trace_poses(px[:1], ow, oh, flags)
+            tr.screen_upscale(ow, oh, rs, read=False)
+            tot = 0.0
+            for _ in range(10):
+                l2_flush()
+                tr.screen_upscale(ow, oh, rs, read=False)
+                tot += tr.last_upscale_ms()
+            msu = tot / 10
+            nbytes = ow * oh * 4 * (1 + rs * rs)
+            others["screen_upscale_%dx%d_x%d (screen.h:126-149)" % (ow, oh, rs)] = {
+                "ms": msu, "algorithmic_bytes": nbytes,
+                "roofline": {"bound": "hbm", "achieved": nbytes / (msu * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": nbytes / (msu * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["source"]}}
         tr.level_upload(lv)
         tr.level_prepare_render()
         tr.frame_config(w, h, want_ids=True)

@@ -209,6 +209,20 @@ int pwn_trace_screen(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, floa
 	uint32_t *sbuf_host, float *zbuf_host);
 
 /*
+ * screen_upscale (screen.h:126-149) on the device: every pixel of the dimx x dimy frame in
+ * sbuf becomes an rscale x rscale block of a display surface of pitch_bytes per row
+ * (screen->pitch), at exactly the words the reference's pointer walk writes -- with a padded
+ * pitch (pitch_bytes/4 > dimx*rscale) that walk drifts by the padding per block row, and so
+ * does this.  The surface (dimy*rscale rows of pitch_bytes) stays on the device
+ * (pwn_surface_device_ptr); with pixels_host != NULL it is also copied there, synchronously.
+ * Words the reference leaves untouched are 0.
+ */
+int pwn_screen_upscale(pwn_ctx *ctx, int dimx, int dimy, int rscale, int pitch_bytes, void *pixels_host);
+int pwn_surface_device_ptr(pwn_ctx *ctx, uint64_t *surface_dev, uint64_t *bytes);
+/* device time in ms of the last pwn_screen_upscale kernel (CUDA events on the context stream; syncs) */
+int pwn_last_upscale_ms(pwn_ctx *ctx, float *k3_ms);
+
+/*
  * A scripted fly-through: n poses, frame i written to sbuf_host + i*rwidth*rheight
  * (pinned or pageable).  The batch is pipelined over three device frame sets and two
  * streams: with PWN_F_BLUR the launch that traces pose i also blurs frame i-1 (chained by

@@ -47,6 +47,7 @@ class Oracle:
         lib.orc_kat_rsqrt.restype = C.c_float
         lib.orc_kat_rsqrt.argtypes = [C.c_float]
         lib.orc_kat_libm.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_size_t]
+        lib.orc_upscale.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         self.dims = None
 
     def level_set(self, cells, portals):
@@ -110,6 +111,17 @@ class Oracle:
         out = ts.copy()
         zb = np.ascontiguousarray(zbuf, dtype=np.float32)
         self.lib.orc_blur(w, h, rwidth, y0, y1, out.ctypes.data, zb.ctypes.data, ts.ctypes.data, nthreads)
+        return out
+
+    def upscale(self, frame, rscale, pitch_words=None, w=None, h=None):
+        """screen_upscale (screen.h:126-149) of the top-left (h, w) of `frame`"""
+        frame = np.ascontiguousarray(frame, dtype=np.uint32)
+        h = frame.shape[0] if h is None else h
+        w = frame.shape[1] if w is None else w
+        pitch_words = w * rscale if pitch_words is None else pitch_words
+        out = np.zeros((h * rscale, pitch_words), np.uint32)
+        if self.lib.orc_upscale(frame.ctypes.data, w, h, frame.shape[1], rscale, pitch_words, out.ctypes.data) != 0:
+            raise RuntimeError("orc_upscale failed")
         return out
 
     def libm(self, x):

@@ -823,6 +823,28 @@ int orc_blur(int dimx, int dimy, int rwidth, int y0, int y1, uint32_t *sbuf, con
 	return 0;
 }
 
+/*
+ * screen_upscale (screen.h:126-149), restated by destination index: the reference's single
+ * running pointer puts sub-pixel (y, x) of source pixel (py, px) at word
+ * py*(w*rscale + pitch*(rscale-1)) + px*rscale + y*pitch + x of the surface.
+ */
+int orc_upscale(const uint32_t *frame, int w, int h, int rwidth, int rscale, int pitch_words, uint32_t *surface)
+{
+	int px, py, x, y;
+	const long long rowstep = (long long)w*rscale + (long long)pitch_words*(rscale - 1);
+	if(w <= 0 || h <= 0 || rscale < 1 || pitch_words < w*rscale) return -1;
+	for(py = 0; py < h; py++)
+	for(px = 0; px < w; px++)
+	{
+		const uint32_t pd = frame[(size_t)py*rwidth + px];
+		uint32_t *d = surface + py*rowstep + (long long)px*rscale;
+		for(y = 0; y < rscale; y++)
+		for(x = 0; x < rscale; x++)
+			d[(long long)y*pitch_words + x] = pd;
+	}
+	return 0;
+}
+
 /* known-answer helpers */
 void orc_kat_libm(const float *in, float *s, float *c, float *e, size_t n)
 {

@@ -333,6 +333,24 @@ double ref_time_frames(const float *cam16, float sec, int w, int h, int nthreads
 	return t1 - t0;
 }
 
+/*
+ * screen_upscale (screen.h:126-149) of a caller-supplied frame into a caller-supplied surface:
+ * the globals it reads (sbuf, rwidth, rheight, rscale, screen) are pointed at the arguments
+ * for the call and restored.
+ */
+int ref_screen_upscale(const uint32_t *frame, int w, int h, int scale, int pitch_bytes, void *pixels)
+{
+	SDL_Surface surf;
+	SDL_Surface *old_screen = screen;
+	uint32_t *old_sbuf = sbuf;
+	int ow = rwidth, oh = rheight, os = rscale;
+	surf.pitch = pitch_bytes; surf.pixels = pixels;
+	screen = &surf; sbuf = (uint32_t *)frame; rwidth = w; rheight = h; rscale = scale;
+	screen_upscale();
+	screen = old_screen; sbuf = old_sbuf; rwidth = ow; rheight = oh; rscale = os;
+	return 0;
+}
+
 int ref_max_threads(void)
 {
 #ifdef _OPENMP

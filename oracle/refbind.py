@@ -57,6 +57,8 @@ class Ref:
         lib.ref_rcpps.argtypes = [_f32p, _f32p, C.c_size_t]
         lib.ref_rsqrtps.argtypes = [_f32p, _f32p, C.c_size_t]
         lib.ref_libm.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_size_t]
+        if hasattr(lib, "ref_screen_upscale"):
+            lib.ref_screen_upscale.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         self.flags = lib.ref_flags()
         self.has_blur = bool(self.flags & 1)
         self.has_ids = bool(self.flags & 2)
@@ -121,6 +123,15 @@ class Ref:
 
     def max_threads(self):
         return self.lib.ref_max_threads()
+
+    def screen_upscale(self, frame, rscale, pitch_words=None):
+        """the reference's screen_upscale (screen.h:126-149) of a (h, w) uint32 frame"""
+        frame = np.ascontiguousarray(frame, dtype=np.uint32)
+        h, w = frame.shape
+        pitch_words = w * rscale if pitch_words is None else pitch_words
+        out = np.zeros((h * rscale, pitch_words), np.uint32)
+        self.lib.ref_screen_upscale(frame.ctypes.data, w, h, rscale, pitch_words * 4, out.ctypes.data)
+        return out
 
     # -- known-answer helpers ---------------------------------------------------
     def rcpps(self, x):

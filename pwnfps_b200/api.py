@@ -59,6 +59,7 @@ ABI_SYMBOLS = [
     "pwn_frame_device_ptrs", "pwn_frame_redirect", "pwn_frame_ipc_export",
     "pwn_frame_ipc_import", "pwn_frame_ipc_close", "pwn_host_alloc", "pwn_host_free",
     "pwn_launch_count", "pwn_last_opcount", "pwn_last_kernel_ms", "pwn_time_frames", "pwn_fp32_peak", "pwn_stream",
+    "pwn_screen_upscale", "pwn_surface_device_ptr", "pwn_last_upscale_ms",
 ]
 
 
@@ -109,6 +110,9 @@ def lib():
     L.pwn_time_frames.argtypes = [vp, vp, i, i, f, u, i, C.POINTER(f)]
     L.pwn_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.pwn_stream.argtypes = [vp, u64p]
+    L.pwn_screen_upscale.argtypes = [vp, i, i, i, i, vp]
+    L.pwn_surface_device_ptr.argtypes = [vp, u64p, u64p]
+    L.pwn_last_upscale_ms.argtypes = [vp, C.POINTER(f)]
     _lib = L
     return L
 
@@ -147,8 +151,31 @@ def host():
     H.pwn_mat4_roty.restype = None
     H.pwn_flythrough.argtypes = [C.POINTER(_CLevel), C.c_int, C.c_void_p]
     H.pwn_flythrough.restype = C.c_int
+    H.pwn_save_ppm.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    H.pwn_frame_diff.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     _host = H
     return H
+
+
+def save_ppm(path, sbuf, w=None, h=None):
+    """dump a (rheight, rwidth) uint32 frame (0xAARRGGBB) as a binary PPM"""
+    sbuf = np.ascontiguousarray(sbuf, dtype=np.uint32)
+    h = sbuf.shape[0] if h is None else h
+    w = sbuf.shape[1] if w is None else w
+    rc = host().pwn_save_ppm(os.fsencode(path), sbuf.ctypes.data, w, h, sbuf.shape[1])
+    if rc != 0:
+        raise OSError("pwn_save_ppm(%s) failed (%d)" % (path, rc))
+
+
+def frame_diff(a, b, gain=64):
+    """per colour byte |a - b| * gain, saturated: a frame that shows where two frames differ"""
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    b = np.ascontiguousarray(b, dtype=np.uint32)
+    assert a.shape == b.shape
+    out = np.zeros_like(a)
+    if host().pwn_frame_diff(a.ctypes.data, b.ctypes.data, out.ctypes.data, a.shape[1], a.shape[0], a.shape[1], gain) != 0:
+        raise ValueError("pwn_frame_diff failed")
+    return out
 
 
 def _check(rc):
@@ -456,6 +483,20 @@ class Tracer:
 
     def sync(self):
         _check(self.L.pwn_sync(self.h))
+
+    def screen_upscale(self, dimx, dimy, rscale, pitch_words=None, read=True):
+        """screen_upscale (screen.h:126-149) of the frame in sbuf; returns the surface as a
+        (dimy*rscale, pitch_words) uint32 array, or None with read=False (surface stays on the device)."""
+        pitch_words = dimx * rscale if pitch_words is None else pitch_words
+        out = np.zeros((dimy * rscale, pitch_words), np.uint32) if read else None
+        _check(self.L.pwn_screen_upscale(self.h, dimx, dimy, rscale, pitch_words * 4,
+                                         out.ctypes.data if read else None))
+        return out
+
+    def last_upscale_ms(self):
+        t = C.c_float()
+        _check(self.L.pwn_last_upscale_ms(self.h, C.byref(t)))
+        return t.value
 
     def read_frame(self, want_z=True, want_ids=False):
         sbuf = np.zeros((self.rheight, self.rwidth), np.uint32)

@@ -15,6 +15,7 @@
 
 #include "pwntrace.h"
 #include "trace_kernel.cuh"
+#include "upscale_kernel.cuh"
 
 using namespace pwn;
 
@@ -81,6 +82,10 @@ struct pwn_ctx
 	unsigned long long *d_sums = nullptr;
 	size_t sums_cap = 0;
 	unsigned long long *d_opcount = nullptr;
+	uint32_t *d_surface = nullptr;   // K3: the display surface (screen->pixels)
+	size_t surface_words = 0;
+	cudaEvent_t ev_k3a = nullptr, ev_k3b = nullptr;
+	bool timed_k3 = false;
 
 	int nshards = 1, shard = 0;
 	int libm_fma = 1;          // glibc build the reference host would run: 1 "_fma", 0 "_sse2"
@@ -120,6 +125,8 @@ extern "C" int pwn_create(pwn_ctx **out, int device)
 	CU(cudaEventCreate(&ctx->ev_k1a));
 	CU(cudaEventCreate(&ctx->ev_k1b));
 	CU(cudaEventCreate(&ctx->ev_k2b));
+	CU(cudaEventCreate(&ctx->ev_k3a));
+	CU(cudaEventCreate(&ctx->ev_k3b));
 	for(int i = 0; i < 3; i++)
 	{
 		CU(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
@@ -159,7 +166,8 @@ extern "C" int pwn_destroy(pwn_ctx *ctx)
 	cudaFree(ctx->d_rcp); cudaFree(ctx->d_rsqrt);
 	cudaFree(ctx->d_sph_pos); cudaFree(ctx->d_sph_col); cudaFree(ctx->d_sph_rr);
 	cudaFree(ctx->d_parts_off); cudaFree(ctx->d_parts_idx);
-	cudaFree(ctx->d_sums); cudaFree(ctx->d_opcount);
+	cudaFree(ctx->d_sums); cudaFree(ctx->d_opcount); cudaFree(ctx->d_surface);
+	cudaEventDestroy(ctx->ev_k3a); cudaEventDestroy(ctx->ev_k3b);
 	cudaEventDestroy(ctx->ev_k1a); cudaEventDestroy(ctx->ev_k1b); cudaEventDestroy(ctx->ev_k2b);
 	for(int i = 0; i < 3; i++) { cudaEventDestroy(ctx->ev_done[i]); cudaEventDestroy(ctx->ev_copied[i]); }
 	cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->copy_stream);
@@ -662,6 +670,77 @@ extern "C" int pwn_trace_screen(pwn_ctx *ctx, const float cam[16], int dimx, int
 	CU(cudaMemcpyAsync(sbuf_host, f.sbuf, n*4, cudaMemcpyDeviceToHost, ctx->stream));
 	if(zbuf_host) CU(cudaMemcpyAsync(zbuf_host, f.zbuf, n*4, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
+	return PWN_OK;
+}
+
+// ---- K3: screen_upscale (screen.h:126-149) ----------------------------------------------------------
+extern "C" int pwn_screen_upscale(pwn_ctx *ctx, int dimx, int dimy, int rscale, int pitch_bytes, void *pixels_host)
+{
+	CTX_ENTER(ctx);
+	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "pwn_screen_upscale before pwn_frame_config");
+	if(dimx <= 0 || dimy <= 0 || dimx > ctx->rwidth || dimy > ctx->rheight) return fail(PWN_E_ARG, "pwn_screen_upscale: bad size");
+	if(rscale < 1 || rscale > 64) return fail(PWN_E_ARG, "pwn_screen_upscale: rscale %d", rscale);
+	if(pitch_bytes <= 0 || (pitch_bytes & 3) || pitch_bytes/4 < dimx*rscale)
+		return fail(PWN_E_ARG, "pwn_screen_upscale: pitch %d bytes for %d pixels x %d", pitch_bytes, dimx, rscale);
+	UpscaleParams U;
+	U.src = ctx->fs[0].sbuf;
+	U.w = dimx; U.h = dimy; U.rwidth = ctx->rwidth; U.rscale = rscale;
+	U.pitch = pitch_bytes/4;
+	U.rowstep = (long long)dimx*rscale + (long long)U.pitch*(rscale - 1);
+	// the words the reference's walk can touch end at (h-1)*rowstep + (rscale-1)*pitch + w*rscale <= h*rscale*pitch
+	const size_t words = (size_t)dimy*rscale*U.pitch;
+	if(words > ctx->surface_words)
+	{
+		CU(cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_surface); ctx->d_surface = nullptr; ctx->surface_words = 0;
+		CU(cudaMalloc(&ctx->d_surface, words*4));
+		CU(cudaMemsetAsync(ctx->d_surface, 0, words*4, ctx->stream));
+		ctx->surface_words = words;
+	}
+	U.dst = ctx->d_surface;
+	CU(cudaEventRecord(ctx->ev_k3a, ctx->stream));
+	if(U.pitch == dimx*rscale && (U.pitch & 3) == 0 && (ctx->rwidth & 3) == 0)
+	{
+		dim3 grid((U.pitch/4 + 255)/256, dimy);
+		if(rscale == 1) k_upscale_packed<1><<<grid, 256, 0, ctx->stream>>>(U);
+		else if(rscale == 2) k_upscale_packed<2><<<grid, 256, 0, ctx->stream>>>(U);
+		else if(rscale == 4) k_upscale_packed<4><<<grid, 256, 0, ctx->stream>>>(U);
+		else k_upscale_packed<0><<<grid, 256, 0, ctx->stream>>>(U);
+	}
+	else
+	{
+		// padded pitch: the walk leaves words untouched; they read as 0 whatever the surface held before
+		CU(cudaMemsetAsync(ctx->d_surface, 0, words*4, ctx->stream));
+		dim3 grid((dimx*rscale + 255)/256, dimy);
+		k_upscale_any<<<grid, 256, 0, ctx->stream>>>(U);
+	}
+	CU(cudaGetLastError());
+	CU(cudaEventRecord(ctx->ev_k3b, ctx->stream));
+	ctx->timed_k3 = true;
+	ctx->launches++;
+	if(pixels_host != nullptr)
+	{
+		CU(cudaMemcpyAsync(pixels_host, ctx->d_surface, words*4, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+	}
+	return PWN_OK;
+}
+
+extern "C" int pwn_surface_device_ptr(pwn_ctx *ctx, uint64_t *surface_dev, uint64_t *bytes)
+{
+	if(ctx == nullptr) return fail(PWN_E_ARG, "null context");
+	if(surface_dev) *surface_dev = (uint64_t)(uintptr_t)ctx->d_surface;
+	if(bytes) *bytes = (uint64_t)ctx->surface_words*4;
+	return PWN_OK;
+}
+
+extern "C" int pwn_last_upscale_ms(pwn_ctx *ctx, float *k3_ms)
+{
+	CTX_ENTER(ctx);
+	if(k3_ms == nullptr) return fail(PWN_E_ARG, "null pointer");
+	CU(cudaStreamSynchronize(ctx->stream));
+	*k3_ms = 0.0f;
+	if(ctx->timed_k3) CU(cudaEventElapsedTime(k3_ms, ctx->ev_k3a, ctx->ev_k3b));
 	return PWN_OK;
 }
 

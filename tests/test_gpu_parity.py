@@ -259,6 +259,29 @@ def test_flythrough_frames_vs_oracle(tracer, oracle, default_level):
         check_frame(tracer, oracle, poses["cam"][i], float(poses["sec_current"][i]), 480, 270, label="fly %d" % i)
 
 
+def test_screen_upscale(tracer, oracle, default_level):
+    """K3 = screen_upscale (screen.h:126-149): packed path (pitch == w*rscale), the any-pitch path with
+    the reference's row drift, odd widths, and the committed reference fixture sizes"""
+    tracer.level_upload(default_level)
+    tracer.level_prepare_render()
+    cam = api.mat4_roty(api.cam_spawn(default_level), 0.9)
+    for (rw, rh, w, h) in [(320, 200, 320, 200), (96, 64, 50, 37), (33, 9, 33, 9), (130, 20, 129, 20)]:
+        tracer.frame_config(rw, rh)
+        tracer.frame_clear()
+        tracer.trace_cam(cam, w, h, 0.2, api.PWN_F_BLUR if w % 4 == 0 else 0)
+        s, _, _ = tracer.read_frame(want_z=False)
+        for rs in (1, 2, 3, 4, 7):
+            for pad in (0, 4, 5):
+                pitch = w * rs + pad
+                got = tracer.screen_upscale(w, h, rs, pitch)
+                want = oracle.upscale(s, rs, pitch, w=w, h=h)
+                assert np.array_equal(got, want), (rw, rh, w, h, rs, pad)
+    with pytest.raises(api.PwnError):
+        tracer.screen_upscale(w, h, 2, w)          # pitch too small
+    with pytest.raises(api.PwnError):
+        tracer.screen_upscale(w, h, 0)
+
+
 def test_ragged_and_tiny_frames(tracer, oracle, default_level):
     """edge sizes: single pixel, single row/column, widths that are not multiples of 4 or 32, and a
     trace window smaller than the frame (the reference indexes from (0,0) with stride rwidth,

@@ -145,3 +145,23 @@ def test_game_script_spheres(default_level):
         assert np.isclose(np.hypot(sp["pos"][2][0] - sp["pos"][0][0], sp["pos"][2][2] - sp["pos"][0][2]), 0.3, atol=1e-5)
     assert len(seen_cells) >= 5       # the cluster walks
     assert set(np.round(g.spheres()["col"][1][:3].astype(np.float64), 3).tolist()) <= {0.3, 1.3}   # sphere 2 blinks (game.lua:36-40)
+
+
+def test_ppm_dump_and_diff(tmp_path):
+    """host/pwn_image.c: the frame dump used for visual diffing"""
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 2**32, (7, 12), dtype=np.uint32)
+    p = str(tmp_path / "f.ppm")
+    api.save_ppm(p, a, w=10, h=6)
+    raw = open(p, "rb").read()
+    head = b"P6\n10 6\n255\n"
+    assert raw.startswith(head) and len(raw) == len(head) + 10 * 6 * 3
+    px = np.frombuffer(raw[len(head):], np.uint8).reshape(6, 10, 3)
+    assert (px[..., 0] == ((a[:6, :10] >> 16) & 255)).all()
+    assert (px[..., 1] == ((a[:6, :10] >> 8) & 255)).all()
+    assert (px[..., 2] == (a[:6, :10] & 255)).all()
+    b = a.copy()
+    b[2, 3] ^= 0x00010000          # one LSB of red
+    b[4, 5] ^= 0xFF000000          # alpha only: ignored
+    d = api.frame_diff(a, b, gain=64)
+    assert d[2, 3] == 64 << 16 and np.count_nonzero(d) == 1

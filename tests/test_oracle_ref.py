@@ -35,6 +35,23 @@ def test_util_kats(oracle):
         assert np.allclose(got, want, atol=1e-6)
 
 
+def test_upscale_golden(oracle):
+    """screen_upscale (screen.h:126-149) fixtures from the reference, incl. the padded-pitch drift"""
+    g = np.load(os.path.join(GOLDEN, "upscale.npz"))
+    for rs, pitch in g["cases"]:
+        got = oracle.upscale(g["frame"], int(rs), int(pitch))
+        assert np.array_equal(got, g["out_%d_%d" % (rs, pitch)]), (rs, pitch)
+
+
+def test_upscale_vs_reference(oracle, refs):
+    ref = refs("libref.so")
+    rng = np.random.default_rng(3)
+    for w, h, rs, pitch in [(64, 32, 1, None), (64, 32, 2, None), (33, 7, 3, None), (64, 16, 4, None),
+                            (20, 6, 2, 48), (20, 6, 5, 128), (1, 1, 7, 9)]:
+        f = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
+        assert np.array_equal(oracle.upscale(f, rs, pitch), ref.screen_upscale(f, rs, pitch)), (w, h, rs, pitch)
+
+
 def test_randfs_exhaustive_vs_reference(oracle, refs):
     """every residue r in 0..3758 gives the reference's float"""
     ref = refs("libref_noblur.so")

@@ -10,6 +10,7 @@ hot path compiled headless, oracle/make_ref.py).  Writes:
                                        device can reproduce that CPU anywhere
   tests/golden/kat_util.npz            known answers of util.h: randfs stream, col_ftoint,
                                        v_normalise, mat4_roty
+  tests/golden/upscale.npz             screen_upscale of a seeded frame for several (rscale, pitch)
   tests/golden/frames_default.npz      reference frames (sbuf pre-blur + blurred, zbuf, ids)
                                        on the default level: spawn pose 320x240
                                        and three more poses at 160x120
@@ -67,6 +68,13 @@ def main():
     roty = np.stack([ref.mat4_roty(eye, a) for a in angs])
     np.savez_compressed(os.path.join(gold, "kat_util.npz"), seeds=np.array(seeds, np.uint64), cols=cols, packed=packed,
                         vecs=vecs, norm=norm, angs=angs, roty=roty, **rs)
+
+    # screen_upscale (screen.h:126-149): exact and padded pitches
+    frame = np.random.default_rng(11).integers(0, 2**32, (9, 20), dtype=np.uint32)
+    ups = {"frame": frame, "cases": np.array([[1, 20], [2, 40], [3, 60], [4, 80], [1, 28], [2, 52], [3, 64]], np.int32)}
+    for rs_, pitch in ups["cases"]:
+        ups["out_%d_%d" % (rs_, pitch)] = refb.screen_upscale(frame, int(rs_), int(pitch))
+    np.savez_compressed(os.path.join(gold, "upscale.npz"), **ups)
 
     # frames
     out = {}
