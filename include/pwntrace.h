@@ -182,6 +182,13 @@ int pwn_trace_frame(pwn_ctx *ctx, const float from[4], const float rayb[4], cons
 	int dimx, int dimy, float sec_current, unsigned flags);
 
 /*
+ * REFLECT of defs.h:8 -- mirror bounce levels per pixel -- for hosts built with another value
+ * than the shipped 2.  0, 1 or 2; anything else is PWN_E_UNSUPPORTED.  (REFLECT_BLUR, defs.h:6,
+ * is the flag PWN_F_NO_REFLECT_BLUR; POSTPROC_BLUR, defs.h:7, is PWN_F_BLUR.)
+ */
+int pwn_trace_config(pwn_ctx *ctx, int reflect);
+
+/*
  * The blur pass alone (screen.h:69-123) over the frame currently in sbuf/zbuf: for
  * harnesses that trace row bands on several GPUs and gather them first.
  */

@@ -165,6 +165,10 @@ def main():
         cc("libref.so", [REF], [], REF_CFLAGS)
         cc("libref_noblur.so", [REF], ["REF_NO_BLUR"], REF_CFLAGS)
         cc("libref_strict.so", [REF], ["REF_NO_BLUR"], STRICT_CFLAGS)
+        # the compile-time switches of defs.h:6-8 (strict flags, so the restatement must match to the bit)
+        cc("libref_reflect0.so", [REF], ["REF_NO_BLUR", "REF_REFLECT=0"], STRICT_CFLAGS)
+        cc("libref_reflect1.so", [REF], ["REF_NO_BLUR", "REF_REFLECT=1"], STRICT_CFLAGS)
+        cc("libref_norblur.so", [REF], ["REF_NO_BLUR", "REF_NO_REFLECT_BLUR"], STRICT_CFLAGS)
 
         # the reference HOST (defs.h util.h level.h + this harness as main.c) with the product's
         # drop-in shim in place of trace.h/screen.h, linked against libpwntrace.so

@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "pwn_frame_device_ptrs", "pwn_frame_redirect", "pwn_frame_ipc_export",
     "pwn_frame_ipc_import", "pwn_frame_ipc_close", "pwn_host_alloc", "pwn_host_free",
     "pwn_launch_count", "pwn_last_opcount", "pwn_last_kernel_ms", "pwn_time_frames", "pwn_fp32_peak", "pwn_stream",
-    "pwn_screen_upscale", "pwn_surface_device_ptr", "pwn_last_upscale_ms",
+    "pwn_screen_upscale", "pwn_surface_device_ptr", "pwn_last_upscale_ms", "pwn_trace_config",
 ]
 
 
@@ -68,7 +68,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    path = os.environ.get("PWN_LIBPWNTRACE") or _build.build()   # the override is for A/B timing of experimental builds
     L = C.CDLL(path)
     vp, i, f, u = C.c_void_p, C.c_int, C.c_float, C.c_uint
     u64p = C.POINTER(C.c_uint64)
@@ -113,6 +113,7 @@ def lib():
     L.pwn_screen_upscale.argtypes = [vp, i, i, i, i, vp]
     L.pwn_surface_device_ptr.argtypes = [vp, u64p, u64p]
     L.pwn_last_upscale_ms.argtypes = [vp, C.POINTER(f)]
+    L.pwn_trace_config.argtypes = [vp, i]
     _lib = L
     return L
 
@@ -483,6 +484,10 @@ class Tracer:
 
     def sync(self):
         _check(self.L.pwn_sync(self.h))
+
+    def trace_config(self, reflect=2):
+        """REFLECT (defs.h:8): bounce levels, 0..2"""
+        _check(self.L.pwn_trace_config(self.h, reflect))
 
     def screen_upscale(self, dimx, dimy, rscale, pitch_words=None, read=True):
         """screen_upscale (screen.h:126-149) of the frame in sbuf; returns the surface as a

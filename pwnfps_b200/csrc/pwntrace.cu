@@ -88,6 +88,7 @@ struct pwn_ctx
 	bool timed_k3 = false;
 
 	int nshards = 1, shard = 0;
+	int reflect = 2;           // REFLECT as shipped (defs.h:8)
 	int libm_fma = 1;          // glibc build the reference host would run: 1 "_fma", 0 "_sse2"
 	unsigned long long launches = 0;
 	bool timed = false;        // events of the last trace are valid
@@ -578,6 +579,10 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 		P.opcount = ctx->d_opcount;
 	}
 	P.reflect_blur = (flags & PWN_F_NO_REFLECT_BLUR) ? 0 : 1;
+	P.reflect = ctx->reflect;
+	// a redirected frame lives on another GPU: whole 128-byte row segments per warp store cross NVLink
+	// at about twice the rate of the four 32-byte pieces an 8x4 warp tile would send
+	P.rowtile = (ctx->r_sbuf != nullptr) ? 1 : 0;
 	const bool blurp = blur && prev != nullptr && P.ids == nullptr;
 	if(blurp) P.prev = blur_params(ctx, prev->tsbuf, prev->zbuf, prev->sbuf, dimx, dimy);
 
@@ -608,6 +613,15 @@ extern "C" int pwn_trace_frame(pwn_ctx *ctx, const float from[4], const float ra
 	CTX_ENTER(ctx);
 	if(from == nullptr || rayb == nullptr || rdx == nullptr || rdy == nullptr) return fail(PWN_E_ARG, "pwn_trace_frame: null vector");
 	return launch_trace(ctx, ctx->fs[0], from, rayb, rdx, rdy, dimx, dimy, sec_current, flags, true);
+}
+
+extern "C" int pwn_trace_config(pwn_ctx *ctx, int reflect)
+{
+	if(ctx == nullptr) return fail(PWN_E_ARG, "null context");
+	// the kernel keeps the blend state of two bounce levels in registers
+	if(reflect < 0 || reflect > 2) return fail(PWN_E_UNSUPPORTED, "REFLECT %d: this build traces 0..2 bounce levels", reflect);
+	ctx->reflect = reflect;
+	return PWN_OK;
 }
 
 extern "C" int pwn_blur_frame(pwn_ctx *ctx, int dimx, int dimy)

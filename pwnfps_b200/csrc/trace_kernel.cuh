@@ -99,6 +99,8 @@ struct TraceParams
 	pwn_ids *ids;              // [rwidth*rheight][3] or null
 	unsigned long long *opcount; // IDS builds: sum of algorithmic FP32 lane-ops (DESIGN.md "Work model")
 	int reflect_blur;
+	int reflect;               // REFLECT (defs.h:8): bounce levels, 0..2
+	int rowtile;               // 1: a warp covers 32x1 pixels (128-byte row stores, for frames reached over NVLink) instead of 8x4
 	uint32_t zero;             // always 0; opaque to the compiler (see xmov)
 	BlurParams prev;           // BLURP builds: the blur pass of the PREVIOUS frame of a pose batch
 };
@@ -186,16 +188,21 @@ struct Aux   // nearest sphere so far (trace.h:196-200)
 constexpr int K1_ROWS = 4;
 constexpr int K1_THREADS = 32*K1_ROWS;
 constexpr int K1_MIN_CTAS = 8;   // 8 CTAs x 4 warps per SM at 64 registers; 9 (56 regs) and 10 (48 regs) spill and are slower
+#ifndef PWN_SPH_MIN_CTAS
+#define PWN_SPH_MIN_CTAS 8
+#endif
+constexpr int K1_MIN_CTAS_SPH = PWN_SPH_MIN_CTAS;   // with spheres the nearest-hit record adds 12 live registers
 
 template <bool SPH, bool IDS, bool LFMA, bool BLURP>
-__global__ void __launch_bounds__(K1_THREADS, K1_MIN_CTAS) k_trace(const __grid_constant__ TraceParams P)
+__global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTAS) k_trace(const __grid_constant__ TraceParams P)
 {
 	const LevelDev &L = P.lv;
 	__shared__ float s_ray[3][K1_ROWS][32];
 
 	// ---- pixel of this thread: CTA = 32x8 pixels, warp = 8x4 ----------------------
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int tx = (warp & 3)*8 + (lane & 7), ty = (warp >> 2)*4 + (lane >> 3);
+	const int tx = P.rowtile ? lane : (warp & 3)*8 + (lane & 7);
+	const int ty = P.rowtile ? warp : (warp >> 2)*4 + (lane >> 3);
 	const int x = blockIdx.x*32 + tx;
 	const int lrow0 = blockIdx.y*K1_ROWS;
 	// local row -> global row through the band interleave (8 | 32: a CTA never straddles bands)
@@ -604,7 +611,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_CTAS) k_trace(const __grid_
 		}
 
 		// ================= trace_hit_bounce, trace.h:3-106 =================
-		if(seg >= 2 || refl == 0.0f)   // REFLECT == 2 (defs.h:8)
+		if(seg >= P.reflect || refl == 0.0f)   // hitctr >= REFLECT (trace.h:6-7; REFLECT == 2 as shipped, defs.h:8)
 		{
 			ob = cb; og = cg; orr = cr; oa = ca;
 			break;

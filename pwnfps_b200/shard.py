@@ -168,6 +168,8 @@ def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), fr
 
     # gather: local trace, then one NCCL gather of the packed rows (sbuf)
     s, _ = frame_tensors(tr)
+    gather_frame(s, h, rank, world, dist)      # untimed: the first collective builds the NCCL communicator
+    torch.cuda.synchronize()
     tot_k = tot_g = 0.0
     for p in poses:
         dist.barrier()

@@ -259,6 +259,31 @@ def test_flythrough_frames_vs_oracle(tracer, oracle, default_level):
         check_frame(tracer, oracle, poses["cam"][i], float(poses["sec_current"][i]), 480, 270, label="fly %d" % i)
 
 
+def test_compile_time_switches(tracer, oracle, default_level):
+    """REFLECT 0 / 1 (pwn_trace_config) and REFLECT_BLUR off (PWN_F_NO_REFLECT_BLUR), defs.h:6-8"""
+    tracer.level_upload(default_level)
+    tracer.level_prepare_render()
+    oracle_set_level(oracle, default_level)
+    cam = api.mat4_roty(api.cam_spawn(default_level), 2.2)
+    w, h = 320, 200
+    tracer.frame_config(w, h)
+    try:
+        for reflect, rblur in ((0, True), (1, True), (2, False), (1, False)):
+            tracer.trace_config(reflect)
+            oracle.config(reflect, rblur)
+            tracer.frame_clear()
+            tracer.trace_cam(cam, w, h, 1.3, 0 if rblur else api.PWN_F_NO_REFLECT_BLUR)
+            s, z, _ = tracer.read_frame()
+            so, zo, _ = oracle.trace_frame(cam, 1.3, w, h)
+            assert (z.view(np.uint32) == zo.view(np.uint32)).all(), (reflect, rblur)
+            assert (s == so).all(), (reflect, rblur, int((s != so).sum()))
+        with pytest.raises(api.PwnError):
+            tracer.trace_config(3)
+    finally:
+        tracer.trace_config(2)
+        oracle.config(2, True)
+
+
 def test_screen_upscale(tracer, oracle, default_level):
     """K3 = screen_upscale (screen.h:126-149): packed path (pitch == w*rscale), the any-pitch path with
     the reference's row drift, odd widths, and the committed reference fixture sizes"""

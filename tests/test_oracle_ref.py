@@ -126,6 +126,32 @@ def test_default_level_vs_reference(oracle, refs, default_level, tmp_path):
             assert (oracle.blur(so, zo, w, h) == sb).all()
 
 
+def test_compile_time_switches_vs_reference(oracle, refs, default_level, tmp_path):
+    """REFLECT 0 / 1 and REFLECT_BLUR off (defs.h:6-8), each against the reference built that way
+    (strict flags: bit-exact)"""
+    from oracle import refbind
+    if not refbind.available("libref_reflect1.so"):
+        pytest.skip("oracle/_ref switch variants not built")
+    p = str(tmp_path / "level.txt")
+    default_level.save_txt(p)
+    oracle_set_level(oracle, default_level)
+    cam0 = api.cam_spawn(default_level)
+    try:
+        for variant, reflect, rblur in (("libref_reflect0.so", 0, True), ("libref_reflect1.so", 1, True),
+                                        ("libref_norblur.so", 2, False)):
+            ref = refs(variant)
+            ref.level_load(p)
+            oracle.config(reflect, rblur)
+            for yaw, sec, (w, h) in [(0.0, 0.0, (320, 240)), (2.2, 1.3, (333, 77))]:
+                cam = api.mat4_roty(cam0, yaw)
+                sr, zr, _, _ = ref.trace_frame(cam, sec, w, h)
+                so, zo, _ = oracle.trace_frame(cam, sec, w, h)
+                assert (zr.view(np.uint32) == zo.view(np.uint32)).all(), variant
+                assert (sr == so).all(), (variant, int((sr != so).sum()))
+    finally:
+        oracle.config(2, True)
+
+
 def test_flythrough_poses_vs_reference(oracle, refs, default_level, tmp_path):
     ref = refs("libref_ids.so")
     p = str(tmp_path / "level.txt")
