@@ -15,7 +15,7 @@ from pwnfps_b200 import api, levels  # noqa: E402
 
 def main():
     tr = api.Tracer(0)
-    stream = torch.cuda.ExternalStream(tr.stream())
+    stream = torch.cuda.ExternalStream(tr.stream_ptr(), device=torch.device("cuda", 0))
     out = []
     lvd = levels.default_level()
     mz = levels.maze(dim=128, seed=1)
