@@ -256,6 +256,26 @@ int pwn_frame_ipc_export(pwn_ctx *ctx, void *handle64, uint64_t *sbuf_off, uint6
 int pwn_frame_ipc_import(pwn_ctx *ctx, const void *handle64, uint64_t *base_dev);
 int pwn_frame_ipc_close(pwn_ctx *ctx, uint64_t base_dev);
 
+/*
+ * A sharded frame WITH the blur pass.  screen.h:69-123 gathers from anywhere in the pre-blur
+ * frame, so every shard needs all of it: with pwn_frame_peers set, pwn_trace_shard_blur
+ *   1. traces the own bands (pwn_shard_config) and stores every pixel into the pre-blur buffer
+ *      of EVERY shard -- the all-gather is part of the trace kernel, whole 128-byte row
+ *      segments over NVLink;
+ *   2. meets the other shards at a barrier on the device (flags in each frame allocation,
+ *      signalled and polled by a one-warp kernel in stream order; no host round trip);
+ *   3. blurs the own bands from the local copy and stores them into shard 0's sbuf;
+ *   4. meets them again: on return of a later pwn_sync, shard 0's frame is complete and the
+ *      pre-blur buffers may be overwritten by the next frame.
+ * base_dev[s] = device address of shard s's frame allocation in THIS process (pwn_frame_ipc_import
+ * of the handle shard s exported; the own entry is ignored).  All shards must configure the same
+ * frame size and call pwn_trace_shard_blur the same number of times.  nshards == 0 clears.
+ * A shard that never arrives ends the wait after 4 s; pwn_frame_peers_status then reports 1.
+ */
+int pwn_frame_peers(pwn_ctx *ctx, int nshards, const uint64_t *base_dev);
+int pwn_trace_shard_blur(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags);
+int pwn_frame_peers_status(pwn_ctx *ctx, int *timed_out);
+
 /* pinned host memory for frames (cudaHostAlloc): what pwn_trace_poses copies into at full PCIe rate */
 int pwn_host_alloc(void **out, size_t bytes);
 int pwn_host_free(void *p);

@@ -60,6 +60,7 @@ ABI_SYMBOLS = [
     "pwn_frame_ipc_import", "pwn_frame_ipc_close", "pwn_host_alloc", "pwn_host_free",
     "pwn_launch_count", "pwn_last_opcount", "pwn_last_kernel_ms", "pwn_time_frames", "pwn_fp32_peak", "pwn_stream",
     "pwn_screen_upscale", "pwn_surface_device_ptr", "pwn_last_upscale_ms", "pwn_trace_config",
+    "pwn_frame_peers", "pwn_trace_shard_blur", "pwn_frame_peers_status",
 ]
 
 
@@ -114,6 +115,9 @@ def lib():
     L.pwn_surface_device_ptr.argtypes = [vp, u64p, u64p]
     L.pwn_last_upscale_ms.argtypes = [vp, C.POINTER(f)]
     L.pwn_trace_config.argtypes = [vp, i]
+    L.pwn_frame_peers.argtypes = [vp, i, u64p]
+    L.pwn_trace_shard_blur.argtypes = [vp, vp, i, i, f, u]
+    L.pwn_frame_peers_status.argtypes = [vp, C.POINTER(i)]
     _lib = L
     return L
 
@@ -578,6 +582,23 @@ class Tracer:
 
     def frame_redirect(self, sbuf_dev, zbuf_dev, tsbuf_dev):
         _check(self.L.pwn_frame_redirect(self.h, sbuf_dev, zbuf_dev, tsbuf_dev))
+
+    def frame_peers(self, bases):
+        """bases[s] = device address (in this process) of shard s's frame allocation; None/[] clears"""
+        if not bases:
+            _check(self.L.pwn_frame_peers(self.h, 0, None))
+            return
+        arr = (C.c_uint64 * len(bases))(*[int(b or 0) for b in bases])
+        _check(self.L.pwn_frame_peers(self.h, len(bases), arr))
+
+    def trace_shard_blur(self, cam, dimx, dimy, sec_current, flags=0):
+        cam = np.ascontiguousarray(cam, dtype=np.float32).reshape(16)
+        _check(self.L.pwn_trace_shard_blur(self.h, cam.ctypes.data, dimx, dimy, float(sec_current), flags))
+
+    def peers_timed_out(self):
+        v = C.c_int()
+        _check(self.L.pwn_frame_peers_status(self.h, C.byref(v)))
+        return bool(v.value)
 
     def ipc_export(self):
         hnd = (C.c_char * 64)()

@@ -20,6 +20,7 @@ struct BlurParams
 	const uint2 *jump;     // per 4-pixel group g: the affine map (A, C) that advances a row's stream by 32*g draws
 	int dimx, dimy, rwidth;
 	int y0, y1;            // rows to produce
+	int nshards, shard;    // rows y0 + the 32-row bands b with b % nshards == shard (1, 0: all rows)
 	float fstr;            // 0.002f * dimy (screen.h:86), computed on the host in float
 };
 
@@ -88,9 +89,45 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ BlurParams P)
 {
 	const int x = blockIdx.x*blockDim.x + threadIdx.x;
-	const int y = P.y0 + blockIdx.y;
+	const int lrow = blockIdx.y;
+	const int y = P.y0 + ((lrow >> 5)*P.nshards + P.shard)*32 + (lrow & 31);
 	if(x >= P.dimx || y >= P.y1) return;
 	blur_pixel(P, x, y);
+}
+
+// ---- barrier between the GPUs of a sharded frame, on the device ---------------------------------
+// Lane t signals shard t (stores this launch's epoch into its own slot of t's flag array, over
+// NVLink) and then waits for t's signal in the local array.  Launched in stream order after the
+// kernel whose stores it publishes; a peer that never arrives ends the wait after `timeout_ns`
+// with the error word set instead of hanging the GPU.
+struct BarrierParams
+{
+	uint32_t *peer_flags[8];   // flag array of every shard (own entry = local)
+	uint32_t *local;           // [0..7] barrier A, [8..15] barrier B, [16] error
+	int nshards, shard, slot;
+	uint32_t epoch;
+	unsigned long long timeout_ns;
+};
+
+__global__ void k_peer_barrier(const BarrierParams B)
+{
+	const int t = threadIdx.x;
+	if(t >= B.nshards || t == B.shard) return;
+	__threadfence_system();
+	uint32_t *remote = B.peer_flags[t] + B.slot*8 + B.shard;
+	asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(remote), "r"(B.epoch) : "memory");
+	const uint32_t *mine = B.local + B.slot*8 + t;
+	unsigned long long t0, t1;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+	for(;;)
+	{
+		uint32_t v;
+		asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+		if((int32_t)(v - B.epoch) >= 0) break;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+		if(t1 - t0 > B.timeout_ns) { B.local[16] = 1u; break; }
+		__nanosleep(200);
+	}
 }
 
 // ---- order-independent frame checksum: sum_i mix64(i<<32 | word_i) mod 2^64 ----------

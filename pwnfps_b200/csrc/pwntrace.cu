@@ -43,7 +43,8 @@ struct FrameSet
 	void *base = nullptr;      // one allocation: sbuf | tsbuf | zbuf  (so one IPC handle covers the frame)
 	uint32_t *sbuf = nullptr, *tsbuf = nullptr;
 	float *zbuf = nullptr;
-	size_t off_sbuf = 0, off_tsbuf = 0, off_zbuf = 0, bytes = 0;
+	uint32_t *flags = nullptr; // 64 words after the planes: inter-GPU barrier flags (k_peer_barrier)
+	size_t off_sbuf = 0, off_tsbuf = 0, off_zbuf = 0, off_flags = 0, bytes = 0;
 };
 
 struct pwn_ctx
@@ -89,6 +90,11 @@ struct pwn_ctx
 
 	int nshards = 1, shard = 0;
 	int reflect = 2;           // REFLECT as shipped (defs.h:8)
+	// sharded frame with the blur pass: the other shards' frame allocations (pwn_frame_peers)
+	char *peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	int npeer_shards = 0;
+	uint32_t epoch = 0;
+	bool allgather_now = false;   // launch_trace: trace into the pre-blur buffer here and on every peer, no blur
 	int libm_fma = 1;          // glibc build the reference host would run: 1 "_fma", 0 "_sse2"
 	unsigned long long launches = 0;
 	bool timed = false;        // events of the last trace are valid
@@ -449,9 +455,10 @@ extern "C" int pwn_frame_config(pwn_ctx *ctx, int rwidth, int rheight, int want_
 		for(int i = 0; i < 3; i++)
 		{
 			FrameSet &f = ctx->fs[i];
-			f.bytes = 3*plane;
+			f.bytes = 3*plane + 256;
 			CU(cudaMalloc(&f.base, f.bytes));
-			f.off_sbuf = 0; f.off_tsbuf = plane; f.off_zbuf = 2*plane;
+			f.off_sbuf = 0; f.off_tsbuf = plane; f.off_zbuf = 2*plane; f.off_flags = 3*plane;
+			f.flags = (uint32_t *)((char *)f.base + f.off_flags);
 			f.sbuf = (uint32_t *)((char *)f.base + f.off_sbuf);
 			f.tsbuf = (uint32_t *)((char *)f.base + f.off_tsbuf);
 			f.zbuf = (float *)((char *)f.base + f.off_zbuf);
@@ -467,6 +474,9 @@ extern "C" int pwn_frame_config(pwn_ctx *ctx, int rwidth, int rheight, int want_
 		CU(cudaMalloc(&ctx->d_jump, ngroups*sizeof(uint2)));
 		CU(cudaMemcpy(ctx->d_jump, jt.data(), ngroups*sizeof(uint2), cudaMemcpyHostToDevice));
 		ctx->rwidth = rwidth; ctx->rheight = rheight;
+		for(int t = 0; t < 8; t++) ctx->peer_base[t] = nullptr;
+		ctx->npeer_shards = 0;
+		ctx->epoch = 0;
 	}
 	if(want_ids && ctx->d_ids == nullptr)
 	{
@@ -481,7 +491,8 @@ extern "C" int pwn_frame_clear(pwn_ctx *ctx)
 {
 	CTX_ENTER(ctx);
 	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "pwn_frame_clear before pwn_frame_config");
-	for(int i = 0; i < 3; i++) CU(cudaMemsetAsync(ctx->fs[i].base, 0, ctx->fs[i].bytes, ctx->stream));
+	// the planes only: the barrier flags behind them carry the epoch of the last sharded frame
+	for(int i = 0; i < 3; i++) CU(cudaMemsetAsync(ctx->fs[i].base, 0, ctx->fs[i].off_flags, ctx->stream));
 	if(ctx->d_ids) CU(cudaMemsetAsync(ctx->d_ids, 0xFF, (size_t)ctx->rwidth*ctx->rheight*3*sizeof(pwn_ids), ctx->stream));
 	return PWN_OK;
 }
@@ -500,13 +511,14 @@ static BlurParams blur_params(pwn_ctx *ctx, const uint32_t *src, const float *z,
 	BlurParams B;
 	B.src = src; B.zbuf = z; B.dst = dst; B.jump = ctx->d_jump;
 	B.dimx = dimx; B.dimy = dimy; B.rwidth = ctx->rwidth; B.y0 = 0; B.y1 = dimy;
+	B.nshards = 1; B.shard = 0;
 	B.fstr = 0.002f * (float)dimy;   // screen.h:86
 	return B;
 }
 
-static int launch_blur(pwn_ctx *ctx, const BlurParams &B)
+static int launch_blur(pwn_ctx *ctx, const BlurParams &B, int nrows = -1)
 {
-	dim3 grid((B.dimx + 255)/256, B.dimy), block(256);
+	dim3 grid((B.dimx + 255)/256, nrows < 0 ? B.dimy : nrows), block(256);
 	k_blur<<<grid, block, 0, ctx->stream>>>(B);
 	CU(cudaGetLastError());
 	ctx->launches++;
@@ -549,7 +561,7 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 	if(ctx->nsph > 0 && from[3] != ctx->sph_w)
 		return fail(PWN_E_UNSUPPORTED, "camera w (%g) differs from sphere w (%g)", from[3], ctx->sph_w);
 	if((flags & PWN_F_IDS) && ctx->d_ids == nullptr) return fail(PWN_E_STATE, "PWN_F_IDS without pwn_frame_config(want_ids)");
-	if((flags & PWN_F_BLUR) && ctx->nshards > 1)
+	if((flags & PWN_F_BLUR) && ctx->nshards > 1 && !ctx->allgather_now)
 		return fail(PWN_E_UNSUPPORTED, "blur needs the whole pre-blur frame: gather the bands, then pwn_blur_frame");
 
 	TraceParams P;
@@ -583,6 +595,13 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 	// a redirected frame lives on another GPU: whole 128-byte row segments per warp store cross NVLink
 	// at about twice the rate of the four 32-byte pieces an 8x4 warp tile would send
 	P.rowtile = (ctx->r_sbuf != nullptr) ? 1 : 0;
+	if(ctx->allgather_now)
+	{
+		P.sbuf = f.tsbuf; P.zbuf = f.zbuf;
+		for(int t = 0; t < ctx->nshards; t++)
+			if(t != ctx->shard) P.peer[P.npeers++] = (uint32_t *)(ctx->peer_base[t] + f.off_tsbuf);
+		P.rowtile = 1;
+	}
 	const bool blurp = blur && prev != nullptr && P.ids == nullptr;
 	if(blurp) P.prev = blur_params(ctx, prev->tsbuf, prev->zbuf, prev->sbuf, dimx, dimy);
 
@@ -598,7 +617,7 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 		ctx->launches++;
 		if(timing) { CU(cudaEventRecord(ctx->ev_k1b, ctx->stream)); ctx->timed = true; }
 	}
-	if(blur && !defer_blur)
+	if(blur && !defer_blur && !ctx->allgather_now)
 	{
 		int rc = launch_blur(ctx, blur_params(ctx, tsb, P.zbuf, sb, dimx, dimy));
 		if(rc != PWN_OK) return rc;
@@ -613,6 +632,90 @@ extern "C" int pwn_trace_frame(pwn_ctx *ctx, const float from[4], const float ra
 	CTX_ENTER(ctx);
 	if(from == nullptr || rayb == nullptr || rdx == nullptr || rdy == nullptr) return fail(PWN_E_ARG, "pwn_trace_frame: null vector");
 	return launch_trace(ctx, ctx->fs[0], from, rayb, rdx, rdy, dimx, dimy, sec_current, flags, true);
+}
+
+// ---- sharded frame WITH the blur pass: all-gather fused into K1, device-side barriers, sharded K2 -----
+extern "C" int pwn_frame_peers(pwn_ctx *ctx, int nshards, const uint64_t *base_dev)
+{
+	if(ctx == nullptr) return fail(PWN_E_ARG, "null context");
+	for(int t = 0; t < 8; t++) ctx->peer_base[t] = nullptr;
+	ctx->npeer_shards = 0;
+	if(nshards == 0) return PWN_OK;
+	if(nshards < 2 || nshards > 8 || base_dev == nullptr) return fail(PWN_E_ARG, "pwn_frame_peers: %d shards (2..8)", nshards);
+	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "pwn_frame_peers before pwn_frame_config");
+	if(nshards != ctx->nshards) return fail(PWN_E_STATE, "pwn_frame_peers: %d shards but pwn_shard_config says %d", nshards, ctx->nshards);
+	for(int t = 0; t < nshards; t++)
+	{
+		ctx->peer_base[t] = (t == ctx->shard) ? (char *)ctx->fs[0].base : (char *)(uintptr_t)base_dev[t];
+		if(ctx->peer_base[t] == nullptr) return fail(PWN_E_ARG, "pwn_frame_peers: null frame for shard %d", t);
+	}
+	ctx->npeer_shards = nshards;
+	return PWN_OK;
+}
+
+static int launch_barrier(pwn_ctx *ctx, int slot)
+{
+	BarrierParams B;
+	memset(&B, 0, sizeof(B));
+	for(int t = 0; t < ctx->nshards; t++) B.peer_flags[t] = (uint32_t *)(ctx->peer_base[t] + ctx->fs[0].off_flags);
+	B.local = ctx->fs[0].flags;
+	B.nshards = ctx->nshards; B.shard = ctx->shard; B.slot = slot; B.epoch = ctx->epoch;
+	B.timeout_ns = 4000000000ull;
+	k_peer_barrier<<<1, 32, 0, ctx->stream>>>(B);
+	CU(cudaGetLastError());
+	ctx->launches++;
+	return PWN_OK;
+}
+
+extern "C" int pwn_trace_shard_blur(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags)
+{
+	CTX_ENTER(ctx);
+	if(cam == nullptr) return fail(PWN_E_ARG, "pwn_trace_shard_blur: null cam");
+	if(ctx->npeer_shards != ctx->nshards || ctx->nshards < 2) return fail(PWN_E_STATE, "pwn_trace_shard_blur before pwn_frame_peers");
+	if(ctx->r_sbuf || ctx->r_zbuf || ctx->r_tsbuf) return fail(PWN_E_STATE, "pwn_trace_shard_blur with a redirected frame");
+	if(dimx <= 0 || dimy <= 0) return fail(PWN_E_ARG, "pwn_trace_shard_blur: bad size");
+	float rayb[4], rdx[4], rdy[4];
+	pwn_ray_setup(cam, dimx, dimy, rayb, rdx, rdy);
+	const FrameSet &f = ctx->fs[0];
+	ctx->epoch++;
+	// K1: own bands into the pre-blur buffer of every shard (and zbuf here)
+	ctx->allgather_now = true;
+	int rc = launch_trace(ctx, f, cam + 12, rayb, rdx, rdy, dimx, dimy, sec_current, (flags | PWN_F_BLUR) & ~PWN_F_IDS, true);
+	ctx->allgather_now = false;
+	if(rc != PWN_OK) return rc;
+	if(!ctx->timed) { CU(cudaEventRecord(ctx->ev_k1a, ctx->stream)); CU(cudaEventRecord(ctx->ev_k1b, ctx->stream)); ctx->timed = true; }
+	// A: every shard's bands have landed everywhere
+	rc = launch_barrier(ctx, 0);
+	if(rc != PWN_OK) return rc;
+	// K2 on the own bands, straight into shard 0's frame
+	const int nbands = (dimy + 31)/32;
+	const int nb_local = nbands > ctx->shard ? (nbands - ctx->shard + ctx->nshards - 1)/ctx->nshards : 0;
+	if(nb_local > 0)
+	{
+		BlurParams B = blur_params(ctx, f.tsbuf, f.zbuf, (uint32_t *)(ctx->peer_base[0] + f.off_sbuf), dimx, dimy);
+		B.nshards = ctx->nshards; B.shard = ctx->shard;
+		rc = launch_blur(ctx, B, nb_local*32);
+		if(rc != PWN_OK) return rc;
+	}
+	// B: every shard's blurred bands are in shard 0's frame, and nobody still reads a pre-blur
+	// buffer that the next frame's K1 will overwrite
+	rc = launch_barrier(ctx, 1);
+	if(rc != PWN_OK) return rc;
+	CU(cudaEventRecord(ctx->ev_k2b, ctx->stream));
+	ctx->timed_blur = true;
+	return PWN_OK;
+}
+
+extern "C" int pwn_frame_peers_status(pwn_ctx *ctx, int *timed_out)
+{
+	CTX_ENTER(ctx);
+	if(timed_out == nullptr) return fail(PWN_E_ARG, "null pointer");
+	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "no frame configured");
+	uint32_t v = 0;
+	CU(cudaMemcpyAsync(&v, ctx->fs[0].flags + 16, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	*timed_out = (int)v;
+	return PWN_OK;
 }
 
 extern "C" int pwn_trace_config(pwn_ctx *ctx, int reflect)

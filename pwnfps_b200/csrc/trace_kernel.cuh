@@ -100,6 +100,8 @@ struct TraceParams
 	unsigned long long *opcount; // IDS builds: sum of algorithmic FP32 lane-ops (DESIGN.md "Work model")
 	int reflect_blur;
 	int reflect;               // REFLECT (defs.h:8): bounce levels, 0..2
+	uint32_t *peer[7];         // the same pre-blur buffer on the other shards' GPUs (pwn_frame_peers): every pixel is
+	int npeers;                // stored there too -- the all-gather the sharded blur pass needs, fused into the trace
 	int rowtile;               // 1: a warp covers 32x1 pixels (128-byte row stores, for frames reached over NVLink) instead of 8x4
 	uint32_t zero;             // always 0; opaque to the compiler (see xmov)
 	BlurParams prev;           // BLURP builds: the blur pass of the PREVIOUS frame of a pose batch
@@ -727,7 +729,9 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 	}
 
 	// ---- col_ftoint (util.h:48-59): B | G<<8 | R<<16 | A<<24 ------------------------------
-	P.sbuf[pix] = pack_lane(ob) | (pack_lane(og) << 8) | (pack_lane(orr) << 16) | (pack_lane(oa) << 24);
+	const uint32_t word = pack_lane(ob) | (pack_lane(og) << 8) | (pack_lane(orr) << 16) | (pack_lane(oa) << 24);
+	P.sbuf[pix] = word;
+	for(int p = 0; p < P.npeers; p++) P.peer[p][pix] = word;
 
 	// ---- pose batches: this thread also blurs its pixel of the previous frame (screen.h:69-123),
 	// whose trace ran in the previous launch.  The launches are chained with programmatic dependent

@@ -101,6 +101,27 @@ def close_peer_frame(tr, base):
         tr.ipc_close(base)
 
 
+def open_all_peers(tr, rank, world, dist):
+    """Sharded frame with the blur pass: every rank opens every other rank's frame allocation
+    (CUDA IPC) and hands the list to pwn_frame_peers.  Returns the imported bases to close later."""
+    handle = tr.ipc_export()[0]
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(handle))
+    bases = [0] * world
+    for r in range(world):
+        if r != rank:
+            bases[r] = tr.ipc_import(handles[r])
+    tr.frame_peers(bases)
+    return bases
+
+
+def close_all_peers(tr, bases):
+    tr.frame_peers(None)
+    for b in bases:
+        if b:
+            tr.ipc_close(b)
+
+
 def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), frames=16):
     """BASELINE configs[4]: one 8K frame of the 10k-sector maze, row bands over `world` GPUs,
     assembled on GPU 0; device-timed, max over ranks.  Returns a dict on every rank."""
@@ -165,6 +186,44 @@ def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), fr
     except api.PwnError as e:
         out["fused_error"] = str(e)
         tr.frame_redirect(0, 0, 0)
+
+    # the same frames WITH the blur pass: all-gather fused into K1, device-side barriers, every
+    # shard blurs its own bands into GPU 0's frame (pwn_trace_shard_blur); against it, the blur of
+    # the gathered frame on GPU 0 alone
+    try:
+        want_b = tr_sums_blur = None
+        tr.shard_config(1, 0)
+        if rank == 0:
+            want_b = tr.trace_poses(poses, w, h, api.PWN_F_BLUR, want_sums=True)
+            tr.trace_cam(poses[0]["cam"], w, h, float(poses[0]["sec_current"]), api.PWN_F_BLUR)
+            out["blur_on_gpu0_ms"] = tr.last_kernel_ms()[1]
+        tr.shard_config(world, rank)
+        dist.barrier()
+        bases = open_all_peers(tr, rank, world, dist)
+        got = []
+        for it in range(2):
+            t1 = t2 = 0.0
+            for k, p in enumerate(poses):
+                dist.barrier()
+                tr.trace_shard_blur(p["cam"], w, h, float(p["sec_current"]))
+                a, b = tr.last_kernel_ms()
+                t1 += a
+                t2 += b
+                if it == 1 and k % 4 == 0 and rank == 0:
+                    s0, _, _ = tr.read_frame(want_z=False)
+                    got.append(int(api.checksum_ref(s0, w, h)))
+        out["sharded_blur_trace_ms"] = allmax(t1) / frames
+        out["sharded_blur_rest_ms"] = allmax(t2) / frames
+        out["sharded_blur_ms"] = allmax(t1 + t2) / frames
+        out["sharded_blur_mrays"] = w * h / out["sharded_blur_ms"] / 1e3
+        timed_out = tr.peers_timed_out()
+        dist.barrier()
+        close_all_peers(tr, bases)
+        if rank == 0:
+            out["sharded_blur_frames_equal_one_gpu"] = bool(got == [int(v) for v in want_b[::4]]) and not timed_out
+    except api.PwnError as e:
+        out["sharded_blur_error"] = str(e)
+        tr.frame_peers(None)
 
     # gather: local trace, then one NCCL gather of the packed rows (sbuf)
     s, _ = frame_tensors(tr)

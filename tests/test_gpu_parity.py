@@ -508,3 +508,50 @@ def test_error_paths(tracer, default_level):
     with pytest.raises(api.PwnError):
         tracer.level_upload(api.Level(cells, default_level.portals))
     tracer.level_upload(default_level)
+
+
+def test_sharded_blur_allgather_in_one_process(tracer, default_level):
+    """A sharded frame WITH the blur pass (pwn_frame_peers + pwn_trace_shard_blur): three contexts on
+    one GPU stand in for three GPUs -- every K1 stores its bands into all three pre-blur buffers, the
+    device-side barrier kernels meet across the three streams, every shard blurs its own bands into
+    shard 0's frame.  Result = the one-context blurred frame, bit for bit, frame after frame."""
+    n = 3
+    ts = [tracer] + [api.Tracer(0) for _ in range(n - 1)]
+    try:
+        w, h = 640, 360
+        cam0 = api.cam_spawn(default_level)
+        cams = [api.mat4_roty(cam0, a) for a in (2.0, 0.4, 4.1, 5.5)]
+        for t in ts:
+            t.level_upload(default_level)
+            t.level_prepare_render()
+            t.frame_config(w, h)
+            t.frame_clear()
+        tracer.shard_config(1, 0)
+        want = []
+        for k, cam in enumerate(cams):
+            tracer.trace_cam(cam, w, h, 0.3 * k, api.PWN_F_BLUR)
+            want.append(tracer.read_frame(want_z=False)[0])
+        bases = [t.device_ptrs()[0] for t in ts]       # sbuf is at offset 0 of the frame allocation
+        for r, t in enumerate(ts):
+            t.shard_config(n, r)
+            t.frame_peers(bases)
+        for k, cam in enumerate(cams):
+            if k == 2:
+                ts[0].frame_clear()                    # must not disturb the barrier epochs
+            for t in ts:
+                t.trace_shard_blur(cam, w, h, 0.3 * k)
+            for t in ts:
+                t.sync()
+            assert not any(t.peers_timed_out() for t in ts)
+            got = ts[0].read_frame(want_z=False)[0]
+            assert (got == want[k]).all(), (k, int((got != want[k]).sum()))
+            k1, k2 = ts[0].last_kernel_ms()
+            assert k1 > 0 and k2 > 0
+        with pytest.raises(api.PwnError):
+            ts[1].frame_peers(bases[:2])               # disagrees with pwn_shard_config
+    finally:
+        for t in ts:
+            t.frame_peers(None)
+            t.shard_config(1, 0)
+        for t in ts[1:]:
+            t.close()
