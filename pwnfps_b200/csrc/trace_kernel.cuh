@@ -189,10 +189,17 @@ struct Aux   // nearest sphere so far (trace.h:196-200)
 // CTA = 32 x K1_ROWS pixels, K1_ROWS/4 ... one warp per 8x4 pixels
 constexpr int K1_ROWS = 4;
 constexpr int K1_THREADS = 32*K1_ROWS;
-constexpr int K1_MIN_CTAS = 8;   // 8 CTAs x 4 warps per SM at 64 registers; 9 (56 regs) and 10 (48 regs) spill and are slower
+#ifndef PWN_MIN_CTAS
+#define PWN_MIN_CTAS 8
+#endif
+constexpr int K1_MIN_CTAS = PWN_MIN_CTAS;   // 8 CTAs x 4 warps per SM at 64 registers; 9 (56 regs) and 10 (48 regs) spill and are slower
 #ifndef PWN_SPH_MIN_CTAS
 #define PWN_SPH_MIN_CTAS 8
 #endif
+#ifndef PWN_WALK_UNROLL
+#define PWN_WALK_UNROLL 1
+#endif
+constexpr int K1_WALK_UNROLL = PWN_WALK_UNROLL;   // 1: the walk stays rolled (measured: see DESIGN.md)
 constexpr int K1_MIN_CTAS_SPH = PWN_SPH_MIN_CTAS;   // with spheres the nearest-hit record adds 12 live registers
 
 template <bool SPH, bool IDS, bool LFMA, bool BLURP>
@@ -322,7 +329,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 		cell = __ldg(&L.cellmap[ci]); } while(0)
 
 		// ================= trace.h:250-675: the walk =================
-		#pragma unroll 1
+		#pragma unroll K1_WALK_UNROLL
 		for(int maxsteps = 1000; maxsteps > 0; maxsteps--)
 		{
 			if(IDS) nstep++;
