@@ -144,6 +144,7 @@ def host():
     H.pwn_level_derive.argtypes = [C.POINTER(_CLevel)]
     H.pwn_level_save_txt.argtypes = [C.POINTER(_CLevel), C.c_char_p]
     H.pwn_level_save_bin.argtypes = [C.POINTER(_CLevel), C.c_char_p]
+    H.pwn_level_save_txtx.argtypes = [C.POINTER(_CLevel), C.c_char_p]
     H.pwn_level_load_bin.restype = C.POINTER(_CLevel)
     H.pwn_level_load_bin.argtypes = [C.c_char_p]
     H.pwn_game_init.argtypes = [C.c_void_p]
@@ -261,6 +262,15 @@ class Level:
         H = host()
         p = self._to_c()
         rc = H.pwn_level_save_bin(p, os.fsencode(path))
+        H.pwn_level_free(p)
+        if rc != 0:
+            raise PwnError(-1, "cannot write %s" % path)
+
+    def save_txtx(self, path):
+        """extended text format "!pwnlv" (pwn_level.h): level.txt rules on any grid, '@' cells for pairs >= 26"""
+        H = host()
+        p = self._to_c()
+        rc = H.pwn_level_save_txtx(p, os.fsencode(path))
         H.pwn_level_free(p)
         if rc != 0:
             raise PwnError(-1, "cannot write %s" % path)

@@ -134,10 +134,13 @@ int pwn_level_link(pwn_level *lv)
 typedef struct { const unsigned char *p, *end; } rd_t;
 static int rd_getc(rd_t *r) { return r->p < r->end ? *r->p++ : -1; }
 
+static pwn_level *parse_extended(const char *text, size_t len);
+
 pwn_level *pwn_level_parse(const char *text, size_t len)
 {
 	int x, z;
 	rd_t r;
+	if(len >= 6 && memcmp(text, "!pwnlv", 6) == 0) return parse_extended(text, len);
 	r.p = (const unsigned char *)text; r.end = r.p + len;
 	pwn_level *lv = pwn_level_new(64, 64, 26);
 	if(lv == NULL) return NULL;
@@ -171,6 +174,108 @@ pwn_level *pwn_level_parse(const char *text, size_t len)
 done_load:
 	pwn_level_derive(lv);
 	return lv;
+}
+
+/*
+ * The extended text format (pwn_level.h): the same grid alphabet and the same per-character rules
+ * as level.h:107-228, on a w x h grid, with '@' cells named by trailing "@ id x z" lines.
+ */
+static pwn_level *parse_extended(const char *text, size_t len)
+{
+	int w = 0, h = 0, np = 0, x, z, used = 0;
+	char *copy = malloc(len + 1);
+	if(copy == NULL) return NULL;
+	memcpy(copy, text, len);
+	copy[len] = 0;
+	if(sscanf(copy, "!pwnlv %d %d %d%n", &w, &h, &np, &used) != 3 || w < 1 || h < 1 || w > 4096 || h > 4096 || np < 26 || np > (1 << 22))
+	{ free(copy); return NULL; }
+	pwn_level *lv = pwn_level_new(w, h, np);
+	if(lv == NULL) { free(copy); return NULL; }
+	rd_t r;
+	r.p = (const unsigned char *)copy + used; r.end = (const unsigned char *)copy + len;
+	while(r.p < r.end && *r.p != '\n') r.p++;      /* rest of the header line */
+	if(r.p < r.end) r.p++;
+	for(z = 0; z < h; z++)
+	{
+		for(x = 0; x < w; x++)
+		{
+			int c = rd_getc(&r);
+			if(c == -1 || c == '\r' || c == '\n')
+			{
+				if(c == -1) goto grid_done;
+				else if(x == 0) { x--; continue; }
+				else break;
+			}
+			if(x == 0 && c == '@' && r.p < r.end && *r.p == ' ') { r.p--; goto grid_done; }   /* fewer than h rows: the '@' lines begin */
+			if(c == '*') { c = ';'; lv->sx = x; lv->sz = z; }
+			if(c >= 'a' && c <= 'z'-1)
+			{
+				portal_register(&lv->portals[c-'a'], x, z);
+				c = (c-'a')+'A' + 1;
+			}
+			if(c >= 'A' && c <= 'Z') portal_register(&lv->portals[c-'A'], x, z);
+			lv->cells[z*w + x] = c;
+		}
+		if(x == w)   /* a full row: drop the rest of its line, as a 64-wide row of the reference drops nothing */
+		{
+			while(r.p < r.end && *r.p != '\n') r.p++;
+		}
+	}
+grid_done:
+	/* "@ id x z": the '@' cell at (x, z) belongs to portal pair id >= 26; registration in line order */
+	{
+		const char *q = (const char *)r.p;
+		while(q < copy + len)
+		{
+			int id, px, pz;
+			if(*q == '@' && sscanf(q, "@ %d %d %d", &id, &px, &pz) == 3)
+			{
+				if(id < 26 || id >= np || px < 0 || pz < 0 || px >= w || pz >= h || lv->cells[pz*w + px] != '@')
+				{ pwn_level_free(lv); free(copy); return NULL; }
+				lv->cells[pz*w + px] = PWN_PORTAL_CODE(id);
+				portal_register(&lv->portals[id], px, pz);
+			}
+			while(q < copy + len && *q != '\n') q++;
+			if(q < copy + len) q++;
+		}
+	}
+	free(copy);
+	pwn_level_derive(lv);
+	return lv;
+}
+
+int pwn_level_save_txtx(const pwn_level *lv, const char *fname)
+{
+	int x, z;
+	for(z = 0; z < lv->h; z++)
+	for(x = 0; x < lv->w; x++)
+	{
+		int32_t c = lv->cells[z*lv->w + x];
+		if(c >= 0x100) { if(PWN_PORTAL_INDEX(c) >= lv->nportals) return -1; continue; }
+		if(c < 32 || c > 126 || c == '*' || c == '@' || (c >= 'a' && c <= 'z')) return -1;
+	}
+	FILE *fp = fopen(fname, "wb");
+	if(fp == NULL) return -1;
+	fprintf(fp, "!pwnlv %d %d %d\n", lv->w, lv->h, lv->nportals < 26 ? 26 : lv->nportals);
+	for(z = 0; z < lv->h; z++)
+	{
+		for(x = 0; x < lv->w; x++)
+		{
+			int32_t c = lv->cells[z*lv->w + x];
+			if(c >= 0x100) c = '@';
+			else if(x == lv->sx && z == lv->sz && c == ';') c = '*';
+			fputc(c, fp);
+		}
+		fputc('\n', fp);
+	}
+	/* row-major, so that reading registers the ends in the order pwn_level_link does */
+	for(z = 0; z < lv->h; z++)
+	for(x = 0; x < lv->w; x++)
+	{
+		int32_t c = lv->cells[z*lv->w + x];
+		if(c >= 0x100) fprintf(fp, "@ %d %d %d\n", PWN_PORTAL_INDEX(c), x, z);
+	}
+	return fclose(fp) == 0 ? 0 : -1;
 }
 
 pwn_level *pwn_level_load(const char *fname)

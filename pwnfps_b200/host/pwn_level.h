@@ -52,6 +52,20 @@ int32_t pwn_level_get_cell(const pwn_level *lv, int cx, int cz);
 int pwn_level_save_txt(const pwn_level *lv, const char *fname);
 
 /*
+ * Extended text format for levels beyond the reference's limits, read by
+ * pwn_level_load / pwn_level_parse when the file starts with "!pwnlv":
+ *   !pwnlv <w> <h> <nportals>          nportals >= 26
+ *   <h rows of <= w characters>        the level.txt alphabet and rules (level.h:107-228: '*' spawn,
+ *                                      letters, the lower-case double registration, short rows,
+ *                                      blank lines); '@' = a cell of a portal pair with id >= 26
+ *   @ <id> <x> <z>                     one line per '@' cell; the first two of an id are its ends
+ *                                      (a line starting "@ " also ends a grid of fewer than h rows)
+ * A level that fits 64x64 / 26 letters should be kept as plain level.txt (pwn_level_save_txt),
+ * which the reference's own loader reads.  pwn_level_save_txtx writes this format for any level.
+ */
+int pwn_level_save_txtx(const pwn_level *lv, const char *fname);
+
+/*
  * Binary level file for levels beyond the reference's limits: little endian,
  *   char magic[8] = "PWNLV001"; int32 w, h, nportals, sx, sz;
  *   int32 cells[h*w]; pwn_portal portals[nportals] (as derived: rot12, c1, c2 included).

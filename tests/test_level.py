@@ -165,3 +165,37 @@ def test_ppm_dump_and_diff(tmp_path):
     b[4, 5] ^= 0xFF000000          # alpha only: ignored
     d = api.frame_diff(a, b, gain=64)
     assert d[2, 3] == 64 << 16 and np.count_nonzero(d) == 1
+
+
+def test_extended_text_format(tmp_path):
+    """the "!pwnlv" text format (SURVEY 8f-3): level.txt rules on any grid, '@' cells for pairs >= 26;
+    a level round-trips through it, and the default level written in it loads as level.txt does"""
+    lv = levels.maze(dim=128, seed=1)
+    assert len(lv.portals) > 26
+    p = str(tmp_path / "maze.pwnlv.txt")
+    lv.save_txtx(p)
+    assert open(p, "rb").read(6) == b"!pwnlv"
+    back = api.level_load(p)
+    assert back.cells.shape == lv.cells.shape and (back.cells == lv.cells).all()
+    assert (back.sx, back.sz) == (lv.sx, lv.sz)
+    assert len(back.portals) == len(lv.portals)
+    assert (back.portals_i32() == lv.portals_i32()).all()
+    d = levels.default_level()
+    p2 = str(tmp_path / "default.pwnlv.txt")
+    d.save_txtx(p2)
+    p3 = str(tmp_path / "default.txt")
+    d.save_txt(p3)                      # (both writers start from the cells: the lower-case marks are gone)
+    back, plain = api.level_load(p2), api.level_load(p3)
+    assert (back.cells == plain.cells).all() and (back.portals_i32() == plain.portals_i32()).all()
+    assert (back.sx, back.sz) == (plain.sx, plain.sz)
+    # hand-written: short rows, blank line, CRLF, lower-case double registration, one '@' pair + a stray third
+    txt = b"!pwnlv 70 5 30\r\n" + b"." * 70 + b"\r\n\r\n" + b".*;;a;;@;;@;;@.\n" + b".;;;A;;;;;;;;;.\n" + b"...\n" + b"@ 27 7 1\n@ 27 10 1\n@ 27 13 1\n"
+    lv2 = api.level_parse(txt)
+    assert lv2.cells.shape == (5, 70) and (lv2.sx, lv2.sz) == (1, 1)
+    assert lv2.cells[1, 4] == ord("B") and lv2.cells[2, 4] == ord("A")      # 'a' registers in A, becomes B
+    pm = lv2.portals_i32()
+    assert tuple(pm[0][:4]) == (4, 1, 4, 2) and tuple(pm[1][:3]) == (4, 1, -1)
+    assert lv2.cells[1, 7] == 0x100 + 27 and tuple(pm[27][:4]) == (7, 1, 10, 1)   # third '@' cell ignored by the table
+    assert lv2.cells[1, 13] == 0x100 + 27
+    with pytest.raises(api.PwnError):
+        api.level_parse(b"!pwnlv 10 10 30\n..@..\n@ 5 2 0\n")      # id < 26 must be written as a letter
