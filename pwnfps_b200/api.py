@@ -276,10 +276,9 @@ class Level:
             raise PwnError(-1, "cannot write %s" % path)
 
     def save_txt(self, path):
+        """level.txt as the reference's loader reads it (64x64 / 26 letters; lower-case marks restored)"""
         H = host()
-        p = H.pwn_level_new(self.w, self.h, len(self.portals))
-        C.memmove(p.contents.cells, self.cells.ctypes.data, self.cells.nbytes)
-        p.contents.sx, p.contents.sz = self.sx, self.sz
+        p = self._to_c()
         rc = H.pwn_level_save_txt(p, os.fsencode(path))
         H.pwn_level_free(p)
         if rc != 0:

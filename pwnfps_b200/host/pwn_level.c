@@ -135,6 +135,7 @@ typedef struct { const unsigned char *p, *end; } rd_t;
 static int rd_getc(rd_t *r) { return r->p < r->end ? *r->p++ : -1; }
 
 static pwn_level *parse_extended(const char *text, size_t len);
+static int32_t cell_as_written(const pwn_level *lv, int x, int z);
 
 pwn_level *pwn_level_parse(const char *text, size_t len)
 {
@@ -262,9 +263,7 @@ int pwn_level_save_txtx(const pwn_level *lv, const char *fname)
 		for(x = 0; x < lv->w; x++)
 		{
 			int32_t c = lv->cells[z*lv->w + x];
-			if(c >= 0x100) c = '@';
-			else if(x == lv->sx && z == lv->sz && c == ';') c = '*';
-			fputc(c, fp);
+			fputc(c >= 0x100 ? '@' : cell_as_written(lv, x, z), fp);
 		}
 		fputc('\n', fp);
 	}
@@ -298,6 +297,23 @@ pwn_level *pwn_level_load(const char *fname)
 	return lv;
 }
 
+/*
+ * The character a cell was loaded from.  level.h:144-161 turns a lower-case letter into the NEXT
+ * upper-case one after registering the cell as an end of its own pair: a cell 'L'+1 that the table
+ * lists as an end of pair L was written in lower case.
+ */
+static int32_t cell_as_written(const pwn_level *lv, int x, int z)
+{
+	int32_t c = lv->cells[z*lv->w + x];
+	if(c >= 'B' && c <= 'Z' && c - 'B' < lv->nportals)
+	{
+		const pwn_portal *pm = &lv->portals[c - 'B'];
+		if((pm->x1 == x && pm->z1 == z) || (pm->x2 == x && pm->x2 != -1 && pm->z2 == z)) return (c - 'B') + 'a';
+	}
+	if(x == lv->sx && z == lv->sz && c == ';') return '*';
+	return c;
+}
+
 int pwn_level_save_txt(const pwn_level *lv, const char *fname)
 {
 	int x, z;
@@ -314,9 +330,7 @@ int pwn_level_save_txt(const pwn_level *lv, const char *fname)
 	{
 		for(x = 0; x < lv->w; x++)
 		{
-			int32_t c = lv->cells[z*lv->w + x];
-			if(x == lv->sx && z == lv->sz && c == ';') c = '*';
-			fputc(c, fp);
+			fputc(cell_as_written(lv, x, z), fp);
 		}
 		fputc('\n', fp);
 	}

@@ -259,6 +259,17 @@ def test_flythrough_frames_vs_oracle(tracer, oracle, default_level):
         check_frame(tracer, oracle, poses["cam"][i], float(poses["sec_current"][i]), 480, 270, label="fly %d" % i)
 
 
+def test_lowercase_portal_quirk(tracer, oracle, default_level):
+    """pair M of level.txt leads into a cell that answers as the unpaired N (level.h:144-161)"""
+    tracer.level_upload(default_level)
+    tracer.level_prepare_render()
+    oracle_set_level(oracle, default_level)
+    for (x, z, yaw) in [(4.5, 2.5, 0.0), (4.3, 2.2, 0.3), (4.5, 5.5, 3.1415927), (5.5, 2.5, 5.9)]:
+        cam = api.mat4_roty(api.cam_spawn(default_level), yaw)
+        cam[12], cam[14] = x, z
+        check_frame(tracer, oracle, cam, 0.5, 320, 200, label="quirk %g %g %g" % (x, z, yaw))
+
+
 def test_compile_time_switches(tracer, oracle, default_level):
     """REFLECT 0 / 1 (pwn_trace_config) and REFLECT_BLUR off (PWN_F_NO_REFLECT_BLUR), defs.h:6-8"""
     tracer.level_upload(default_level)

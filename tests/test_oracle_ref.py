@@ -152,6 +152,28 @@ def test_compile_time_switches_vs_reference(oracle, refs, default_level, tmp_pat
         oracle.config(2, True)
 
 
+def test_lowercase_portal_quirk_vs_reference(oracle, refs, default_level, tmp_path):
+    """level.txt:5 has a lower-case 'm': the cell joins pair M and then BECOMES 'N' (level.h:144-161), so
+    M at (4,3) leads into a cell that answers as the unpaired N.  Poses that look straight at both."""
+    ref, strict = refs("libref_ids.so"), refs("libref_strict.so")
+    p = str(tmp_path / "level.txt")
+    default_level.save_txt(p)
+    for r in (ref, strict):
+        r.level_load(p)
+    cells, pm = ref.level_get()
+    assert (cells == default_level.cells).all() and cells[4, 4] == ord("N")
+    assert tuple(pm[12][:4]) == (4, 3, 4, 4) and pm[13][2] == -1
+    oracle_set_level(oracle, default_level)
+    saw = 0
+    for (x, z, yaw) in [(4.5, 2.5, 0.0), (4.3, 2.2, 0.3), (4.5, 5.5, 3.1415927), (5.5, 2.5, 5.9)]:
+        cam = api.mat4_roty(api.cam_spawn(default_level), yaw)
+        cam[12], cam[14] = x, z
+        s, z_, so, zo = _compare(oracle, ref, strict, cam, 0.5, 320, 200)
+        _, _, ids = oracle.trace_frame(cam, 0.5, 320, 200, want_ids=True)
+        saw += int((ids[..., 0]["nportal"] > 0).sum())
+    assert saw > 1000          # primary rays did cross M
+
+
 def test_flythrough_poses_vs_reference(oracle, refs, default_level, tmp_path):
     ref = refs("libref_ids.so")
     p = str(tmp_path / "level.txt")
