@@ -269,6 +269,28 @@ def run_ours(args, rank, world, local_rank):
     e2e_ms = allmax(sum(ms_e2e))
     e2e_value = float(e2e_steps) * FRAMES * w * h * world / (e2e_ms * 1e-3) / 1e6
 
+    # ---- the drop-in call itself, frame by frame (trace_screen_centred -> pwn_trace_screen): no pipelining
+    # across frames, the frame is complete in the host's buffer on return.  Into the host's own malloc'd
+    # buffer as it is (pageable) and after pwn_host_register page-locked it in place, as the shim does.
+    single = None
+    if rank == 0 and world == 1:
+        single = {}
+        nfr = 150
+        for kind in ("pageable", "registered"):
+            hostbuf = np.zeros((h, w), np.uint32)
+            if kind == "registered":
+                api.host_register(hostbuf)
+            for i in range(5):
+                tr.trace_screen_centred(lv, 0, 0, w, h, poses["cam"][i], float(poses["sec_current"][i]), blur=bool(flags), sbuf=hostbuf)
+            t0 = time.perf_counter()
+            for i in range(0, FRAMES, FRAMES // nfr):
+                tr.trace_screen_centred(lv, 0, 0, w, h, poses["cam"][i], float(poses["sec_current"][i]), blur=bool(flags), sbuf=hostbuf)
+            dt = time.perf_counter() - t0
+            if kind == "registered":
+                api.host_unregister(hostbuf)
+            single[kind] = {"ms_per_frame": dt / nfr * 1e3, "mrays_per_s": nfr * w * h / dt / 1e6}
+        single["how"] = "pwn_trace_screen per frame (K1, K2, D2H of sbuf, sync), wall clock over %d of the %d poses" % (nfr, FRAMES)
+
     # ---- roofline of K1, live: per-launch events over the same 600 poses ---------------------
     # (single-frame path: K1 then K2 as two launches, each bracketed by events on the stream)
     k1 = k2 = 0.0
@@ -408,7 +430,8 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": FRAMES * api.POSE_DTYPE.itemsize,
                     "d2h_bytes_per_step": FRAMES * w * h * 4, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                    "how": "pwn_trace_poses into pinned host memory, %d-frame chunks; trace of frame i+1 overlaps the copy of frame i" % chunk},
+                    "how": "pwn_trace_poses into pinned host memory, %d-frame chunks; trace of frame i+1 overlaps the copy of frame i" % chunk,
+                    "single_frame_call": single},
             "gpu_launches": int(launches), "wall_s": wall,
         }
         if others is not None:

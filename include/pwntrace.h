@@ -279,6 +279,14 @@ int pwn_frame_peers_status(pwn_ctx *ctx, int *timed_out);
 /* pinned host memory for frames (cudaHostAlloc): what pwn_trace_poses copies into at full PCIe rate */
 int pwn_host_alloc(void **out, size_t bytes);
 int pwn_host_free(void *p);
+/*
+ * Page-lock a buffer the HOST allocated (the reference mallocs sbuf/zbuf, main.c:395-400), in
+ * place: pwn_trace_screen / pwn_read_frame / pwn_trace_poses then copy into it at PCIe rate
+ * instead of through the driver's staging buffers.  Registering twice is harmless.  Unregister
+ * before the host frees the buffer.
+ */
+int pwn_host_register(void *p, size_t bytes);
+int pwn_host_unregister(void *p);
 
 /* ---- measurement hooks (bench harness) ------------------------------------------------ */
 /* kernels launched by this context since creation (K1, K2, checksum, clear) */

@@ -133,6 +133,9 @@ static int ref_alloc(int w, int h)
 	int i;
 	if(w <= 0 || h <= 0) return -1;
 	if(w == rwidth && h == rheight && sbuf != NULL) return 0;
+#ifdef REF_SHIM
+	pwn_screen_release_buffers();   /* the shim page-locks sbuf/zbuf in place */
+#endif
 	for(i = 0; i < 3; i++) { free(buf_base[i]); buf_base[i] = NULL; }
 	size_t n = (size_t)w*(size_t)h*4 + 64;
 	for(i = 0; i < 3; i++)

@@ -61,6 +61,7 @@ ABI_SYMBOLS = [
     "pwn_launch_count", "pwn_last_opcount", "pwn_last_kernel_ms", "pwn_time_frames", "pwn_fp32_peak", "pwn_stream",
     "pwn_screen_upscale", "pwn_surface_device_ptr", "pwn_last_upscale_ms", "pwn_trace_config",
     "pwn_frame_peers", "pwn_trace_shard_blur", "pwn_frame_peers_status",
+    "pwn_host_register", "pwn_host_unregister",
 ]
 
 
@@ -116,6 +117,8 @@ def lib():
     L.pwn_last_upscale_ms.argtypes = [vp, C.POINTER(f)]
     L.pwn_trace_config.argtypes = [vp, i]
     L.pwn_frame_peers.argtypes = [vp, i, u64p]
+    L.pwn_host_register.argtypes = [vp, C.c_size_t]
+    L.pwn_host_unregister.argtypes = [vp]
     L.pwn_trace_shard_blur.argtypes = [vp, vp, i, i, f, u]
     L.pwn_frame_peers_status.argtypes = [vp, C.POINTER(i)]
     _lib = L
@@ -182,6 +185,15 @@ def frame_diff(a, b, gain=64):
     if host().pwn_frame_diff(a.ctypes.data, b.ctypes.data, out.ctypes.data, a.shape[1], a.shape[0], a.shape[1], gain) != 0:
         raise ValueError("pwn_frame_diff failed")
     return out
+
+
+def host_register(arr):
+    """page-lock a numpy array in place (pwn_host_register); pair with host_unregister"""
+    _check(lib().pwn_host_register(arr.ctypes.data, arr.nbytes))
+
+
+def host_unregister(arr):
+    _check(lib().pwn_host_unregister(arr.ctypes.data))
 
 
 def _check(rc):

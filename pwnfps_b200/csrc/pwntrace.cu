@@ -1004,6 +1004,26 @@ extern "C" int pwn_host_free(void *p)
 	return PWN_OK;
 }
 
+// The reference host mallocs sbuf/zbuf (main.c:395-400): pageable memory, which the copy engine
+// reaches only through the driver's staging buffers.  Page-locking the host's own buffers in place
+// lets pwn_trace_screen copy at PCIe rate without the host changing its allocation.
+extern "C" int pwn_host_register(void *p, size_t bytes)
+{
+	if(p == nullptr || bytes == 0) return fail(PWN_E_ARG, "pwn_host_register: null buffer");
+	cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+	if(e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return PWN_OK; }
+	if(e != cudaSuccess) { cudaGetLastError(); return fail(PWN_E_CUDA, "cudaHostRegister(%p, %zu): %s", p, bytes, cudaGetErrorString(e)); }
+	return PWN_OK;
+}
+
+extern "C" int pwn_host_unregister(void *p)
+{
+	if(p == nullptr) return fail(PWN_E_ARG, "pwn_host_unregister: null buffer");
+	cudaError_t e = cudaHostUnregister(p);
+	if(e != cudaSuccess) { cudaGetLastError(); return fail(PWN_E_CUDA, "cudaHostUnregister(%p): %s", p, cudaGetErrorString(e)); }
+	return PWN_OK;
+}
+
 // ---- measurement hooks ------------------------------------------------------------------------------------
 extern "C" int pwn_launch_count(pwn_ctx *ctx, uint64_t *count)
 {

@@ -34,6 +34,16 @@ static size_t pwn_screen_sph_cap = 0;
 #define PWN_SCREEN_DIM ((int)(sizeof(((level *)0)->data[0])/sizeof(((level *)0)->data[0][0])))
 #define PWN_SCREEN_NPORTAL ((int)(sizeof(((level *)0)->pmap)/sizeof(((level *)0)->pmap[0])))
 
+static uint32_t *pwn_screen_reg_s = NULL;
+static float *pwn_screen_reg_z = NULL;
+
+static void pwn_screen_release_buffers(void)
+{
+	if(pwn_screen_reg_s != NULL) pwn_host_unregister(pwn_screen_reg_s);
+	if(pwn_screen_reg_z != NULL) pwn_host_unregister(pwn_screen_reg_z);
+	pwn_screen_reg_s = NULL; pwn_screen_reg_z = NULL;
+}
+
 static void pwn_screen_upload_level(level *lv)
 {
 	int x, z, i;
@@ -104,8 +114,18 @@ void trace_screen_centred(level *lv, int x1, int y1, int x2, int y2, const mat4 
 		PWN_SCREEN_CHECK(pwn_frame_config(pwn_screen_ctx, rwidth, rheight, 0));
 		pwn_screen_w = rwidth; pwn_screen_h = rheight;
 	}
+	/* the host's own malloc'd frame buffers (main.c:395-400), page-locked in place for the copies.
+	 * In the reference they live as long as the process; a host that reallocates them calls
+	 * pwn_screen_release_buffers() before free().  A failure only costs speed. */
+	if(sbuf != pwn_screen_reg_s || zbuf != pwn_screen_reg_z)
+	{
+		pwn_screen_release_buffers();
+		if(pwn_host_register(sbuf, sizeof(uint32_t)*(size_t)rwidth*rheight) == PWN_OK) pwn_screen_reg_s = sbuf;
+		if(pwn_host_register(zbuf, sizeof(float)*(size_t)rwidth*rheight) == PWN_OK) pwn_screen_reg_z = zbuf;
+	}
 	pwn_screen_upload_parts(lv);
 
+	PWN_SCREEN_CHECK(pwn_trace_config(pwn_screen_ctx, REFLECT));   /* defs.h:8 */
 	unsigned flags = 0;
 #ifdef POSTPROC_BLUR
 	flags |= PWN_F_BLUR;
@@ -117,15 +137,22 @@ void trace_screen_centred(level *lv, int x1, int y1, int x2, int y2, const mat4 
 		flags, sbuf, zbuf));
 }
 
-/* nearest-neighbour blit of sbuf into the SDL surface, rscale x rscale per pixel (screen.h:126-149) */
+/*
+ * nearest-neighbour blit of sbuf into the SDL surface, rscale x rscale per pixel (screen.h:126-149).
+ * The reference walks one running pointer, so block row py starts at py*(w*rscale + pitch*(rscale-1))
+ * words -- py*rscale*pitch only when the pitch is not padded; the same words are written here.
+ * It stays on the host: sbuf has to cross PCIe anyway and is rscale^2 smaller than the surface
+ * (pwn_screen_upscale is the device version for hosts that present from device memory).
+ */
 void screen_upscale(void)
 {
 	int px, py, y, x;
 	const int pitch = screen->pitch/(int)sizeof(uint32_t);
+	const size_t rowstep = (size_t)rwidth*rscale + (size_t)pitch*(rscale - 1);
 	for(py = 0; py < rheight; py++)
 	{
 		const uint32_t *s = sbuf + (size_t)py*rwidth;
-		uint32_t *row0 = (uint32_t *)screen->pixels + (size_t)py*rscale*pitch;
+		uint32_t *row0 = (uint32_t *)screen->pixels + (size_t)py*rowstep;
 		for(px = 0; px < rwidth; px++)
 			for(x = 0; x < rscale; x++)
 				row0[px*rscale + x] = s[px];

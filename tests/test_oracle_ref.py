@@ -50,6 +50,13 @@ def test_upscale_vs_reference(oracle, refs):
                             (20, 6, 2, 48), (20, 6, 5, 128), (1, 1, 7, 9)]:
         f = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
         assert np.array_equal(oracle.upscale(f, rs, pitch), ref.screen_upscale(f, rs, pitch)), (w, h, rs, pitch)
+    # the drop-in shim's host-side screen_upscale (pwnfps_b200/host/pwn_screen.h) writes the same words
+    from oracle import refbind
+    if refbind.available("libref_shim.so"):
+        shim = refs("libref_shim.so")
+        for w, h, rs, pitch in [(64, 32, 2, None), (33, 7, 3, None), (20, 6, 2, 48), (20, 6, 5, 128)]:
+            f = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
+            assert np.array_equal(shim.screen_upscale(f, rs, pitch), ref.screen_upscale(f, rs, pitch)), (w, h, rs, pitch)
 
 
 def test_randfs_exhaustive_vs_reference(oracle, refs):
