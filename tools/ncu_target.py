@@ -17,5 +17,9 @@ t.frame_config(*size)
 poses = api.flythrough(lv, 600)
 for i in range(0, 600, 600 // n):
     t.trace_cam(poses["cam"][i], size[0], size[1], float(poses["sec_current"][i]), api.PWN_F_BLUR)
+# the pose pipeline: trace of frame i + blur of frame i-1 in one launch (k_trace<..., BLURP>)
+t.trace_poses(poses[:: 600 // n], size[0], size[1], api.PWN_F_BLUR)
+# K3: the frame above to a surface twice as wide and high
+t.screen_upscale(size[0], size[1], 2, read=False)
 t.sync()
 t.close()
