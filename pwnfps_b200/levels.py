@@ -1,5 +1,5 @@
 """pwnfps_b200.levels -- levels for the headless harness: the default level (as parsed by
-the reference's own loader, tools/make_golden.py) and the deterministic synthetic levels of
+the reference's own loader, tests/tools/make_golden.py) and the deterministic synthetic levels of
 BASELINE.json configs 3-5.  Generators use their own LCG so that a level
 is a pure function of its seed on every platform."""
 import os

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""tools/make_golden.py -- generates the committed fixtures from the reference itself.
+"""tests/tools/make_golden.py -- generates the committed fixtures from the reference itself.
 
 Runs HERE (where /root/reference exists), through oracle/_ref (the reference's own
 hot path compiled headless, oracle/make_ref.py).  Writes:
@@ -22,7 +22,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import refbind  # noqa: E402
 from pwnfps_b200 import api  # noqa: E402

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
-"""tools/render.py -- render poses of a level on the GPU and dump them for visual diffing.
+"""tests/tools/render.py -- render poses of a level on the GPU and dump them for visual diffing.
 
-  python tools/render.py out_prefix [--level default|hall|maze|PATH] [--size 640x360] [--frames 4]
+  python tests/tools/render.py out_prefix [--level default|hall|maze|PATH] [--size 640x360] [--frames 4]
                          [--spheres] [--check]
 
 Writes out_prefix_NNN.ppm (host/pwn_image.c) and .png (zlib, no dependencies); with --check the
@@ -15,7 +15,7 @@ import zlib
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from pwnfps_b200 import api, levels  # noqa: E402
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""tools/validate_flythrough.py -- one-off full-size parity run of BASELINE configs[1]:
+"""tests/tools/validate_flythrough.py -- one-off full-size parity run of BASELINE configs[1]:
 all 600 poses of the scripted fly-through at 1920x1080, blur on, device (pose pipeline, as the
 bench runs it) against the CPU oracle, frame by frame, by checksum; plus the 16 seeded poses of
 the 10k-sector maze at 3840x2160 (configs[3]).  Prints one summary line per config."""
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from pwnfps_b200 import api, levels  # noqa: E402
