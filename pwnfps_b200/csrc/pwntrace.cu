@@ -68,8 +68,10 @@ struct pwn_ctx
 	// spheres
 	float4 *d_sph_pos = nullptr, *d_sph_col = nullptr;
 	float2 *d_sph_rr = nullptr;
-	uint32_t *d_parts_off = nullptr, *d_parts_idx = nullptr;
-	size_t sph_cap = 0, idx_cap = 0;
+	uint32_t *d_parts_off = nullptr, *d_parts_idx = nullptr;   // all five point into d_parts_blob
+	void *d_parts_blob = nullptr, *h_parts_stage = nullptr;
+	size_t parts_cap = 0;
+	cudaEvent_t ev_parts = nullptr;
 	int nsph = 0;
 	float sph_w = 1.0f;
 
@@ -171,8 +173,8 @@ extern "C" int pwn_destroy(pwn_ctx *ctx)
 	free_frames(ctx);
 	cudaFree(ctx->d_cellmap); cudaFree(ctx->d_portals);
 	cudaFree(ctx->d_rcp); cudaFree(ctx->d_rsqrt);
-	cudaFree(ctx->d_sph_pos); cudaFree(ctx->d_sph_col); cudaFree(ctx->d_sph_rr);
-	cudaFree(ctx->d_parts_off); cudaFree(ctx->d_parts_idx);
+	cudaFree(ctx->d_parts_blob); cudaFreeHost(ctx->h_parts_stage);
+	if(ctx->ev_parts) cudaEventDestroy(ctx->ev_parts);
 	cudaFree(ctx->d_sums); cudaFree(ctx->d_opcount); cudaFree(ctx->d_surface);
 	cudaEventDestroy(ctx->ev_k3a); cudaEventDestroy(ctx->ev_k3b);
 	cudaEventDestroy(ctx->ev_k1a); cudaEventDestroy(ctx->ev_k1b); cudaEventDestroy(ctx->ev_k2b);
@@ -359,8 +361,7 @@ extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells
 	CU(cudaMemcpy(ctx->d_portals, recs.data(), recs.size()*sizeof(PortalRec), cudaMemcpyHostToDevice));
 	ctx->w = w; ctx->h = h;
 	ctx->have_level = true;
-	ctx->nsph = 0;
-	cudaFree(ctx->d_parts_off); ctx->d_parts_off = nullptr;   // sized for the previous level
+	ctx->nsph = 0;   // the per-cell sphere lists belong to the previous grid: pwn_parts_upload rebuilds them
 	return PWN_OK;
 }
 
@@ -370,6 +371,9 @@ static int cvtt_host(float v)
 	if(!(v < 2147483648.0f && v >= -2147483648.0f)) return (int)0x80000000;
 	return (int)v;
 }
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static size_t align16(size_t v) { return align_up(v, 16); }
 
 extern "C" int pwn_parts_upload(pwn_ctx *ctx, int nsph, const pwn_sphere *sph)
 {
@@ -404,35 +408,38 @@ extern "C" int pwn_parts_upload(pwn_ctx *ctx, int nsph, const pwn_sphere *sph)
 		if(pass == 0) for(size_t c = 0; c < ncell; c++) off[c+1] += off[c];
 		else
 		{
-			CU(cudaStreamSynchronize(ctx->stream));
-			if((size_t)nsph > ctx->sph_cap)
+			// one pinned staging block [pos | col | rr | off | idx] and ONE stream-ordered copy into one
+			// device block: the upload sits in the frame loop (level_prepare_render runs every frame,
+			// main.c:95), five synchronous pageable copies cost more than the binning itself
+			const size_t b_pos = 0, b_col = b_pos + align16((size_t)nsph*sizeof(float4)), b_rr = b_col + align16((size_t)nsph*sizeof(float4));
+			const size_t b_off = b_rr + align16((size_t)nsph*sizeof(float2)), b_idx = b_off + align16((ncell + 1)*sizeof(uint32_t));
+			const size_t total = b_idx + align16(idx.size()*sizeof(uint32_t));
+			if(ctx->ev_parts == nullptr) CU(cudaEventCreateWithFlags(&ctx->ev_parts, cudaEventDisableTiming));
+			else CU(cudaEventSynchronize(ctx->ev_parts));      // the previous upload has left the staging block
+			if(total > ctx->parts_cap)
 			{
-				cudaFree(ctx->d_sph_pos); cudaFree(ctx->d_sph_col); cudaFree(ctx->d_sph_rr);
-				ctx->sph_cap = (size_t)nsph*2;
-				CU(cudaMalloc(&ctx->d_sph_pos, ctx->sph_cap*sizeof(float4)));
-				CU(cudaMalloc(&ctx->d_sph_col, ctx->sph_cap*sizeof(float4)));
-				CU(cudaMalloc(&ctx->d_sph_rr, ctx->sph_cap*sizeof(float2)));
+				CU(cudaStreamSynchronize(ctx->stream));
+				cudaFree(ctx->d_parts_blob); cudaFreeHost(ctx->h_parts_stage);
+				ctx->d_parts_blob = nullptr; ctx->h_parts_stage = nullptr; ctx->parts_cap = 0;
+				CU(cudaMalloc(&ctx->d_parts_blob, total*2));
+				CU(cudaHostAlloc(&ctx->h_parts_stage, total*2, cudaHostAllocDefault));
+				ctx->parts_cap = total*2;
 			}
-			if(ctx->d_parts_off == nullptr) CU(cudaMalloc(&ctx->d_parts_off, (ncell + 1)*sizeof(uint32_t)));
-			if(idx.size() > ctx->idx_cap)
-			{
-				cudaFree(ctx->d_parts_idx);
-				ctx->idx_cap = idx.size()*2;
-				CU(cudaMalloc(&ctx->d_parts_idx, ctx->idx_cap*sizeof(uint32_t)));
-			}
-			std::vector<float4> pos(nsph), col(nsph);
-			std::vector<float2> rr(nsph);
+			char *hs = (char *)ctx->h_parts_stage, *ds = (char *)ctx->d_parts_blob;
+			float4 *pos = (float4 *)(hs + b_pos), *col = (float4 *)(hs + b_col);
+			float2 *rr = (float2 *)(hs + b_rr);
 			for(int i = 0; i < nsph; i++)
 			{
 				pos[i] = make_float4(sph[i].pos[0], sph[i].pos[1], sph[i].pos[2], sph[i].pos[3]);
 				col[i] = make_float4(sph[i].col[0], sph[i].col[1], sph[i].col[2], sph[i].col[3]);
 				rr[i] = make_float2(sph[i].r, sph[i].refl);
 			}
-			CU(cudaMemcpy(ctx->d_sph_pos, pos.data(), nsph*sizeof(float4), cudaMemcpyHostToDevice));
-			CU(cudaMemcpy(ctx->d_sph_col, col.data(), nsph*sizeof(float4), cudaMemcpyHostToDevice));
-			CU(cudaMemcpy(ctx->d_sph_rr, rr.data(), nsph*sizeof(float2), cudaMemcpyHostToDevice));
-			CU(cudaMemcpy(ctx->d_parts_off, off.data(), (ncell + 1)*sizeof(uint32_t), cudaMemcpyHostToDevice));
-			CU(cudaMemcpy(ctx->d_parts_idx, idx.data(), idx.size()*sizeof(uint32_t), cudaMemcpyHostToDevice));
+			memcpy(hs + b_off, off.data(), (ncell + 1)*sizeof(uint32_t));
+			memcpy(hs + b_idx, idx.data(), idx.size()*sizeof(uint32_t));
+			CU(cudaMemcpyAsync(ds, hs, total, cudaMemcpyHostToDevice, ctx->stream));
+			CU(cudaEventRecord(ctx->ev_parts, ctx->stream));
+			ctx->d_sph_pos = (float4 *)(ds + b_pos); ctx->d_sph_col = (float4 *)(ds + b_col); ctx->d_sph_rr = (float2 *)(ds + b_rr);
+			ctx->d_parts_off = (uint32_t *)(ds + b_off); ctx->d_parts_idx = (uint32_t *)(ds + b_idx);
 		}
 	}
 	ctx->nsph = nsph;
@@ -440,7 +447,6 @@ extern "C" int pwn_parts_upload(pwn_ctx *ctx, int nsph, const pwn_sphere *sph)
 }
 
 // ---- frame buffers ----------------------------------------------------------------------------
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 extern "C" int pwn_frame_config(pwn_ctx *ctx, int rwidth, int rheight, int want_ids)
 {
