@@ -146,6 +146,8 @@ int pwn_libm_config(pwn_ctx *ctx, int fma_build);
 void pwn_host_libm_eval(const float *in, float *s, float *c, float *e, size_t n, int fma_build);
 /* test hook: sin, cos, exp of n floats evaluated by the device functions K1 uses */
 int pwn_debug_libm(pwn_ctx *ctx, const float *in, float *sin_out, float *cos_out, float *exp_out, int n);
+/* test hook: the device's col_ftoint (util.h:48-59) on n BGRA float quadruples */
+int pwn_debug_pack(pwn_ctx *ctx, const float *bgra, uint32_t *packed, int n);
 
 /* ---- level: once per level (grid and portals are immutable after load, script.h:65-69) ---- */
 /*

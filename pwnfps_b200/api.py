@@ -61,7 +61,7 @@ ABI_SYMBOLS = [
     "pwn_launch_count", "pwn_last_opcount", "pwn_last_kernel_ms", "pwn_time_frames", "pwn_fp32_peak", "pwn_stream",
     "pwn_screen_upscale", "pwn_surface_device_ptr", "pwn_last_upscale_ms", "pwn_trace_config",
     "pwn_frame_peers", "pwn_trace_shard_blur", "pwn_frame_peers_status",
-    "pwn_host_register", "pwn_host_unregister",
+    "pwn_host_register", "pwn_host_unregister", "pwn_debug_pack",
 ]
 
 
@@ -118,6 +118,7 @@ def lib():
     L.pwn_trace_config.argtypes = [vp, i]
     L.pwn_frame_peers.argtypes = [vp, i, u64p]
     L.pwn_host_register.argtypes = [vp, C.c_size_t]
+    L.pwn_debug_pack.argtypes = [vp, vp, vp, i]
     L.pwn_host_unregister.argtypes = [vp]
     L.pwn_trace_shard_blur.argtypes = [vp, vp, i, i, f, u]
     L.pwn_frame_peers_status.argtypes = [vp, C.POINTER(i)]
@@ -509,6 +510,13 @@ class Tracer:
 
     def sync(self):
         _check(self.L.pwn_sync(self.h))
+
+    def debug_pack(self, bgra):
+        """the device's col_ftoint (util.h:48-59) on (n,4) float32 BGRA rows -> (n,) uint32"""
+        v = np.ascontiguousarray(bgra, dtype=np.float32).reshape(-1, 4)
+        out = np.zeros(len(v), np.uint32)
+        _check(self.L.pwn_debug_pack(self.h, v.ctypes.data, out.ctypes.data, len(v)))
+        return out
 
     def trace_config(self, reflect=2):
         """REFLECT (defs.h:8): bounce levels, 0..2"""

@@ -246,6 +246,24 @@ extern "C" int pwn_debug_libm(pwn_ctx *ctx, const float *in, float *sin_out, flo
 	return PWN_OK;
 }
 
+extern "C" int pwn_debug_pack(pwn_ctx *ctx, const float *bgra, uint32_t *packed, int n)
+{
+	CTX_ENTER(ctx);
+	if(bgra == nullptr || packed == nullptr || n <= 0) return fail(PWN_E_ARG, "pwn_debug_pack: bad arguments");
+	float4 *d = nullptr;
+	uint32_t *o = nullptr;
+	CU(cudaMalloc(&d, sizeof(float4)*(size_t)n));
+	CU(cudaMalloc(&o, sizeof(uint32_t)*(size_t)n));
+	CU(cudaMemcpyAsync(d, bgra, sizeof(float4)*(size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+	k_pack_eval<<<(n + 255)/256, 256, 0, ctx->stream>>>(d, o, n);
+	CU(cudaGetLastError());
+	ctx->launches++;
+	CU(cudaMemcpyAsync(packed, o, sizeof(uint32_t)*(size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	cudaFree(d); cudaFree(o);
+	return PWN_OK;
+}
+
 // ---- level ---------------------------------------------------------------------------------
 static uint32_t class_of(int32_t c)
 {
@@ -324,7 +342,7 @@ extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells
 			r.flags = rot | (kind << 8) | ((uint32_t)peek_of(xcell) << 16);
 			r.ccx = (float)dcx + 0.5f; r.ccz = (float)dcz + 0.5f;   // (cx + 0.5f), trace.h:584
 			r.dcx = dcx; r.dcz = dcz;
-			if(recs.size() >= (1u << 24)) return fail(PWN_E_LIMIT, "more than 2^24 portal cells");
+			if(recs.size() >= (1u << 20)) return fail(PWN_E_LIMIT, "more than 2^20 portal cells");
 			entry |= (uint32_t)recs.size() << CM_REC_SHIFT;
 			recs.push_back(r);
 		}
@@ -347,6 +365,9 @@ extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells
 			else if(c == CL_RAISED) slow = ntwo || n == CL_OOB;
 			else slow = n == CL_OOB;
 			if(slow) map[ci] |= 1u << (CM_SLOW_SHIFT + d);
+			// a 2-high room next to a plain cell inside the grid: only the height window matters there
+			if((c == CL_TWO || c == CL_TWO_FOG) && (n == CL_SOLID || n == CL_ONE || n == CL_ONE_FOG || (n >= CL_RAMP_GT && n <= CL_RAMP_CARET)))
+				map[ci] |= 1u << (CM_HWIN_SHIFT + d);
 		}
 	}
 	if(recs.empty()) { PortalRec r; memset(&r, 0, sizeof(r)); recs.push_back(r); }

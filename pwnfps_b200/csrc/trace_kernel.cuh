@@ -40,15 +40,18 @@ enum : uint32_t
 	CL_RAMP_LT = 7,    // '<'
 	CL_RAMP_COMMA = 8, // ','
 	CL_RAMP_CARET = 9, // '^'
-	CL_PORTAL = 10,    // letter cell; bits 8.. of the map entry index PortalRec
+	CL_PORTAL = 10,    // letter cell; bits 12.. of the map entry index PortalRec
 	CL_OOB = 15,       // the one-cell border around the map: the ray is leaving the grid
 
-	// Map entry = class | slow[4] << 4 | portal record << 8.  slow[d] (d = FXP, FZP, FXN, FZN) is set
+	// Map entry = class | slow[4] << 4 | hwin[4] << 8 | portal record << 12.  slow[d] (d = FXP, FZP, FXN, FZN) is set
 	// on a room cell when stepping out of it through face d can need more than the plain advance:
 	// the neighbour is the border, a raised cell steps into a 2-high room (trace.h:343-351), or a
 	// 2-high room steps into anything but another 2-high room (trace.h:395-440).  The flattening
 	// (pwn_level_upload) derives the bits; the room step tests one of them instead of the classes.
-	CM_SLOW_SHIFT = 4, CM_REC_SHIFT = 8
+	// hwin[d] (bits 8-11) marks the commonest slow case: a 2-high room stepping into a plain cell inside
+	// the grid (solid, 1-high, ramp).  All the reference does there is end the ray on the wall above the
+	// opening when it is outside the height window (trace.h:415-440); the slow path tests this bit first.
+	CM_SLOW_SHIFT = 4, CM_HWIN_SHIFT = 8, CM_REC_SHIFT = 12
 };
 
 enum : uint32_t { PK_WALL = 0, PK_PASS = 1, PK_RAISED = 2 };   // what a 2-high room sees through a cell (trace.h:404-440)
@@ -154,14 +157,24 @@ __device__ __forceinline__ float randfs(uint32_t &seed)
 	return __fsub_rn(__fmul_rn((float)r, __uint_as_float(0x3A0B79B3u)), 1.0f);
 }
 
-// cvtps2dq + packssdw + packuswb on one lane (util.h:48-59)
+// cvtps2dq + packssdw + packuswb on one lane (util.h:48-59).  cvtps2dq rounds to nearest even and gives
+// 0x80000000 for NaN and for |s| >= 2^31, which the two saturating packs turn into 0; everything else
+// saturates to 0..255.  cvt.rni.sat.u8 does the same in one F2IP except for s >= 2^31 (255 instead of 0).
 __device__ __forceinline__ uint32_t pack_lane(float v)
 {
-	float s = __fmul_rn(v, 255.0f);
-	// cvtps2dq: RN-even; NaN and |s| >= 2^31 give 0x80000000, which the packs clamp to 0
-	if(!(s < 2147483648.0f)) return 0u;
-	int q = __float2int_rn(s);
-	return (uint32_t)min(max(q, 0), 255);
+	const float s = __fmul_rn(v, 255.0f);
+	uint32_t q;
+	asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q) : "f"(s));
+	return (s >= 2147483648.0f) ? 0u : q;
+}
+
+// col_ftoint (util.h:48-59) alone, for known-answer tests of the pack (pwn_debug_pack)
+__global__ void k_pack_eval(const float4 *in, uint32_t *out, int n)
+{
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	const float4 v = in[i];
+	out[i] = pack_lane(v.x) | (pack_lane(v.y) << 8) | (pack_lane(v.z) << 16) | (pack_lane(v.w) << 24);
 }
 
 // The portal rotation exchanges x and z quantities.  Written as plain copies the exchange becomes a
@@ -430,6 +443,12 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 				// outside the grid): leaving the grid, raised floors, 2-high room into anything else
 				if(((cur >> ldir) | oobm) & (1u << CM_SLOW_SHIFT))
 				{
+					if(((cur >> ldir) & (1u << CM_HWIN_SHIFT)) != 0u && oobm == 0u)
+					{
+						if(py < 0.0f || py > 1.0f) PWN_WALL_EXIT(SF_WALL)   // trace.h:415,432-439
+					}
+					else
+					{
 					if(((cell & 15u) == CL_OOB) | (oobm != 0u)) PWN_OOB_FIX(xfirst);
 					const uint32_t ncls = cell & 15u;
 					if(!two)
@@ -462,6 +481,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 								PWN_WALL_EXIT(SF_WALL)
 							}
 						}
+					}
 					}
 				}
 			}

@@ -79,3 +79,17 @@ def rgb_diff(a, b):
     a8 = np.ascontiguousarray(a).view(np.uint8).reshape(a.shape + (4,))[..., :3].astype(np.int16)
     b8 = np.ascontiguousarray(b).view(np.uint8).reshape(b.shape + (4,))[..., :3].astype(np.int16)
     return np.abs(a8 - b8).max(axis=-1)
+
+
+def pack_edge_cols():
+    """BGRA quadruples that exercise col_ftoint (util.h:48-59): ties to even, saturation, negatives,
+    NaN, inf, |255 v| >= 2^31 (cvtps2dq's 0x80000000), denormals"""
+    rng = np.random.default_rng(8)
+    lanes = np.concatenate([
+        np.array([0.0, -0.0, 0.5 / 255, 1.5 / 255, 2.5 / 255, 254.5 / 255, 255.5 / 255, 1.0, 1.0000001, 2.0, 30.0, -1.0, -1e30,
+                  1e30, 8421504.0, 8421505.0, 8421506.0, 2147483648.0 / 255, 3e9, np.inf, -np.inf, np.nan, 1e-40, -1e-40], np.float32),
+        (np.arange(0, 600, dtype=np.float32) * 0.5 / 255).astype(np.float32),
+        rng.uniform(-0.2, 1.3, 4000).astype(np.float32),
+        (rng.uniform(0, 1, 400) * 2.0 ** rng.integers(-10, 40, 400)).astype(np.float32)])
+    lanes = np.resize(lanes, (len(lanes) + 3) // 4 * 4)
+    return np.stack([lanes, np.roll(lanes, 1), np.roll(lanes, 7), np.roll(lanes, 13)], axis=1).astype(np.float32)

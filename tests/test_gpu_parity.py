@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, oracle_set_level, rgb_diff
+from conftest import GOLDEN, oracle_set_level, pack_edge_cols, rgb_diff
 from pwnfps_b200 import api, levels
 
 pytestmark = pytest.mark.gpu
@@ -70,6 +70,17 @@ def check_frame(tracer, oracle, cam, sec, w, h, exact_rgb=None, label=""):
     assert (s == so).all(), (label, int((s != so).sum()))
     return {"rgb_exact": float((d == 0).mean()), "rgb_le1": float(frac_ok), "ids_bounce_mismatch": float(bad.mean()),
             "sbuf": s, "zbuf": z, "osbuf": so, "ozbuf": zo}
+
+
+def test_col_ftoint_known_answers(tracer, oracle):
+    """the pack (util.h:48-59: cvtps2dq, packssdw, packuswb) on the device against the oracle and the
+    reference's committed answers: ties to even, saturation, negatives, NaN, inf, |255 v| >= 2^31"""
+    k = np.load(os.path.join(GOLDEN, "kat_util.npz"))
+    assert (tracer.debug_pack(k["cols"]) == k["packed"]).all()
+    cols = pack_edge_cols()
+    got = tracer.debug_pack(cols)
+    want = np.array([oracle.col_ftoint(c) for c in cols], np.uint32)
+    assert (got == want).all(), np.flatnonzero(got != want)[:5]
 
 
 def test_default_level_poses(tracer, oracle, default_level):

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, oracle_set_level, rgb_diff
+from conftest import GOLDEN, oracle_set_level, pack_edge_cols, rgb_diff
 from pwnfps_b200 import api, levels
 
 IDF = ("cell", "ldir", "kind", "nstep", "nportal")
@@ -57,6 +57,17 @@ def test_upscale_vs_reference(oracle, refs):
         for w, h, rs, pitch in [(64, 32, 2, None), (33, 7, 3, None), (20, 6, 2, 48), (20, 6, 5, 128)]:
             f = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
             assert np.array_equal(shim.screen_upscale(f, rs, pitch), ref.screen_upscale(f, rs, pitch)), (w, h, rs, pitch)
+
+
+def test_col_ftoint_edges_vs_reference(oracle, refs):
+    """the pack on ties, saturation, NaN, inf and out-of-int-range values: restatement = reference"""
+    ref = refs("libref_noblur.so")
+    cols = pack_edge_cols()
+    with np.errstate(all="ignore"):
+        got = np.array([oracle.col_ftoint(c) for c in cols], np.uint32)
+        want = np.array([ref.col_ftoint(c) for c in cols], np.uint32)
+    assert (got == want).all(), cols[np.flatnonzero(got != want)[:3]]
+    assert len(np.unique(want)) > 500
 
 
 def test_randfs_exhaustive_vs_reference(oracle, refs):
