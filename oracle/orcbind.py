@@ -9,6 +9,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libpwnoracle.so")
+LIB_STRICT = os.path.join(HERE, "libpwnoracle_strict.so")
 
 IDS_DTYPE = np.dtype([("cell", "<i4"), ("ldir", "<i2"), ("kind", "<i2"),
                       ("nstep", "<i4"), ("nportal", "<i4")])
@@ -19,16 +20,20 @@ _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 def build():
     src = os.path.join(HERE, "pwn_oracle.c")
-    if os.path.isfile(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(src):
+    if all(os.path.isfile(p) and os.path.getmtime(p) >= os.path.getmtime(src) for p in (LIB, LIB_STRICT)):
         return
-    subprocess.run(["make", "-C", HERE, "libpwnoracle.so"], check=True,
+    subprocess.run(["make", "-C", HERE, "libpwnoracle.so", "libpwnoracle_strict.so"], check=True,
                    stdout=subprocess.DEVNULL)
 
 
 class Oracle:
-    def __init__(self):
+    """strict=False: randfs as gcc folds it under the reference's shipped -ffast-math (what the shipped
+    build and the device compute).  strict=True: the source as written = the reference built without
+    -ffast-math."""
+
+    def __init__(self, strict=False):
         build()
-        lib = C.CDLL(LIB)
+        lib = C.CDLL(LIB_STRICT if strict else LIB)
         self.lib = lib
         lib.orc_level_set.argtypes = [C.c_int, C.c_int, _i32p, C.c_int, _i32p]
         lib.orc_spheres_set.argtypes = [C.c_int, C.c_void_p]
@@ -49,8 +54,12 @@ class Oracle:
         lib.orc_kat_libm.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_size_t]
         lib.orc_upscale.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         self.dims = None
+        # the strict build of the same restatement, kept in step (level, spheres, config) by this one
+        self.twin = None if strict else Oracle(strict=True)
 
     def level_set(self, cells, portals):
+        if self.twin is not None:
+            self.twin.level_set(cells, portals)
         cells = np.ascontiguousarray(cells, dtype=np.int32)
         h, w = cells.shape
         pm = np.ascontiguousarray(portals, dtype=np.int32).reshape(-1, 7)
@@ -62,6 +71,8 @@ class Oracle:
 
     def spheres_set(self, sph):
         """sph: (n,10) float32 rows r refl x y z w b g r a, or None."""
+        if self.twin is not None:
+            self.twin.spheres_set(sph)
         if sph is None or len(sph) == 0:
             self.lib.orc_spheres_set(0, None)
             return
@@ -69,6 +80,8 @@ class Oracle:
         self.lib.orc_spheres_set(sph.shape[0], sph.ctypes.data)
 
     def config(self, reflect=2, reflect_blur=True):
+        if self.twin is not None:
+            self.twin.config(reflect, reflect_blur)
         self.lib.orc_config(reflect, 1 if reflect_blur else 0)
 
     def ray_setup(self, cam16, dimx, dimy):

@@ -577,3 +577,18 @@ def test_sharded_blur_allgather_in_one_process(tracer, default_level):
             t.shard_config(1, 0)
         for t in ts[1:]:
             t.close()
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_fuzz_random_levels(tracer, oracle, block):
+    """seeded random levels (tests/fuzz_levels.py; the same files pin the oracle to the reference in
+    test_oracle_ref.py): every cell class beside every other, portals anywhere, open edges, cameras
+    inside walls -- device = oracle bit for bit (ids of all three segments, zbuf, sbuf)"""
+    import fuzz_levels
+    for seed in range(block * 10, block * 10 + 10):
+        lv = api.level_parse(fuzz_levels.random_level_text(seed, open_edges=(seed % 4 == 3)))
+        tracer.level_upload(lv)
+        tracer.level_prepare_render()
+        oracle_set_level(oracle, lv)
+        for k, pose in enumerate(fuzz_levels.random_poses(lv, seed, 3)):
+            check_frame(tracer, oracle, pose["cam"], float(pose["sec_current"]), 160, 96, label="fuzz %d/%d" % (seed, k))

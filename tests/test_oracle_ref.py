@@ -1,9 +1,10 @@
 """Pins the CPU restatement (oracle/pwn_oracle.c) against the reference's own code compiled
 headless (oracle/_ref) and against the committed fixtures generated from it.
 
-Bars:  ids and zbuf bit-exact vs the shipped-flags build; sbuf bit-exact vs the same sources
-built without -ffast-math, and within 1 LSB on < 1e-5 of pixels vs the shipped-flags build
-(gcc's fast-math code generation, DESIGN.md "Oracle")."""
+Bars:  ids and zbuf bit-exact vs the shipped-flags build, sbuf within 1 LSB on < 1e-5 of pixels
+(gcc's fast-math code generation of the colour arithmetic, DESIGN.md "Oracle"); the restatement
+built without the one mirrored fast-math folding (randfs) is bit-exact, sbuf included, vs the same
+reference sources built without -ffast-math."""
 import os
 
 import numpy as np
@@ -110,8 +111,13 @@ def _compare(oracle, ref, ref_strict, cam, sec, w, h, dim_ref=64):
     d = rgb_diff(s, so)
     assert d.max() <= 1 and (d > 0).mean() < 1e-5
     if ref_strict is not None:
+        # the reference sources built WITHOUT -ffast-math against the restatement built without the
+        # mirrored randfs folding (oracle.twin): equal to the bit.  Against the mirrored build a 1-ulp
+        # jitter difference may flip a colour byte once in a few million pixels.
         ss, zs, _, _ = ref_strict.trace_frame(cam, sec, w, h)
-        assert (ss == so).all() and (zs.view(np.uint32) == zo.view(np.uint32)).all()
+        st, zt, _ = oracle.twin.trace_frame(cam, sec, w, h)
+        assert (ss == st).all() and (zs.view(np.uint32) == zt.view(np.uint32)).all()
+        assert (zs.view(np.uint32) == zo.view(np.uint32)).all() and (rgb_diff(ss, so) > 0).sum() <= 2
     return s, z, so, zo
 
 
@@ -163,7 +169,7 @@ def test_compile_time_switches_vs_reference(oracle, refs, default_level, tmp_pat
             for yaw, sec, (w, h) in [(0.0, 0.0, (320, 240)), (2.2, 1.3, (333, 77))]:
                 cam = api.mat4_roty(cam0, yaw)
                 sr, zr, _, _ = ref.trace_frame(cam, sec, w, h)
-                so, zo, _ = oracle.trace_frame(cam, sec, w, h)
+                so, zo, _ = oracle.twin.trace_frame(cam, sec, w, h)      # strict flags on both sides
                 assert (zr.view(np.uint32) == zo.view(np.uint32)).all(), variant
                 assert (sr == so).all(), (variant, int((sr != so).sum()))
     finally:
@@ -329,3 +335,25 @@ def test_many_spheres_vs_wide_reference(oracle, refs):
     finally:
         wide.objs_clear()
     assert hits > 500
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fuzz_random_levels_vs_reference(oracle, refs, tmp_path, seed):
+    """seeded random level.txt files (tests/fuzz_levels.py): the loader restatement reads what the
+    reference's level_load reads, and every frame matches (ids + zbuf bit-exact vs the shipped
+    flags, sbuf bit-exact vs the strict build)"""
+    import fuzz_levels
+    ref, strict = refs("libref_ids.so"), refs("libref_strict.so")
+    txt = fuzz_levels.random_level_text(seed, open_edges=(seed % 4 == 3))
+    p = str(tmp_path / "level.txt")
+    open(p, "wb").write(txt)
+    for r in (ref, strict):
+        r.level_load(p)
+    lv = api.level_parse(txt)
+    cells, pm = ref.level_get()
+    assert (cells == lv.cells).all()
+    assert (pm == lv.portals_i32()).all()
+    assert ref.spawn() == (lv.sx, lv.sz)
+    oracle_set_level(oracle, lv)
+    for pose in fuzz_levels.random_poses(lv, seed, 3):
+        _compare(oracle, ref, strict, pose["cam"], float(pose["sec_current"]), 160, 96)
