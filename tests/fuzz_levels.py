@@ -88,3 +88,22 @@ def random_poses(lv, seed, n, dim=22):
         poses["cam"][i] = api.mat4_roty(cam.reshape(16), 6.2831853 * r.unit())
         poses["sec_current"][i] = np.float32(10.0 * r.unit())
     return poses
+
+
+def random_spheres(lv, seed, n, dim=22):
+    """n spheres inside the block (bounding boxes stay inside the grid: level_part_add_bbox, level.h:1-39,
+    writes unchecked), around walkable cells, some overlapping cell borders and each other"""
+    r = Lcg(seed + 4242)
+    walk = np.argwhere(np.isin(lv.cells[:dim, :dim], [ord(c) for c in ';$#&"']))
+    lv.spheres = lv.spheres[:0]
+    if len(walk) == 0:
+        return lv
+    for _ in range(n):
+        z, x = walk[r.below(len(walk))]
+        rad = 0.05 + 0.4 * r.unit()
+        px = min(max(x + r.unit(), 1.0), dim - 1.0)
+        pz = min(max(z + r.unit(), 1.0), dim - 1.0)
+        lv.sphere_add(np.float32(rad), np.float32((0.0, 0.3, 0.6, 0.9)[r.below(4)]), np.float32(px),
+                      np.float32(0.1 + 1.3 * r.unit()), np.float32(pz),
+                      np.float32(r.unit()), np.float32(r.unit()), np.float32(r.unit()))
+    return lv

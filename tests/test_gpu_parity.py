@@ -587,8 +587,10 @@ def test_fuzz_random_levels(tracer, oracle, block):
     import fuzz_levels
     for seed in range(block * 10, block * 10 + 10):
         lv = api.level_parse(fuzz_levels.random_level_text(seed, open_edges=(seed % 4 == 3)))
+        if seed % 3 == 1:
+            fuzz_levels.random_spheres(lv, seed, 10)
         tracer.level_upload(lv)
-        tracer.level_prepare_render()
+        tracer.level_prepare_render(lv)
         oracle_set_level(oracle, lv)
         for k, pose in enumerate(fuzz_levels.random_poses(lv, seed, 3)):
             check_frame(tracer, oracle, pose["cam"], float(pose["sec_current"]), 160, 96, label="fuzz %d/%d" % (seed, k))

@@ -354,6 +354,17 @@ def test_fuzz_random_levels_vs_reference(oracle, refs, tmp_path, seed):
     assert (cells == lv.cells).all()
     assert (pm == lv.portals_i32()).all()
     assert ref.spawn() == (lv.sx, lv.sz)
+    for r in (ref, strict):
+        r.objs_clear()
+    if seed % 3 == 1:
+        fuzz_levels.random_spheres(lv, seed, 10)
+        for r in (ref, strict):
+            for sp in lv.spheres:
+                r.obj_sphere(sp["r"], sp["refl"], sp["pos"][0], sp["pos"][1], sp["pos"][2], sp["col"][0], sp["col"][1], sp["col"][2])
     oracle_set_level(oracle, lv)
-    for pose in fuzz_levels.random_poses(lv, seed, 3):
-        _compare(oracle, ref, strict, pose["cam"], float(pose["sec_current"]), 160, 96)
+    try:
+        for pose in fuzz_levels.random_poses(lv, seed, 3):
+            _compare(oracle, ref, strict, pose["cam"], float(pose["sec_current"]), 160, 96)
+    finally:
+        for r in (ref, strict):
+            r.objs_clear()
