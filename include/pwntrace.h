@@ -207,6 +207,8 @@ int pwn_sync(pwn_ctx *ctx);
 
 /* device -> host; any pointer may be NULL.  Full frames: rwidth*rheight elements (ids: x3). Synchronous. */
 int pwn_read_frame(pwn_ctx *ctx, uint32_t *sbuf, float *zbuf, pwn_ids *ids);
+/* host -> device, the inverse: a pre-blur frame assembled elsewhere, for pwn_blur_frame / pwn_screen_upscale */
+int pwn_write_frame(pwn_ctx *ctx, const uint32_t *sbuf, const float *zbuf);
 
 /*
  * The drop-in call: everything trace_screen_centred does for the host, with host

@@ -61,7 +61,7 @@ ABI_SYMBOLS = [
     "pwn_launch_count", "pwn_last_opcount", "pwn_last_kernel_ms", "pwn_time_frames", "pwn_fp32_peak", "pwn_stream",
     "pwn_screen_upscale", "pwn_surface_device_ptr", "pwn_last_upscale_ms", "pwn_trace_config",
     "pwn_frame_peers", "pwn_trace_shard_blur", "pwn_frame_peers_status",
-    "pwn_host_register", "pwn_host_unregister", "pwn_debug_pack",
+    "pwn_host_register", "pwn_host_unregister", "pwn_debug_pack", "pwn_write_frame",
 ]
 
 
@@ -119,6 +119,7 @@ def lib():
     L.pwn_frame_peers.argtypes = [vp, i, u64p]
     L.pwn_host_register.argtypes = [vp, C.c_size_t]
     L.pwn_debug_pack.argtypes = [vp, vp, vp, i]
+    L.pwn_write_frame.argtypes = [vp, vp, vp]
     L.pwn_host_unregister.argtypes = [vp]
     L.pwn_trace_shard_blur.argtypes = [vp, vp, i, i, f, u]
     L.pwn_frame_peers_status.argtypes = [vp, C.POINTER(i)]
@@ -544,6 +545,17 @@ class Tracer:
                                      zbuf.ctypes.data if want_z else None,
                                      ids.ctypes.data if want_ids else None))
         return sbuf, zbuf, ids
+
+    def write_frame(self, sbuf=None, zbuf=None):
+        """host -> device: (rheight, rwidth) uint32 sbuf and/or float32 zbuf"""
+        if sbuf is not None:
+            sbuf = np.ascontiguousarray(sbuf, dtype=np.uint32)
+            assert sbuf.shape == (self.rheight, self.rwidth)
+        if zbuf is not None:
+            zbuf = np.ascontiguousarray(zbuf, dtype=np.float32)
+            assert zbuf.shape == (self.rheight, self.rwidth)
+        _check(self.L.pwn_write_frame(self.h, sbuf.ctypes.data if sbuf is not None else None,
+                                      zbuf.ctypes.data if zbuf is not None else None))
 
     def trace_screen_centred(self, lv, x1, y1, x2, y2, cam, sec_current=0.0, blur=True, sbuf=None, zbuf=None):
         """trace_screen_centred (screen.h:31): [p1,p2) window, frame returned in host memory.

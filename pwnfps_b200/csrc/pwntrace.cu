@@ -802,6 +802,18 @@ extern "C" int pwn_read_frame(pwn_ctx *ctx, uint32_t *sbuf, float *zbuf, pwn_ids
 	return PWN_OK;
 }
 
+extern "C" int pwn_write_frame(pwn_ctx *ctx, const uint32_t *sbuf, const float *zbuf)
+{
+	CTX_ENTER(ctx);
+	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "pwn_write_frame before pwn_frame_config");
+	const size_t n = (size_t)ctx->rwidth*ctx->rheight;
+	const FrameSet &f = ctx->fs[0];
+	if(sbuf) CU(cudaMemcpyAsync(f.sbuf, sbuf, n*4, cudaMemcpyHostToDevice, ctx->stream));
+	if(zbuf) CU(cudaMemcpyAsync(f.zbuf, zbuf, n*4, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return PWN_OK;
+}
+
 extern "C" int pwn_trace_screen(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags,
 	uint32_t *sbuf_host, float *zbuf_host)
 {

@@ -594,3 +594,23 @@ def test_fuzz_random_levels(tracer, oracle, block):
         oracle_set_level(oracle, lv)
         for k, pose in enumerate(fuzz_levels.random_poses(lv, seed, 3)):
             check_frame(tracer, oracle, pose["cam"], float(pose["sec_current"]), 160, 96, label="fuzz %d/%d" % (seed, k))
+
+
+def test_blur_on_arbitrary_frames(tracer, oracle, default_level):
+    """K2 on frames the trace would never produce: random colours and depths incl. 0, negative, huge,
+    inf and NaN (float -> int as cvttss2si does it, then the clamp, screen.h:101-106)"""
+    tracer.level_upload(default_level)
+    rng = np.random.default_rng(21)
+    for (w, h) in [(64, 40), (132, 33), (320, 200)]:
+        tracer.frame_config(w, h)
+        s = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
+        z = (rng.uniform(0, 1, (h, w)) * 10.0 ** rng.integers(-2, 4, (h, w))).astype(np.float32)
+        special = np.array([0.0, 1.0, -5.0, 1e9, 1e12, -1e12, 3e38, np.inf, -np.inf, np.nan, 1e-30], np.float32)
+        idx = rng.integers(0, h * w, 400)
+        z.reshape(-1)[idx] = special[rng.integers(0, len(special), 400)]
+        tracer.write_frame(s, z)
+        tracer.blur_frame(w, h)
+        got = tracer.read_frame(want_z=False)[0]
+        with np.errstate(all="ignore"):
+            want = oracle.blur(s, z, w, h)
+        assert (got == want).all(), (w, h, int((got != want).sum()))
