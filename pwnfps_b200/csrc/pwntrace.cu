@@ -354,7 +354,7 @@ extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells
 	{
 		const size_t ci = (size_t)(z + 1)*wp + x + 1;
 		const uint32_t c = map[ci] & 15u;
-		if(c < CL_ONE || c > CL_TWO_FOG) continue;
+		if(!(c & 8u)) continue;   // rooms only
 		const long nb[4] = {1, wp, -1, -wp};   // FXP FZP FXN FZN (defs.h:25-33)
 		for(int d = 0; d < 4; d++)
 		{

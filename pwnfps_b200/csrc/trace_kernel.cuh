@@ -31,17 +31,17 @@ namespace pwn {
 enum : uint32_t
 {
 	CL_SOLID = 0,      // anything not listed below (trace.h:651-664)
-	CL_ONE = 1,        // ';'  1-high            (trace.h:302-352)
-	CL_ONE_FOG = 2,    // '$'  1-high, foggy
-	CL_RAISED = 3,     // '"'  1-high on the upper floor of a 2-high room
-	CL_TWO = 4,        // '#'  2-high            (trace.h:354-441)
-	CL_TWO_FOG = 5,    // '&'  2-high, foggy
-	CL_RAMP_GT = 6,    // '>'  (trace.h:443-505)
-	CL_RAMP_LT = 7,    // '<'
-	CL_RAMP_COMMA = 8, // ','
-	CL_RAMP_CARET = 9, // '^'
-	CL_PORTAL = 10,    // letter cell; bits 12.. of the map entry index PortalRec
-	CL_OOB = 15,       // the one-cell border around the map: the ray is leaving the grid
+	CL_PORTAL = 1,     // letter cell; bits 12.. of the map entry index PortalRec
+	CL_RAMP_GT = 4,    // '>'  (trace.h:443-505)   ramps: (class & 12) == 4; bit 1: along z; bit 0: ray.y += tilt
+	CL_RAMP_LT = 5,    // '<'
+	CL_RAMP_COMMA = 6, // ','
+	CL_RAMP_CARET = 7, // '^'
+	CL_ONE = 8,        // ';'  1-high            (trace.h:302-352)   rooms: bit 3; bit 1: 2-high; bit 0: foggy
+	CL_ONE_FOG = 9,    // '$'  1-high, foggy
+	CL_TWO = 10,       // '#'  2-high            (trace.h:354-441)
+	CL_TWO_FOG = 11,   // '&'  2-high, foggy
+	CL_RAISED = 12,    // '"'  1-high on the upper floor of a 2-high room
+	CL_OOB = 2,        // the one-cell border around the map: the ray is leaving the grid
 
 	// Map entry = class | slow[4] << 4 | hwin[4] << 8 | portal record << 12.  slow[d] (d = FXP, FZP, FXN, FZN) is set
 	// on a room cell when stepping out of it through face d can need more than the plain advance:
@@ -187,6 +187,15 @@ __device__ __forceinline__ void xswap(float &a, float &b)
 	a = __uint_as_float(x); b = __uint_as_float(y);
 }
 __device__ __forceinline__ float xmov(float v, uint32_t zero) { return __uint_as_float(__float_as_uint(v) ^ zero); }
+
+// one bit of a map entry as a predicate.  Written in PTX so that the front end cannot rewrite the test
+// into shift-and-compare chains: ptxas turns and + setp into a single LOP3 with a predicate result.
+__device__ __forceinline__ bool bit_of(uint32_t v, uint32_t mask)
+{
+	uint32_t t;
+	asm("and.b32 %0, %1, %2;" : "=r"(t) : "r"(v), "r"(mask));
+	return t != 0u;
+}
 
 // surface colours, lanes b g r a (defs.h:17-19, trace.h:558)
 enum : int { SF_CEIL = 0, SF_FLOOR = 1, SF_WALL = 2, SF_STRAY = 3 };
@@ -399,11 +408,11 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 
 			const uint32_t cls = cell & 15u;
 
-			if(cls - CL_ONE <= CL_TWO_FOG - CL_ONE)
+			if(cell & 8u)
 			{
 				// 1-high (trace.h:302-352) and 2-high (trace.h:354-441) rooms share the step
-				const bool two = cls >= CL_TWO;
-				const bool fogc = (cls == CL_ONE_FOG) | (cls == CL_TWO_FOG);
+				const bool two = bit_of(cell, 2u);
+				const bool fogc = bit_of(cell, 1u);
 				const bool up2 = two & up;
 				if(IDS) ops += two ? W_TWO : W_ONE;
 				if(up2) wy = __fadd_rn(wy, iay);   // ceiling one unit further (trace.h:357)
@@ -485,7 +494,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 					}
 				}
 			}
-			else if(cls - CL_RAMP_GT <= CL_RAMP_CARET - CL_RAMP_GT)
+			else if(cell & 4u)
 			{
 				// trace.h:443-505
 				if(IDS) ops += W_RAMP;
