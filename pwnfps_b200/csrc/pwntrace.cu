@@ -342,7 +342,7 @@ extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells
 			r.flags = rot | (kind << 8) | ((uint32_t)peek_of(xcell) << 16);
 			r.ccx = (float)dcx + 0.5f; r.ccz = (float)dcz + 0.5f;   // (cx + 0.5f), trace.h:584
 			r.dcx = dcx; r.dcz = dcz;
-			if(recs.size() >= (1u << 20)) return fail(PWN_E_LIMIT, "more than 2^20 portal cells");
+			if(recs.size() >= (1u << 16)) return fail(PWN_E_LIMIT, "more than 65536 portal cells");
 			entry |= (uint32_t)recs.size() << CM_REC_SHIFT;
 			recs.push_back(r);
 		}
@@ -355,6 +355,7 @@ extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells
 		const size_t ci = (size_t)(z + 1)*wp + x + 1;
 		const uint32_t c = map[ci] & 15u;
 		if(!(c & 8u)) continue;   // rooms only
+		if(c == CL_RAISED) map[ci] |= 15u << CM_RZ_SHIFT;
 		const long nb[4] = {1, wp, -1, -wp};   // FXP FZP FXN FZN (defs.h:25-33)
 		for(int d = 0; d < 4; d++)
 		{

@@ -31,7 +31,7 @@ namespace pwn {
 enum : uint32_t
 {
 	CL_SOLID = 0,      // anything not listed below (trace.h:651-664)
-	CL_PORTAL = 1,     // letter cell; bits 12.. of the map entry index PortalRec
+	CL_PORTAL = 1,     // letter cell; bits 16.. of the map entry index PortalRec
 	CL_RAMP_GT = 4,    // '>'  (trace.h:443-505)   ramps: (class & 12) == 4; bit 1: along z; bit 0: ray.y += tilt
 	CL_RAMP_LT = 5,    // '<'
 	CL_RAMP_COMMA = 6, // ','
@@ -43,7 +43,7 @@ enum : uint32_t
 	CL_RAISED = 12,    // '"'  1-high on the upper floor of a 2-high room
 	CL_OOB = 2,        // the one-cell border around the map: the ray is leaving the grid
 
-	// Map entry = class | slow[4] << 4 | hwin[4] << 8 | portal record << 12.  slow[d] (d = FXP, FZP, FXN, FZN) is set
+	// Map entry = class | slow[4] << 4 | hwin[4] << 8 | rz[4] << 12 | portal record << 16.  slow[d] (d = FXP, FZP, FXN, FZN) is set
 	// on a room cell when stepping out of it through face d can need more than the plain advance:
 	// the neighbour is the border, a raised cell steps into a 2-high room (trace.h:343-351), or a
 	// 2-high room steps into anything but another 2-high room (trace.h:395-440).  The flattening
@@ -51,7 +51,10 @@ enum : uint32_t
 	// hwin[d] (bits 8-11) marks the commonest slow case: a 2-high room stepping into a plain cell inside
 	// the grid (solid, 1-high, ramp).  All the reference does there is end the ray on the wall above the
 	// opening when it is outside the height window (trace.h:415-440); the slow path tests this bit first.
-	CM_SLOW_SHIFT = 4, CM_HWIN_SHIFT = 8, CM_REC_SHIFT = 12
+	// rz[d] (bits 12-15) is set on all four faces of a raised cell: with the three groups in the same
+	// per-face layout, one shift of the entry by the face code (done before the next cell is loaded)
+	// answers everything the slow path asks about the cell being left.
+	CM_SLOW_SHIFT = 4, CM_HWIN_SHIFT = 8, CM_RZ_SHIFT = 12, CM_REC_SHIFT = 16
 };
 
 enum : uint32_t { PK_WALL = 0, PK_PASS = 1, PK_RAISED = 2 };   // what a 2-high room sees through a cell (trace.h:404-440)
@@ -406,8 +409,6 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 				}
 			}
 
-			const uint32_t cls = cell & 15u;
-
 			if(cell & 8u)
 			{
 				// 1-high (trace.h:302-352) and 2-high (trace.h:354-441) rooms share the step
@@ -445,14 +446,14 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 					if(IDS) { if(xfirst) cx += gx; else cz += gz; }
 				}
 				if(up2) wy = __fsub_rn(wy, iay);   // trace.h:392
-				const uint32_t cur = cell;
+				const uint32_t faceb = cell >> ldir;   // the bits of the face just crossed, in the positions of face 0
 				cell = __ldg(&L.cellmap[ci]);
 
 				// slow transitions only (the cell's slow bit for the face just crossed, or a ray
 				// outside the grid): leaving the grid, raised floors, 2-high room into anything else
-				if(((cur >> ldir) | oobm) & (1u << CM_SLOW_SHIFT))
+				if((faceb | oobm) & (1u << CM_SLOW_SHIFT))
 				{
-					if(((cur >> ldir) & (1u << CM_HWIN_SHIFT)) != 0u && oobm == 0u)
+					if((faceb & (1u << CM_HWIN_SHIFT)) != 0u && oobm == 0u)
 					{
 						if(py < 0.0f || py > 1.0f) PWN_WALL_EXIT(SF_WALL)   // trace.h:415,432-439
 					}
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 					const uint32_t ncls = cell & 15u;
 					if(!two)
 					{
-						if(cls == CL_RAISED && (ncls == CL_TWO || ncls == CL_TWO_FOG))   // trace.h:343-351
+						if((faceb & (1u << CM_RZ_SHIFT)) != 0u && (ncls == CL_TWO || ncls == CL_TWO_FOG))   // leaving '"': trace.h:343-351
 						{
 							py = __fadd_rn(py, 1.0f);
 							wy = up ? __fsub_rn(wy, iay) : __fadd_rn(wy, iay);
@@ -498,8 +499,8 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 			{
 				// trace.h:443-505
 				if(IDS) ops += W_RAMP;
-				const float tilt = __fmul_rn(0.5f, (cls <= CL_RAMP_LT) ? rx : rz);
-				const bool minus = (cls == CL_RAMP_GT) || (cls == CL_RAMP_COMMA);
+				const float tilt = __fmul_rn(0.5f, bit_of(cell, 2u) ? rz : rx);   // '>' '<' tilt along x, ',' '^' along z
+				const bool minus = !bit_of(cell, 1u);                            // '>' and ','
 				ry = minus ? __fsub_rn(ry, tilt) : __fadd_rn(ry, tilt);
 				wy = py;
 				if(ry >= 0.0f) wy = __fsub_rn(1.0f, wy);
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 				cell = __ldg(&L.cellmap[ci]);
 				if(((cell & 15u) == CL_OOB) | (oobm != 0u)) PWN_OOB_FIX(xfirst);
 			}
-			else if(cls == CL_PORTAL)
+			else if((cell & 15u) == CL_PORTAL)
 			{
 				// trace.h:508-650
 				const uint4 pa = __ldg(reinterpret_cast<const uint4 *>(&L.portals[cell >> CM_REC_SHIFT]));
