@@ -132,7 +132,7 @@ enum : uint32_t
 };
 
 // ---- host-CPU primitives, emulated ---------------------------------------------------
-// rcpps(x), x > 0 normal
+// rcpps(|x|), x normal: neither the table index nor the exponent field looks at the sign bit
 __device__ __forceinline__ float rcp_emul(const LevelDev &L, float x)
 {
 	uint32_t u = __float_as_uint(x);
@@ -303,8 +303,8 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 		}
 		int gx = (irx < 0.0f ? -1 : 1), gz = (irz < 0.0f ? -1 : 1);
 		const bool up = !(iry < 0.0f);                          // gy > 0
-		float iax = rcp_emul(L, fabsf(rx)), iaz = rcp_emul(L, fabsf(rz));
-		const float iay = rcp_emul(L, fabsf(ry));
+		float iax = rcp_emul(L, rx), iaz = rcp_emul(L, rz);   // iavel = rcpps(abs(ray)), trace.h:229-231
+		const float iay = rcp_emul(L, ry);
 		float px = fx, py = fy, pz = fz;
 		float wx = __fsub_rn(px, (float)cx), wy = py, wz = __fsub_rn(pz, (float)cz);
 		if(rx >= 0.0f) wx = __fsub_rn(1.0f, wx);
@@ -662,11 +662,19 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 		if(SPH && hkind == 1) { npx = aux.px; npy = aux.py; npz = aux.pz; }
 		else { npx = px; npy = py; npz = pz; }
 
-		if(ldir == PWN_FXP) { nrx = -nrx; npx = __fsub_rn(npx, 0.001f); }
-		else if(ldir == PWN_FXN) { nrx = -nrx; npx = __fadd_rn(npx, 0.001f); }
-		else if(ldir == PWN_FZP) { nrz = -nrz; npz = __fsub_rn(npz, 0.001f); }
-		else if(ldir == PWN_FZN) { nrz = -nrz; npz = __fadd_rn(npz, 0.001f); }
-		else if(ldir == PWN_FYP) { nry = -nry; npy = __fsub_rn(npy, 0.001f); }
+		// the five flat mirrors (trace.h:12-37): flip the component of the face's axis and step 0.001 back
+		// off the face (a - 0.001f and a + (-0.001f) are the same IEEE operation).  One predicated
+		// sequence for all five: the lanes of a warp hit different faces, and the compiler's jump table
+		// for an if-chain would run once per face present.
+		if((unsigned)ldir <= (unsigned)PWN_FYP)
+		{
+			const float off = (ldir & 2) ? 0.001f : -0.001f;          // FXN, FZN: +; FXP, FZP, FYP: -
+			const bool onx = (ldir == PWN_FXP) | (ldir == PWN_FXN), onz = (ldir == PWN_FZP) | (ldir == PWN_FZN);
+			const bool ony = ldir == PWN_FYP;
+			nrx = onx ? -nrx : nrx; npx = onx ? __fadd_rn(npx, off) : npx;
+			nrz = onz ? -nrz : nrz; npz = onz ? __fadd_rn(npz, off) : npz;
+			nry = ony ? -nry : nry; npy = ony ? __fadd_rn(npy, off) : npy;
+		}
 		else
 		{
 			float nx, ny, nz;
