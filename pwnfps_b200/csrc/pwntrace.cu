@@ -824,9 +824,17 @@ extern "C" int pwn_trace_screen(pwn_ctx *ctx, const float cam[16], int dimx, int
 	if(rc != PWN_OK) return rc;
 	const size_t n = (size_t)ctx->rwidth*ctx->rheight;
 	const FrameSet &f = ctx->fs[0];
+	// zbuf is final when K1 ends: its copy starts then, on the copy stream, under the blur pass
+	const bool early_z = zbuf_host != nullptr && ctx->timed && ctx->timed_blur;
+	if(early_z)
+	{
+		CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k1b, 0));
+		CU(cudaMemcpyAsync(zbuf_host, f.zbuf, n*4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+	}
 	CU(cudaMemcpyAsync(sbuf_host, f.sbuf, n*4, cudaMemcpyDeviceToHost, ctx->stream));
-	if(zbuf_host) CU(cudaMemcpyAsync(zbuf_host, f.zbuf, n*4, cudaMemcpyDeviceToHost, ctx->stream));
+	if(zbuf_host && !early_z) CU(cudaMemcpyAsync(zbuf_host, f.zbuf, n*4, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
+	if(early_z) CU(cudaStreamSynchronize(ctx->copy_stream));
 	return PWN_OK;
 }
 

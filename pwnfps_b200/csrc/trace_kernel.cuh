@@ -224,6 +224,10 @@ constexpr int K1_MIN_CTAS = PWN_MIN_CTAS;   // 8 CTAs x 4 warps per SM at 64 reg
 #ifndef PWN_WALK_UNROLL
 #define PWN_WALK_UNROLL 1
 #endif
+#ifndef PWN_SEG_UNROLL
+#define PWN_SEG_UNROLL 1
+#endif
+constexpr int K1_SEG_UNROLL = PWN_SEG_UNROLL;     // 1: one copy of the segment body for the three segments
 constexpr int K1_WALK_UNROLL = PWN_WALK_UNROLL;   // 1: the walk stays rolled (measured: see DESIGN.md)
 constexpr int K1_MIN_CTAS_SPH = PWN_SPH_MIN_CTAS;   // with spheres the nearest-hit record adds 12 live registers
 
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 
 	const int W = L.w, H = L.h, WP = L.wp;
 
-	#pragma unroll 1
+	#pragma unroll K1_SEG_UNROLL
 	for(int seg = 0; ; seg++)
 	{
 		// ================= trace.h:203-248: segment setup =================

@@ -133,8 +133,16 @@ void trace_screen_centred(level *lv, int x1, int y1, int x2, int y2, const mat4 
 #ifndef REFLECT_BLUR
 	flags |= PWN_F_NO_REFLECT_BLUR;
 #endif
+	/* zbuf is written by the trace and read by the blur pass of this same function; nothing else in the
+	 * reference host reads it (main.c, script.h).  -DPWN_SCREEN_NO_ZBUF leaves the host's copy unfilled
+	 * and halves the bytes that cross PCIe per frame. */
+#ifdef PWN_SCREEN_NO_ZBUF
+	PWN_SCREEN_CHECK(pwn_trace_screen(pwn_screen_ctx, (const float *)cam, x2 - x1, y2 - y1, sec_current,
+		flags, sbuf, NULL));
+#else
 	PWN_SCREEN_CHECK(pwn_trace_screen(pwn_screen_ctx, (const float *)cam, x2 - x1, y2 - y1, sec_current,
 		flags, sbuf, zbuf));
+#endif
 }
 
 /*
