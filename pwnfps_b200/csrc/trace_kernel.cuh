@@ -76,7 +76,7 @@ struct __align__(16) PortalRec
 
 struct LevelDev
 {
-	const uint32_t *cellmap;   // (h+2)*(w+2) entries: class | slow<<4 | rec<<8, border = CL_OOB
+	const uint32_t *cellmap;   // (h+2)*(w+2) entries: class | slow<<4 | hwin<<8 | rz<<12 | rec<<16, border = CL_OOB
 	const PortalRec *portals;
 	int w, h, wp;              // wp = w + 2: row stride of the padded map
 	const uint32_t *rcp_tab;   // 1<<rcp_bits
