@@ -34,6 +34,19 @@ static int fail(int code, const char *fmt, ...)
 #define CU(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) \
 	return fail(PWN_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while(0)
 
+// scoped device memory / events for the helpers that allocate per call: an early error return frees them
+struct DevMem
+{
+	void *p = nullptr;
+	~DevMem() { if(p) cudaFree(p); }
+	template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+struct ScopedEvent
+{
+	cudaEvent_t e = nullptr;
+	~ScopedEvent() { if(e) cudaEventDestroy(e); }
+};
+
 extern "C" const char *pwn_last_error(void) { return g_err; }
 extern "C" int pwn_abi_version(void) { return PWN_ABI_VERSION; }
 
@@ -127,6 +140,7 @@ extern "C" int pwn_create(pwn_ctx **out, int device)
 		return fail(PWN_E_NODEVICE, "device %d is sm_%d%d; libpwntrace is built for sm_100a only", device, prop.major, prop.minor);
 
 	pwn_ctx *ctx = new pwn_ctx();
+	struct Guard { pwn_ctx *c; ~Guard() { if(c) pwn_destroy(c); } } guard{ctx};   // a failed step below undoes the ones before it
 	ctx->device = device;
 	CU(cudaSetDevice(device));
 	CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -153,6 +167,7 @@ extern "C" int pwn_create(pwn_ctx **out, int device)
 	CU(cudaMemcpyToSymbol(c_jumpA, ja, sizeof(ja)));
 	CU(cudaMemcpyToSymbol(c_jumpC, jc, sizeof(jc)));
 
+	guard.c = nullptr;
 	*out = ctx;
 	return PWN_OK;
 }
@@ -176,10 +191,12 @@ extern "C" int pwn_destroy(pwn_ctx *ctx)
 	cudaFree(ctx->d_parts_blob); cudaFreeHost(ctx->h_parts_stage);
 	if(ctx->ev_parts) cudaEventDestroy(ctx->ev_parts);
 	cudaFree(ctx->d_sums); cudaFree(ctx->d_opcount); cudaFree(ctx->d_surface);
-	cudaEventDestroy(ctx->ev_k3a); cudaEventDestroy(ctx->ev_k3b);
-	cudaEventDestroy(ctx->ev_k1a); cudaEventDestroy(ctx->ev_k1b); cudaEventDestroy(ctx->ev_k2b);
-	for(int i = 0; i < 3; i++) { cudaEventDestroy(ctx->ev_done[i]); cudaEventDestroy(ctx->ev_copied[i]); }
-	cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->copy_stream);
+	cudaEvent_t evs[] = {ctx->ev_k3a, ctx->ev_k3b, ctx->ev_k1a, ctx->ev_k1b, ctx->ev_k2b, ctx->ev_done[0], ctx->ev_done[1], ctx->ev_done[2],
+		ctx->ev_copied[0], ctx->ev_copied[1], ctx->ev_copied[2]};
+	for(cudaEvent_t e : evs) if(e) cudaEventDestroy(e);
+	if(ctx->stream) cudaStreamDestroy(ctx->stream);
+	if(ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+	cudaGetLastError();
 	delete ctx;
 	return PWN_OK;
 }
@@ -231,8 +248,9 @@ extern "C" int pwn_debug_libm(pwn_ctx *ctx, const float *in, float *sin_out, flo
 {
 	CTX_ENTER(ctx);
 	if(in == nullptr || sin_out == nullptr || cos_out == nullptr || exp_out == nullptr || n <= 0) return fail(PWN_E_ARG, "pwn_debug_libm: bad arguments");
-	float *d = nullptr;
-	CU(cudaMalloc(&d, sizeof(float)*4*(size_t)n));
+	DevMem mem;
+	CU(cudaMalloc(&mem.p, sizeof(float)*4*(size_t)n));
+	float *d = mem.as<float>();
 	CU(cudaMemcpyAsync(d, in, sizeof(float)*n, cudaMemcpyHostToDevice, ctx->stream));
 	if(ctx->libm_fma) k_libm_eval<true><<<(n + 255)/256, 256, 0, ctx->stream>>>(d, d + n, d + 2*(size_t)n, d + 3*(size_t)n, n);
 	else k_libm_eval<false><<<(n + 255)/256, 256, 0, ctx->stream>>>(d, d + n, d + 2*(size_t)n, d + 3*(size_t)n, n);
@@ -242,7 +260,6 @@ extern "C" int pwn_debug_libm(pwn_ctx *ctx, const float *in, float *sin_out, flo
 	CU(cudaMemcpyAsync(cos_out, d + 2*(size_t)n, sizeof(float)*n, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaMemcpyAsync(exp_out, d + 3*(size_t)n, sizeof(float)*n, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
-	cudaFree(d);
 	return PWN_OK;
 }
 
@@ -250,17 +267,17 @@ extern "C" int pwn_debug_pack(pwn_ctx *ctx, const float *bgra, uint32_t *packed,
 {
 	CTX_ENTER(ctx);
 	if(bgra == nullptr || packed == nullptr || n <= 0) return fail(PWN_E_ARG, "pwn_debug_pack: bad arguments");
-	float4 *d = nullptr;
-	uint32_t *o = nullptr;
-	CU(cudaMalloc(&d, sizeof(float4)*(size_t)n));
-	CU(cudaMalloc(&o, sizeof(uint32_t)*(size_t)n));
+	DevMem md, mo;
+	CU(cudaMalloc(&md.p, sizeof(float4)*(size_t)n));
+	CU(cudaMalloc(&mo.p, sizeof(uint32_t)*(size_t)n));
+	float4 *d = md.as<float4>();
+	uint32_t *o = mo.as<uint32_t>();
 	CU(cudaMemcpyAsync(d, bgra, sizeof(float4)*(size_t)n, cudaMemcpyHostToDevice, ctx->stream));
 	k_pack_eval<<<(n + 255)/256, 256, 0, ctx->stream>>>(d, o, n);
 	CU(cudaGetLastError());
 	ctx->launches++;
 	CU(cudaMemcpyAsync(packed, o, sizeof(uint32_t)*(size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
-	cudaFree(d); cudaFree(o);
 	return PWN_OK;
 }
 
@@ -1107,19 +1124,19 @@ extern "C" int pwn_time_frames(pwn_ctx *ctx, const float cam[16], int dimx, int 
 	if(cam == nullptr || total_ms == nullptr || n <= 0) return fail(PWN_E_ARG, "pwn_time_frames: bad arguments");
 	float rayb[4], rdx[4], rdy[4];
 	pwn_ray_setup(cam, dimx, dimy, rayb, rdx, rdy);
-	cudaEvent_t a, b;
-	CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+	ScopedEvent ea, eb;
+	CU(cudaEventCreate(&ea.e)); CU(cudaEventCreate(&eb.e));
+	cudaEvent_t a = ea.e, b = eb.e;
 	CU(cudaStreamSynchronize(ctx->stream));
 	CU(cudaEventRecord(a, ctx->stream));
 	for(int i = 0; i < n; i++)
 	{
 		int rc = launch_trace(ctx, ctx->fs[0], cam + 12, rayb, rdx, rdy, dimx, dimy, sec_current, flags & ~PWN_F_IDS, false);
-		if(rc != PWN_OK) { cudaEventDestroy(a); cudaEventDestroy(b); return rc; }
+		if(rc != PWN_OK) return rc;
 	}
 	CU(cudaEventRecord(b, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
 	CU(cudaEventElapsedTime(total_ms, a, b));
-	cudaEventDestroy(a); cudaEventDestroy(b);
 	return PWN_OK;
 }
 
@@ -1130,10 +1147,12 @@ extern "C" int pwn_fp32_peak(pwn_ctx *ctx, double *tlaneops)
 	cudaDeviceProp prop;
 	CU(cudaGetDeviceProperties(&prop, ctx->device));
 	const int blocks = prop.multiProcessorCount*8, threads = 256, iters = 4096;
-	float *d = nullptr;
-	CU(cudaMalloc(&d, sizeof(float)*(size_t)blocks*threads));
-	cudaEvent_t a, b;
-	CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+	DevMem mem;
+	CU(cudaMalloc(&mem.p, sizeof(float)*(size_t)blocks*threads));
+	float *d = mem.as<float>();
+	ScopedEvent ea, eb;
+	CU(cudaEventCreate(&ea.e)); CU(cudaEventCreate(&eb.e));
+	cudaEvent_t a = ea.e, b = eb.e;
 	float best = 1e30f;
 	for(int rep = 0; rep < 5; rep++)
 	{
@@ -1147,8 +1166,6 @@ extern "C" int pwn_fp32_peak(pwn_ctx *ctx, double *tlaneops)
 		if(rep > 0 && ms < best) best = ms;
 		ctx->launches++;
 	}
-	cudaEventDestroy(a); cudaEventDestroy(b);
-	cudaFree(d);
 	const double ops = (double)blocks*threads*(double)iters*8.0*8.0*2.0;   // 8 unrolled x 8 chains x (mul + add)
 	*tlaneops = ops/((double)best*1e-3)/1e12;
 	return PWN_OK;
