@@ -539,6 +539,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 				wy = __fmul_rn(wy, iay);
 				cell = __ldg(&L.cellmap[ci]);
 				if(((cell & 15u) == CL_OOB) | (oobm != 0u)) PWN_OOB_FIX(xfirst);
+				PWN_SPHERE_EXIT(false, 0.0f)   // trace.h:668-673: the ramp looked before it stepped
 			}
 			else if((cell & 15u) == CL_PORTAL)
 			{
@@ -595,6 +596,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 				else { ci -= WP; pz = __fsub_rn(pz, 1.0f); if(IDS) cz--; }
 				cell = __ldg(&L.cellmap[ci]);
 				if((cell & 15u) == CL_OOB) PWN_OOB_FIX(false);   // a portal on the rim: never outside before the step
+				PWN_SPHERE_EXIT(false, 0.0f)   // trace.h:668-673
 			}
 			else
 			{
@@ -603,7 +605,8 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 				PWN_WALL_EXIT(ldir == PWN_FYP ? SF_CEIL : SF_WALL)
 			}
 
-			PWN_SPHERE_EXIT(false, 0.0f)   // trace.h:668-673
+			// (trace.h:668-673, the look at the end of every iteration, sits at the end of the ramp and portal
+			// branches: after a room step it repeats the look the step has just taken, with nothing changed)
 		}
 #undef PWN_SPHERE_EXIT
 #undef PWN_WALL_EXIT
