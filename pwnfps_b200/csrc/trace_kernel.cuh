@@ -203,13 +203,27 @@ __device__ __forceinline__ bool bit_of(uint32_t v, uint32_t mask)
 // surface colours, lanes b g r a (defs.h:17-19, trace.h:558)
 enum : int { SF_CEIL = 0, SF_FLOOR = 1, SF_WALL = 2, SF_STRAY = 3 };
 
-struct Aux   // nearest sphere so far (trace.h:196-200)
+// Nearest sphere so far (trace.h:196-200: aux_dist, aux_pos, aux_norm, aux_col, aux_refl).  The
+// reference keeps thirteen floats; six registers carry the same information: the normal, the colour
+// and the reflectance are pure functions of (pos, the sphere, diff) and are rebuilt with the same
+// operations at the one place they are used, when the segment ends on the sphere.  diff is kept
+// because it depends on the ray at the time of the test, which a later portal may rotate.
+struct Aux
 {
-	float dist, refl;
+	float dist;
 	float px, py, pz;
-	float nx, ny, nz;
-	float cb, cg, cr, ca;
+	float diff;       // 0.2 + 0.8*max(0, -ray.norm)  (trace.h:286-290)
+	uint32_t si;      // which sphere
 };
+
+// v_normalise(hit - centre) (trace.h:283-284), shared by the test and by the rebuild at the hit
+__device__ __forceinline__ void sphere_normal(const LevelDev &L, float hx, float hy, float hz, const float4 &sp4, float &nx, float &ny, float &nz)
+{
+	nx = __fsub_rn(hx, sp4.x); ny = __fsub_rn(hy, sp4.y); nz = __fsub_rn(hz, sp4.z);
+	const float nd = __fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(nz, nz)), __fmul_rn(ny, ny));
+	const float ns = rsqrt_emul(L, nd);
+	nx = __fmul_rn(nx, ns); ny = __fmul_rn(ny, ns); nz = __fmul_rn(nz, ns);
+}
 
 // CTA = 32 x K1_ROWS pixels, K1_ROWS/4 ... one warp per 8x4 pixels
 constexpr int K1_ROWS = 4;
@@ -236,6 +250,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 {
 	const LevelDev &L = P.lv;
 	__shared__ float s_ray[3][K1_ROWS][32];
+	__shared__ float s_blend[2][6][K1_THREADS];
 
 	// ---- pixel of this thread: CTA = 32x8 pixels, warp = 8x4 ----------------------
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -279,8 +294,8 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 	float icb = 1.0f, icg = 1.0f, icr = 1.0f, ica = 1.0f;   // icol (screen.h:24)
 
 	// per-level blend state of the two bounce levels (trace.h:89-101)
-	float b0b = 0, b0g = 0, b0r = 0, b0a = 0, refl0 = 0, fog0 = 0;
-	float b1b = 0, b1g = 0, b1r = 0, b1a = 0, refl1 = 0, fog1 = 0;
+	// (colour, refl, fog) of a bounce level wait in shared memory from the bounce to the unwind: twelve
+	// values per pixel that would otherwise sit in registers through the walks of the later segments
 	float ob, og, orr, oa;   // colour coming back from the deepest segment
 	int depth = 0;           // bounce levels to unwind
 
@@ -333,9 +348,8 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 		float cdist = 0.0f, fog = 0.0f;
 		int nstep = 0, nport = 0;
 		Aux aux;
-		aux.dist = -1.0f; aux.refl = 0.25f;
-		aux.px = aux.py = aux.pz = 0.0f; aux.nx = aux.ny = aux.nz = 0.0f;
-		aux.cb = aux.cg = aux.cr = aux.ca = 1.0f;
+		aux.dist = -1.0f;
+		aux.px = aux.py = aux.pz = 0.0f; aux.diff = 0.0f; aux.si = 0u;
 
 		int hkind = 2, hsurf = SF_WALL;   // 0 wall/floor/ceiling, 1 sphere, 2 exhausted
 		float hdist = 0.0f;               // what the reference stores to *dist
@@ -394,18 +408,12 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 									aux.px = __fadd_rn(px, __fmul_rn(sd, rx));
 									aux.py = __fadd_rn(py, __fmul_rn(sd, ry));
 									aux.pz = __fadd_rn(pz, __fmul_rn(sd, rz));
-									float nx = __fsub_rn(aux.px, sp4.x), ny = __fsub_rn(aux.py, sp4.y), nz = __fsub_rn(aux.pz, sp4.z);
-									const float nd = __fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(nz, nz)), __fmul_rn(ny, ny));
-									const float ns = rsqrt_emul(L, nd);
-									nx = __fmul_rn(nx, ns); ny = __fmul_rn(ny, ns); nz = __fmul_rn(nz, ns);
-									aux.nx = nx; aux.ny = ny; aux.nz = nz;
+									float nx, ny, nz;
+									sphere_normal(L, aux.px, aux.py, aux.pz, sp4, nx, ny, nz);
 									float diff = -__fadd_rn(__fadd_rn(__fmul_rn(rx, nx), __fmul_rn(rz, nz)), __fmul_rn(ry, ny));
 									if(diff < 0.0f) diff = 0.0f;
-									aux.refl = rr.y;
-									diff = __fadd_rn(0.2f, __fmul_rn(__fsub_rn(1.0f, 0.2f), diff));
-									const float4 c4 = __ldg(&L.sph_col[si]);
-									aux.cb = __fmul_rn(diff, c4.x); aux.cg = __fmul_rn(diff, c4.y);
-									aux.cr = __fmul_rn(diff, c4.z); aux.ca = __fmul_rn(diff, c4.w);
+									aux.diff = __fadd_rn(0.2f, __fmul_rn(__fsub_rn(1.0f, 0.2f), diff));
+									aux.si = si;
 								}
 							}
 						}
@@ -652,8 +660,11 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 		}
 		else
 		{
-			cb = aux.cb; cg = aux.cg; cr = aux.cr; ca = aux.ca;
-			refl = aux.refl;
+			// aux_col = diff * sphere colour, aux_refl (trace.h:288-292), rebuilt from the record
+			const float4 c4 = __ldg(&L.sph_col[aux.si]);
+			cb = __fmul_rn(aux.diff, c4.x); cg = __fmul_rn(aux.diff, c4.y);
+			cr = __fmul_rn(aux.diff, c4.z); ca = __fmul_rn(aux.diff, c4.w);
+			refl = __ldg(&L.sph_rr[aux.si]).y;
 		}
 
 		// ================= trace_hit_bounce, trace.h:3-106 =================
@@ -707,7 +718,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 				npx = __fsub_rn(npx, __fmul_rn(0.001f, nrx));
 				npy = __fsub_rn(npy, __fmul_rn(0.001f, nry));
 				npz = __fsub_rn(npz, __fmul_rn(0.001f, nrz));
-				nx = aux.nx; ny = aux.ny; nz = aux.nz;
+				sphere_normal(L, aux.px, aux.py, aux.pz, __ldg(&L.sph_pos[aux.si]), nx, ny, nz);   // aux_norm, rebuilt
 			}
 			// rmul = -2*(((0 + rx*nx) + ry*ny) + rz*nz); ray = normalise(rmul*norm + ray)
 			const float rmul = __fmul_rn(-2.0f, __fadd_rn(__fadd_rn(__fmul_rn(nrx, nx), __fmul_rn(nry, ny)), __fmul_rn(nrz, nz)));
@@ -728,8 +739,11 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 			seed = (seed * 25739u + 4u) & 0x7FFFFFFFu;
 		}
 
-		if(seg == 0) { b0b = cb; b0g = cg; b0r = cr; b0a = ca; refl0 = refl; fog0 = fog; }
-		else { b1b = cb; b1g = cg; b1r = cr; b1a = ca; refl1 = refl; fog1 = fog; }
+		{
+			float (*sb)[K1_THREADS] = s_blend[seg];
+			sb[0][threadIdx.x] = cb; sb[1][threadIdx.x] = cg; sb[2][threadIdx.x] = cr; sb[3][threadIdx.x] = ca;
+			sb[4][threadIdx.x] = refl; sb[5][threadIdx.x] = fog;
+		}
 		depth = seg + 1;
 
 		// child: trace_ray(hitctr+1, seed, lv, dist, &pos, &ray, col)  (trace.h:90)
@@ -739,30 +753,19 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 	}
 
 	// ---- unwind the blends, deepest first (trace.h:91-101) ------------------------------
-	if(depth >= 2)
+	#pragma unroll 1
+	for(int lvl = depth - 1; lvl >= 0; lvl--)
 	{
-		const float k = __fsub_rn(1.0f, refl1);
-		ob = __fadd_rn(__fmul_rn(refl1, ob), __fmul_rn(k, b1b));
-		og = __fadd_rn(__fmul_rn(refl1, og), __fmul_rn(k, b1g));
-		orr = __fadd_rn(__fmul_rn(refl1, orr), __fmul_rn(k, b1r));
-		oa = __fadd_rn(__fmul_rn(refl1, oa), __fmul_rn(k, b1a));
-		if(fog1 != 0.0f)
+		float (*sb)[K1_THREADS] = s_blend[lvl];
+		const float refl = sb[4][threadIdx.x], fogl = sb[5][threadIdx.x];
+		const float k = __fsub_rn(1.0f, refl);
+		ob = __fadd_rn(__fmul_rn(refl, ob), __fmul_rn(k, sb[0][threadIdx.x]));
+		og = __fadd_rn(__fmul_rn(refl, og), __fmul_rn(k, sb[1][threadIdx.x]));
+		orr = __fadd_rn(__fmul_rn(refl, orr), __fmul_rn(k, sb[2][threadIdx.x]));
+		oa = __fadd_rn(__fmul_rn(refl, oa), __fmul_rn(k, sb[3][threadIdx.x]));
+		if(fogl != 0.0f)
 		{
-			const float f = libm_expf<LFMA>(__fmul_rn(-0.6f, fog1)), g = __fsub_rn(1.0f, f);
-			ob = __fadd_rn(__fmul_rn(f, ob), g); og = __fadd_rn(__fmul_rn(f, og), g);
-			orr = __fadd_rn(__fmul_rn(f, orr), g); oa = __fadd_rn(__fmul_rn(f, oa), g);
-		}
-	}
-	if(depth >= 1)
-	{
-		const float k = __fsub_rn(1.0f, refl0);
-		ob = __fadd_rn(__fmul_rn(refl0, ob), __fmul_rn(k, b0b));
-		og = __fadd_rn(__fmul_rn(refl0, og), __fmul_rn(k, b0g));
-		orr = __fadd_rn(__fmul_rn(refl0, orr), __fmul_rn(k, b0r));
-		oa = __fadd_rn(__fmul_rn(refl0, oa), __fmul_rn(k, b0a));
-		if(fog0 != 0.0f)
-		{
-			const float f = libm_expf<LFMA>(__fmul_rn(-0.6f, fog0)), g = __fsub_rn(1.0f, f);
+			const float f = libm_expf<LFMA>(__fmul_rn(-0.6f, fogl)), g = __fsub_rn(1.0f, f);
 			ob = __fadd_rn(__fmul_rn(f, ob), g); og = __fadd_rn(__fmul_rn(f, og), g);
 			orr = __fadd_rn(__fmul_rn(f, orr), g); oa = __fadd_rn(__fmul_rn(f, oa), g);
 		}
