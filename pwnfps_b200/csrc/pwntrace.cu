@@ -81,7 +81,7 @@ struct pwn_ctx
 	// spheres
 	float4 *d_sph_pos = nullptr, *d_sph_col = nullptr;
 	float2 *d_sph_rr = nullptr;
-	uint32_t *d_parts_off = nullptr, *d_parts_idx = nullptr;   // all five point into d_parts_blob
+	uint32_t *d_parts_off = nullptr, *d_parts_idx = nullptr, *d_parts_pk = nullptr;   // all six point into d_parts_blob
 	void *d_parts_blob = nullptr, *h_parts_stage = nullptr;
 	size_t parts_cap = 0;
 	cudaEvent_t ev_parts = nullptr;
@@ -452,7 +452,9 @@ extern "C" int pwn_parts_upload(pwn_ctx *ctx, int nsph, const pwn_sphere *sph)
 			// main.c:95), five synchronous pageable copies cost more than the binning itself
 			const size_t b_pos = 0, b_col = b_pos + align16((size_t)nsph*sizeof(float4)), b_rr = b_col + align16((size_t)nsph*sizeof(float4));
 			const size_t b_off = b_rr + align16((size_t)nsph*sizeof(float2)), b_idx = b_off + align16((ncell + 1)*sizeof(uint32_t));
-			const size_t total = b_idx + align16(idx.size()*sizeof(uint32_t));
+			const size_t b_pk = b_idx + align16(idx.size()*sizeof(uint32_t));
+			const size_t total = b_pk + align16(ncell*sizeof(uint32_t));
+			if(idx.size() >= (1u << 24)) return fail(PWN_E_LIMIT, "more than 2^24 sphere list entries");
 			if(ctx->ev_parts == nullptr) CU(cudaEventCreateWithFlags(&ctx->ev_parts, cudaEventDisableTiming));
 			else CU(cudaEventSynchronize(ctx->ev_parts));      // the previous upload has left the staging block
 			if(total > ctx->parts_cap)
@@ -475,10 +477,17 @@ extern "C" int pwn_parts_upload(pwn_ctx *ctx, int nsph, const pwn_sphere *sph)
 			}
 			memcpy(hs + b_off, off.data(), (ncell + 1)*sizeof(uint32_t));
 			memcpy(hs + b_idx, idx.data(), idx.size()*sizeof(uint32_t));
+			uint32_t *pk = (uint32_t *)(hs + b_pk);
+			for(size_t c = 0; c < ncell; c++)
+			{
+				const uint32_t cnt = off[c + 1] - off[c];
+				pk[c] = off[c] | ((cnt < 255u ? cnt : 255u) << 24);
+			}
 			CU(cudaMemcpyAsync(ds, hs, total, cudaMemcpyHostToDevice, ctx->stream));
 			CU(cudaEventRecord(ctx->ev_parts, ctx->stream));
 			ctx->d_sph_pos = (float4 *)(ds + b_pos); ctx->d_sph_col = (float4 *)(ds + b_col); ctx->d_sph_rr = (float2 *)(ds + b_rr);
 			ctx->d_parts_off = (uint32_t *)(ds + b_off); ctx->d_parts_idx = (uint32_t *)(ds + b_idx);
+			ctx->d_parts_pk = (uint32_t *)(ds + b_pk);
 		}
 	}
 	ctx->nsph = nsph;
@@ -616,7 +625,7 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 	P.lv.rcp_shift = 23 - ctx->rcp_bits; P.lv.rsqrt_shift = 23 - ctx->rsqrt_bits;
 	P.lv.rsqrt_mask = (2u << ctx->rsqrt_bits) - 1u;
 	P.lv.sph_pos = ctx->d_sph_pos; P.lv.sph_col = ctx->d_sph_col; P.lv.sph_rr = ctx->d_sph_rr;
-	P.lv.parts_off = ctx->d_parts_off; P.lv.parts_idx = ctx->d_parts_idx; P.lv.nsph = ctx->nsph;
+	P.lv.parts_off = ctx->d_parts_off; P.lv.parts_idx = ctx->d_parts_idx; P.lv.parts_pk = ctx->d_parts_pk; P.lv.nsph = ctx->nsph;
 	for(int i = 0; i < 4; i++) { P.from[i] = from[i]; P.rayb[i] = rayb[i]; P.rdx[i] = rdx[i]; P.rdy[i] = rdy[i]; }
 	P.sec_current = sec;
 	P.dimx = dimx; P.dimy = dimy; P.rwidth = ctx->rwidth;

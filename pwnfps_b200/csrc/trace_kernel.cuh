@@ -87,6 +87,8 @@ struct LevelDev
 	const float4 *sph_pos;     // x y z w
 	const float4 *sph_col;     // b g r a
 	const float2 *sph_rr;      // r, refl
+	const uint32_t *parts_pk;  // (h+2)*(w+2): first list entry | min(count, 255) << 24 -- ONE load per cell step tells whether
+	                           // the cell holds spheres at all; 255 means "count from parts_off"
 	const uint32_t *parts_off; // (h+2)*(w+2)+1
 	const uint32_t *parts_idx;
 	int nsph;
@@ -379,10 +381,12 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 
 			if(SPH)   // trace.h:252-296
 			{
-				if(!oobm)
+				const uint32_t pk = __ldg(&L.parts_pk[ci]);
+				if((pk >> 24) != 0u && !oobm)   // (outside the grid the reference looks at no list, trace.h:252)
 				{
-					const uint32_t e = __ldg(&L.parts_off[ci + 1]);
-					for(uint32_t i = __ldg(&L.parts_off[ci]); i < e; i++)
+					uint32_t i = pk & 0xFFFFFFu, e = i + (pk >> 24);
+					if((pk >> 24) == 255u) e = __ldg(&L.parts_off[ci + 1]);
+					for(; i < e; i++)
 					{
 						const uint32_t si = __ldg(&L.parts_idx[i]);
 						const float4 sp4 = __ldg(&L.sph_pos[si]);

@@ -211,6 +211,28 @@ def test_game_script_spheres_frame_by_frame(tracer, oracle, default_level):
     tracer.level_prepare_render(lv)
 
 
+def test_crowded_cell(tracer, oracle):
+    """300 small spheres inside one cell in front of the spawn: the per-cell list handle saturates at
+    255 and the walk falls back to the CSR offsets"""
+    lv = levels.default_level()
+    rnd = np.random.default_rng(12)
+    cx, cz = lv.sx, lv.sz + 2                       # two cells ahead of the spawn, looking +z
+    assert chr(lv.cells[cz, cx]) in ";#$&"
+    for _ in range(300):
+        lv.sphere_add(np.float32(0.02 + 0.03 * rnd.random()), np.float32(0.3),
+                      np.float32(cx + 0.1 + 0.8 * rnd.random()), np.float32(0.1 + 0.8 * rnd.random()),
+                      np.float32(cz + 0.1 + 0.8 * rnd.random()),
+                      np.float32(rnd.random()), np.float32(rnd.random()), np.float32(rnd.random()))
+    tracer.level_upload(lv)
+    tracer.level_prepare_render(lv)
+    oracle_set_level(oracle, lv)
+    r = check_frame(tracer, oracle, api.cam_spawn(lv), 0.1, 320, 200, label="crowded")
+    _, _, ids = tracer.read_frame(want_ids=True)
+    assert (ids[..., 0]["kind"] == 1).sum() > 2000
+    lv.spheres = lv.spheres[:0]
+    tracer.level_prepare_render(lv)
+
+
 def test_many_spheres_on_the_maze(tracer, oracle):
     """3000 spheres binned per cell on the device side of pwn_parts_upload; sphere hits, sphere
     bounces and spheres seen through portals, bit-exact"""
