@@ -107,6 +107,8 @@ typedef struct pwn_ctx pwn_ctx;
 #define PWN_F_BLUR 1u        /* run the POSTPROC_BLUR pass (screen.h:69-123)         */
 #define PWN_F_IDS 2u         /* also write pwn_ids (needs pwn_frame_config want_ids) */
 #define PWN_F_NO_REFLECT_BLUR 4u /* build without REFLECT_BLUR (defs.h:6); diagnostics */
+#define PWN_F_LOCAL_BANDS 8u /* pwn_trace_shard_blur: the blurred bands stay in this shard's own sbuf (for hosts that
+                                read the bands of every GPU themselves, pwn_read_bands) instead of going to shard 0 */
 
 /* ---- lifetime ------------------------------------------------------------------ */
 int pwn_abi_version(void);
@@ -279,6 +281,13 @@ int pwn_frame_ipc_close(pwn_ctx *ctx, uint64_t base_dev);
 int pwn_frame_peers(pwn_ctx *ctx, int nshards, const uint64_t *base_dev);
 int pwn_trace_shard_blur(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags);
 int pwn_frame_peers_status(pwn_ctx *ctx, int *timed_out);
+/*
+ * Copy the bands this shard owns (pwn_shard_config) from its sbuf to the same rows of a HOST frame
+ * of rwidth*rheight words -- typically one frame in shared memory that every shard's process has
+ * page-locked (pwn_host_register): the frame is assembled in host memory over all the GPUs' PCIe
+ * links at once and never gathered on one GPU.  Synchronous.
+ */
+int pwn_read_bands(pwn_ctx *ctx, int dimx, int dimy, uint32_t *sbuf_host_frame);
 
 /* pinned host memory for frames (cudaHostAlloc): what pwn_trace_poses copies into at full PCIe rate */
 int pwn_host_alloc(void **out, size_t bytes);

@@ -22,6 +22,7 @@ PWN_OK = 0
 PWN_F_BLUR = 1
 PWN_F_IDS = 2
 PWN_F_NO_REFLECT_BLUR = 4
+PWN_F_LOCAL_BANDS = 8
 
 FXP, FZP, FXN, FZN, FYP, FYN = range(6)
 
@@ -61,7 +62,7 @@ ABI_SYMBOLS = [
     "pwn_launch_count", "pwn_last_opcount", "pwn_last_kernel_ms", "pwn_time_frames", "pwn_fp32_peak", "pwn_stream",
     "pwn_screen_upscale", "pwn_surface_device_ptr", "pwn_last_upscale_ms", "pwn_trace_config",
     "pwn_frame_peers", "pwn_trace_shard_blur", "pwn_frame_peers_status",
-    "pwn_host_register", "pwn_host_unregister", "pwn_debug_pack", "pwn_write_frame",
+    "pwn_host_register", "pwn_host_unregister", "pwn_debug_pack", "pwn_write_frame", "pwn_read_bands",
 ]
 
 
@@ -120,6 +121,7 @@ def lib():
     L.pwn_host_register.argtypes = [vp, C.c_size_t]
     L.pwn_debug_pack.argtypes = [vp, vp, vp, i]
     L.pwn_write_frame.argtypes = [vp, vp, vp]
+    L.pwn_read_bands.argtypes = [vp, i, i, vp]
     L.pwn_host_unregister.argtypes = [vp]
     L.pwn_trace_shard_blur.argtypes = [vp, vp, i, i, f, u]
     L.pwn_frame_peers_status.argtypes = [vp, C.POINTER(i)]
@@ -635,6 +637,11 @@ class Tracer:
     def trace_shard_blur(self, cam, dimx, dimy, sec_current, flags=0):
         cam = np.ascontiguousarray(cam, dtype=np.float32).reshape(16)
         _check(self.L.pwn_trace_shard_blur(self.h, cam.ctypes.data, dimx, dimy, float(sec_current), flags))
+
+    def read_bands(self, dimx, dimy, host_frame):
+        """copy this shard's bands into the same rows of a (rheight, rwidth) uint32 host frame (numpy array or address)"""
+        ptr = host_frame.ctypes.data if isinstance(host_frame, np.ndarray) else host_frame
+        _check(self.L.pwn_read_bands(self.h, dimx, dimy, ptr))
 
     def peers_timed_out(self):
         v = C.c_int()

@@ -746,7 +746,8 @@ extern "C" int pwn_trace_shard_blur(pwn_ctx *ctx, const float cam[16], int dimx,
 	const int nb_local = nbands > ctx->shard ? (nbands - ctx->shard + ctx->nshards - 1)/ctx->nshards : 0;
 	if(nb_local > 0)
 	{
-		BlurParams B = blur_params(ctx, f.tsbuf, f.zbuf, (uint32_t *)(ctx->peer_base[0] + f.off_sbuf), dimx, dimy);
+		uint32_t *dst = (flags & PWN_F_LOCAL_BANDS) ? f.sbuf : (uint32_t *)(ctx->peer_base[0] + f.off_sbuf);
+		BlurParams B = blur_params(ctx, f.tsbuf, f.zbuf, dst, dimx, dimy);
 		B.nshards = ctx->nshards; B.shard = ctx->shard;
 		rc = launch_blur(ctx, B, nb_local*32);
 		if(rc != PWN_OK) return rc;
@@ -757,6 +758,24 @@ extern "C" int pwn_trace_shard_blur(pwn_ctx *ctx, const float cam[16], int dimx,
 	if(rc != PWN_OK) return rc;
 	CU(cudaEventRecord(ctx->ev_k2b, ctx->stream));
 	ctx->timed_blur = true;
+	return PWN_OK;
+}
+
+extern "C" int pwn_read_bands(pwn_ctx *ctx, int dimx, int dimy, uint32_t *sbuf_host_frame)
+{
+	CTX_ENTER(ctx);
+	if(sbuf_host_frame == nullptr) return fail(PWN_E_ARG, "pwn_read_bands: null frame");
+	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "pwn_read_bands before pwn_frame_config");
+	if(dimx <= 0 || dimy <= 0 || dimx > ctx->rwidth || dimy > ctx->rheight) return fail(PWN_E_ARG, "pwn_read_bands: bad size");
+	const FrameSet &f = ctx->fs[0];
+	const int nbands = (dimy + 31)/32;
+	for(int b = ctx->shard; b < nbands; b += ctx->nshards)
+	{
+		const int y0 = b*32, rows = (dimy - y0 < 32) ? dimy - y0 : 32;
+		const size_t off = (size_t)y0*ctx->rwidth;
+		CU(cudaMemcpyAsync(sbuf_host_frame + off, f.sbuf + off, (size_t)rows*ctx->rwidth*4, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	CU(cudaStreamSynchronize(ctx->stream));
 	return PWN_OK;
 }
 

@@ -13,6 +13,8 @@ holds the whole (tiny) level.  Two ways to assemble the frame on GPU 0:
 The blur pass (screen.h:69-123) reads the whole pre-blur frame, so it runs on GPU 0 after
 either assembly.  Pose batches shard by pose with no exchange at all (bench.py).
 """
+import time
+
 import numpy as np
 
 BAND = 32   # screen.h:64
@@ -122,6 +124,25 @@ def close_all_peers(tr, bases):
             tr.ipc_close(b)
 
 
+def _shared_host_frame(rank, dist, h, w):
+    """one (h, w) uint32 frame in POSIX shared memory, mapped by every rank of the box"""
+    from multiprocessing import shared_memory
+    name = [None]
+    shm = None
+    if rank == 0:
+        shm = shared_memory.SharedMemory(create=True, size=h * w * 4)
+        name = [shm.name]
+    dist.broadcast_object_list(name, src=0)
+    if rank != 0:
+        shm = shared_memory.SharedMemory(name=name[0])
+        try:        # the creator unlinks; keep this process's resource tracker out of it
+            from multiprocessing import resource_tracker
+            resource_tracker.unregister(shm._name, "shared_memory")
+        except Exception:
+            pass
+    return np.ndarray((h, w), np.uint32, buffer=shm.buf), shm
+
+
 def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), frames=16):
     """BASELINE configs[4]: one 8K frame of the 10k-sector maze, row bands over `world` GPUs,
     assembled on GPU 0; device-timed, max over ranks.  Returns a dict on every rank."""
@@ -217,10 +238,47 @@ def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), fr
         out["sharded_blur_ms"] = allmax(t1 + t2) / frames
         out["sharded_blur_mrays"] = w * h / out["sharded_blur_ms"] / 1e3
         timed_out = tr.peers_timed_out()
+        # end to end into HOST memory: the blurred bands stay on their GPU and every rank copies its own
+        # into one frame in shared memory that all ranks have page-locked -- all the PCIe links at once,
+        # nothing gathered on GPU 0.  Wall clock between barriers, max over ranks.
+        host_ok = None
+        try:
+            host, shm = _shared_host_frame(rank, dist, h, w)
+            api.host_register(host)
+            try:
+                tr.trace_shard_blur(poses[0]["cam"], w, h, float(poses[0]["sec_current"]), api.PWN_F_LOCAL_BANDS)
+                tr.read_bands(w, h, host)
+                tot = 0.0
+                good = True
+                for k, p in enumerate(poses):
+                    dist.barrier()
+                    t0 = time.perf_counter()
+                    tr.trace_shard_blur(p["cam"], w, h, float(p["sec_current"]), api.PWN_F_LOCAL_BANDS)
+                    tr.read_bands(w, h, host)
+                    dist.barrier()
+                    tot += time.perf_counter() - t0
+                    if rank == 0 and k % 4 == 0:
+                        good = good and int(api.checksum_ref(host, w, h)) == int(want_b[k])
+                    dist.barrier()
+                out["host_frame_ms"] = allmax(tot) / frames * 1e3
+                out["host_frame_mrays"] = w * h / out["host_frame_ms"] / 1e3
+                host_ok = good
+            finally:
+                tr.sync()
+                api.host_unregister(host)
+                del host
+                shm.close()
+                dist.barrier()
+                if rank == 0:
+                    shm.unlink()
+        except Exception as e:      # shared memory may be unavailable on a box; the device numbers stand
+            out["host_frame_error"] = "%s: %s" % (type(e).__name__, e)
         dist.barrier()
         close_all_peers(tr, bases)
         if rank == 0:
             out["sharded_blur_frames_equal_one_gpu"] = bool(got == [int(v) for v in want_b[::4]]) and not timed_out
+            if host_ok is not None:
+                out["host_frame_equal_one_gpu"] = bool(host_ok)
     except api.PwnError as e:
         out["sharded_blur_error"] = str(e)
         tr.frame_peers(None)

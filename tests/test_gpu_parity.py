@@ -591,6 +591,20 @@ def test_sharded_blur_allgather_in_one_process(tracer, default_level):
             assert (got == want[k]).all(), (k, int((got != want[k]).sum()))
             k1, k2 = ts[0].last_kernel_ms()
             assert k1 > 0 and k2 > 0
+        # the host-assembled variant: blurred bands stay on their shard and every shard copies its own
+        # bands into one host frame (pwn_read_bands); nothing is gathered on shard 0
+        host = np.zeros((h, w), np.uint32)
+        api.host_register(host)
+        try:
+            for k, cam in enumerate(cams[:2]):
+                host[:] = 0
+                for t in ts:
+                    t.trace_shard_blur(cam, w, h, 0.3 * k, api.PWN_F_LOCAL_BANDS)
+                for t in ts:
+                    t.read_bands(w, h, host)
+                assert (host == want[k]).all(), (k, int((host != want[k]).sum()))
+        finally:
+            api.host_unregister(host)
         with pytest.raises(api.PwnError):
             ts[1].frame_peers(bases[:2])               # disagrees with pwn_shard_config
     finally:
