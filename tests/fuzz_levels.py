@@ -107,3 +107,31 @@ def random_spheres(lv, seed, n, dim=22):
                       np.float32(0.1 + 1.3 * r.unit()), np.float32(pz),
                       np.float32(r.unit()), np.float32(r.unit()), np.float32(r.unit()))
     return lv
+
+
+def random_wide_level(seed, dim=128, block=96, pairs=120):
+    """a block x block random level in a dim x dim grid with `pairs` portal pairs, ids far beyond the 26
+    letters (api.portal_code), paired and derived by the host library the way the loader does"""
+    r = Lcg(seed + 31337)
+    tot = sum(w for _, w in CLASSES)
+    g = np.full((dim, dim), ord("."), np.int32)
+
+    def pick():
+        k = r.below(tot)
+        for c, wgt in CLASSES:
+            if k < wgt:
+                return ord(c)
+            k -= wgt
+    for _ in range(block * 3):
+        x0, z0 = 1 + r.below(block - 2), 1 + r.below(block - 2)
+        w, h = 1 + r.below(9), 1 + r.below(9)
+        g[z0:min(block - 1, z0 + h), x0:min(block - 1, x0 + w)] = pick()
+    for _ in range(block * 4):
+        g[1 + r.below(block - 2), 1 + r.below(block - 2)] = pick()
+    for p in range(pairs):
+        copies = (2, 2, 2, 2, 1, 3)[r.below(6)]
+        for _ in range(copies):
+            g[1 + r.below(block - 2), 1 + r.below(block - 2)] = api.portal_code(p)
+    walk = np.argwhere(g == ord(";"))
+    z, x = walk[r.below(len(walk))] if len(walk) else (1, 1)
+    return api.Level.from_grid(g, pairs, int(x), int(z))

@@ -650,3 +650,15 @@ def test_blur_on_arbitrary_frames(tracer, oracle, default_level):
         with np.errstate(all="ignore"):
             want = oracle.blur(s, z, w, h)
         assert (got == want).all(), (w, h, int((got != want).sum()))
+
+
+def test_fuzz_wide_levels(tracer, oracle):
+    """random 96x96 levels with 120 portal pairs: device = oracle bit for bit"""
+    import fuzz_levels
+    for seed in range(6):
+        lv = fuzz_levels.random_wide_level(seed)
+        tracer.level_upload(lv)
+        tracer.level_prepare_render()
+        oracle_set_level(oracle, lv)
+        for k, pose in enumerate(fuzz_levels.random_poses(lv, seed, 3, dim=96)):
+            check_frame(tracer, oracle, pose["cam"], float(pose["sec_current"]), 160, 96, label="wide fuzz %d/%d" % (seed, k))

@@ -368,3 +368,20 @@ def test_fuzz_random_levels_vs_reference(oracle, refs, tmp_path, seed):
     finally:
         for r in (ref, strict):
             r.objs_clear()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fuzz_wide_levels_vs_wide_reference(oracle, refs, seed):
+    """random 96x96 levels with 120 portal pairs (ids far beyond the 26 letters) against the widened
+    build of the reference: ids + zbuf bit-exact, sbuf within 1 LSB"""
+    import fuzz_levels
+    lv = fuzz_levels.random_wide_level(seed)
+    wide = refs("libref_wide_ids.so")
+    wide.level_set(lv.cells, lv.portals_i32(), lv.sx, lv.sz)
+    oracle_set_level(oracle, lv)
+    crossed = 0
+    for pose in fuzz_levels.random_poses(lv, seed, 3, dim=96):
+        _compare(oracle, wide, None, pose["cam"], float(pose["sec_current"]), 160, 96)
+        _, _, ids = oracle.trace_frame(pose["cam"], float(pose["sec_current"]), 160, 96, want_ids=True)
+        crossed += int(ids["nportal"].sum())
+    assert crossed > 0
