@@ -111,3 +111,11 @@ def test_libm_restatement_matches_host_glibc(oracle):
     # the other build differs on the discriminating inputs, so the probe is meaningful
     s2, c2, e2 = api.host_libm_eval(x[-3:], 1 - fma_build)
     assert (s2.view(np.uint32)[0] != hs.view(np.uint32)[-3]) or (c2.view(np.uint32)[1] != hc.view(np.uint32)[-2])
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md maps each exported entry point to the reference interface it replaces"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    missing = [s for s in api.ABI_SYMBOLS if s not in doc]
+    assert not missing, missing
