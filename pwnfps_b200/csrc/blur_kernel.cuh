@@ -37,13 +37,13 @@ __device__ __forceinline__ float blur_randfs(uint32_t &seed)
 }
 
 // (int)float as cvttss2si does it, FOLLOWED by the clamp to [0, hi] of screen.h:103-106.
-// cvttss2si gives INT_MIN for NaN and for anything outside int range, which the clamp turns into 0;
-// F2I.TRUNC saturates instead, so only v >= 2^31 needs a correction (NaN -> 0 and v < -2^31 ->
-// INT_MIN clamp to 0 either way).
+// cvttss2si gives INT_MIN for NaN and for anything outside int range, which the clamp turns into 0.
+// The unsigned conversion F2I.U32.TRUNC gives 0 for NaN and negatives, the value below 2^32 and
+// 0xFFFFFFFF above: read as a signed number, everything from 2^31 up is negative, so max(., 0) sends
+// exactly the values cvttss2si cannot represent to 0 as well -- three instructions, no compare.
 __device__ __forceinline__ int cvtt_clamp(float v, int hi)
 {
-	int i = __float2int_rz(v);
-	if(v >= 2147483648.0f) i = 0;
+	const int i = (int)__float2uint_rz(v);
 	return min(max(i, 0), hi);
 }
 
