@@ -54,7 +54,10 @@ enum : uint32_t
 	// rz[d] (bits 12-15) is set on all four faces of a raised cell: with the three groups in the same
 	// per-face layout, one shift of the entry by the face code (done before the next cell is loaded)
 	// answers everything the slow path asks about the cell being left.
-	CM_SLOW_SHIFT = 4, CM_HWIN_SHIFT = 8, CM_RZ_SHIFT = 12, CM_REC_SHIFT = 16
+	CM_SLOW_SHIFT = 4, CM_HWIN_SHIFT = 8, CM_RZ_SHIFT = 12, CM_REC_SHIFT = 16,
+	// the value of `oobm` while the ray is outside the grid: it forces the slow bit on and masks the
+	// height-window bit off, each with the same single LOP3 that tests the bit
+	OOB_MARK = (1u << CM_SLOW_SHIFT) | (1u << CM_HWIN_SHIFT)
 };
 
 enum : uint32_t { PK_WALL = 0, PK_PASS = 1, PK_RAISED = 2 };   // what a 2-high room sees through a cell (trace.h:404-440)
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 		int ci = (cz + 1)*WP + cx + 1;
 		if(((unsigned)cx >= (unsigned)W) | ((unsigned)cz >= (unsigned)H))
 		{
-			oobm = 1u << CM_SLOW_SHIFT;
+			oobm = OOB_MARK;
 			ci = (((unsigned)cz >= (unsigned)H ? 0 : cz) + 1)*WP + ((unsigned)cx >= (unsigned)W ? 0 : cx) + 1;
 		}
 		int ldx = (gx < 0 ? PWN_FXN : PWN_FXP), ldz = (gz < 0 ? PWN_FZN : PWN_FZP);
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 #define PWN_OOB_FIX(XSTEP) do { \
 		if(!oobm) { const int row_ = ci / WP; if(!IDS) { cx = ci - row_*WP - 1; cz = row_ - 1; } } \
 		else if(!IDS) { if(XSTEP) cx += gx; else cz += gz; } \
-		oobm = (((unsigned)cx >= (unsigned)W) | ((unsigned)cz >= (unsigned)H)) ? (1u << CM_SLOW_SHIFT) : 0u; \
+		oobm = (((unsigned)cx >= (unsigned)W) | ((unsigned)cz >= (unsigned)H)) ? (uint32_t)OOB_MARK : 0u; \
 		ci = (((unsigned)cz >= (unsigned)H ? 0 : cz) + 1)*WP + ((unsigned)cx >= (unsigned)W ? 0 : cx) + 1; \
 		cell = __ldg(&L.cellmap[ci]); } while(0)
 
@@ -469,7 +472,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 				// outside the grid): leaving the grid, raised floors, 2-high room into anything else
 				if((faceb | oobm) & (1u << CM_SLOW_SHIFT))
 				{
-					if((faceb & (1u << CM_HWIN_SHIFT)) != 0u && oobm == 0u)
+					if(bit_of(faceb & ~oobm, 1u << CM_HWIN_SHIFT))
 					{
 						if(py < 0.0f || py > 1.0f) PWN_WALL_EXIT(SF_WALL)   // trace.h:415,432-439
 					}
