@@ -230,13 +230,13 @@ __device__ __forceinline__ void sphere_normal(const LevelDev &L, float hx, float
 	nx = __fmul_rn(nx, ns); ny = __fmul_rn(ny, ns); nz = __fmul_rn(nz, ns);
 }
 
-// CTA = 32 x K1_ROWS pixels, K1_ROWS/4 ... one warp per 8x4 pixels
+// CTA = 32 x K1_ROWS pixels = four warps of 8x4 pixels (or of 32x1 when the frame is reached over NVLink)
 constexpr int K1_ROWS = 4;
 constexpr int K1_THREADS = 32*K1_ROWS;
 #ifndef PWN_MIN_CTAS
 #define PWN_MIN_CTAS 8
 #endif
-constexpr int K1_MIN_CTAS = PWN_MIN_CTAS;   // 8 CTAs x 4 warps per SM at 64 registers; 9 (56 regs) and 10 (48 regs) spill and are slower
+constexpr int K1_MIN_CTAS = PWN_MIN_CTAS;   // 8 CTAs x 4 warps per SM; the kernel needs 54-56 registers, and 9 or 10 CTAs measure the same
 #ifndef PWN_SPH_MIN_CTAS
 #define PWN_SPH_MIN_CTAS 8
 #endif
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 	__shared__ float s_ray[3][K1_ROWS][32];
 	__shared__ float s_blend[2][6][K1_THREADS];
 
-	// ---- pixel of this thread: CTA = 32x8 pixels, warp = 8x4 ----------------------
+	// ---- pixel of this thread: CTA = 32 x K1_ROWS pixels, warp = 8x4 (or 32x1) ----------------------
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int tx = P.rowtile ? lane : (warp & 3)*8 + (lane & 7);
 	const int ty = P.rowtile ? warp : (warp >> 2)*4 + (lane >> 3);
