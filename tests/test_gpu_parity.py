@@ -256,8 +256,12 @@ def test_maze_wide_level(tracer, oracle):
     tracer.level_upload(lv)
     tracer.level_prepare_render()
     oracle_set_level(oracle, lv)
-    for pz in levels.poses_random(lv, 6, seed=1):
-        check_frame(tracer, oracle, pz["cam"], float(pz["sec_current"]), 480, 270, label="maze")
+    poses = levels.poses_random(lv, 16, seed=1)          # the 16 poses of BASELINE configs[3]
+    for k, pz in enumerate(poses):
+        check_frame(tracer, oracle, pz["cam"], float(pz["sec_current"]), 480, 270, label="maze %d" % k)
+    # pose 10 looks through a quarter-turn portal along a thin column of pixels: an experimental rewrite of
+    # the portal rotation got exactly that column wrong and passed everything at 480x270
+    check_frame(tracer, oracle, poses["cam"][10], float(poses["sec_current"][10]), 960, 540, label="maze 10 fine")
 
 
 def test_large_arguments_and_flags(tracer, oracle, default_level):
