@@ -633,7 +633,7 @@ def test_fuzz_random_levels(tracer, oracle, block):
         tracer.level_prepare_render(lv)
         oracle_set_level(oracle, lv)
         for k, pose in enumerate(fuzz_levels.random_poses(lv, seed, 3)):
-            check_frame(tracer, oracle, pose["cam"], float(pose["sec_current"]), 160, 96, label="fuzz %d/%d" % (seed, k))
+            check_frame(tracer, oracle, pose["cam"], float(pose["sec_current"]), 320, 192, label="fuzz %d/%d" % (seed, k))
 
 
 def test_blur_on_arbitrary_frames(tracer, oracle, default_level):
@@ -665,4 +665,4 @@ def test_fuzz_wide_levels(tracer, oracle):
         tracer.level_prepare_render()
         oracle_set_level(oracle, lv)
         for k, pose in enumerate(fuzz_levels.random_poses(lv, seed, 3, dim=96)):
-            check_frame(tracer, oracle, pose["cam"], float(pose["sec_current"]), 160, 96, label="wide fuzz %d/%d" % (seed, k))
+            check_frame(tracer, oracle, pose["cam"], float(pose["sec_current"]), 320, 192, label="wide fuzz %d/%d" % (seed, k))
