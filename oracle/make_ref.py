@@ -199,6 +199,9 @@ def main():
             _write(d_wi, h, wide[h])
         _write(d_wi, "trace.h", instrument_trace(wide["trace.h"]))
         cc("libref_wide_ids.so", [d_wi], ["REF_NO_BLUR", "REF_WIDE", "REF_IDS"], REF_CFLAGS)
+        # the same instrumented wide sources without -ffast-math: the strict build of the restatement must
+        # match it to the bit, ids of all three segments included
+        cc("libref_wide_ids_strict.so", [d_wi], ["REF_NO_BLUR", "REF_WIDE", "REF_IDS"], STRICT_CFLAGS)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     print("make_ref: built %s" % sorted(os.listdir(OUT)))

@@ -103,22 +103,39 @@ def test_golden_frames(oracle, default_level):
 
 
 def _compare(oracle, ref, ref_strict, cam, sec, w, h, dim_ref=64):
+    """ref: an instrumented build with the shipped flags; ref_strict: the same sources without -ffast-math
+    (instrumented or not).  Against ref: zbuf and the primary segment's ids bit-exact; bounce-segment ids
+    and sbuf may differ on a few grazing pixels per million (gcc's fast-math code generation moves a
+    jittered bounce ray by an ulp) -- counted and bounded.  Against ref_strict the strict build of the
+    restatement (oracle.twin) is exact: sbuf, zbuf and, when ref_strict is instrumented, every id."""
     s, z, ids, _ = ref.trace_frame(cam, sec, w, h, want_ids=True)
     so, zo, io = oracle.trace_frame(cam, sec, w, h, want_ids=True)
     assert (z.view(np.uint32) == zo.view(np.uint32)).all()
     for f in IDF:
-        assert (ids[f] == io[f]).all(), f
+        assert (ids[..., 0][f] == io[..., 0][f]).all(), f
+    graze = np.zeros((h, w), bool)
+    for seg in (1, 2):
+        for f in IDF:
+            graze |= ids[..., seg][f] != io[..., seg][f]
     d = rgb_diff(s, so)
-    assert d.max() <= 1 and (d > 0).mean() < 1e-5
+    budget = max(2, int(1e-5 * w * h))
+    assert graze.sum() <= budget, int(graze.sum())
+    assert (d[~graze] <= 1).all() and ((d > 0) & ~graze).sum() <= budget
     if ref_strict is not None:
-        # the reference sources built WITHOUT -ffast-math against the restatement built without the
-        # mirrored randfs folding (oracle.twin): equal to the bit.  Against the mirrored build a 1-ulp
-        # jitter difference may flip a colour byte once in a few million pixels.
-        ss, zs, _, _ = ref_strict.trace_frame(cam, sec, w, h)
-        st, zt, _ = oracle.twin.trace_frame(cam, sec, w, h)
+        want_ids = ref_strict.has_ids
+        ss, zs, ids_s, _ = ref_strict.trace_frame(cam, sec, w, h, want_ids=want_ids)
+        st, zt, it = oracle.twin.trace_frame(cam, sec, w, h, want_ids=want_ids)
         assert (ss == st).all() and (zs.view(np.uint32) == zt.view(np.uint32)).all()
-        assert (zs.view(np.uint32) == zo.view(np.uint32)).all() and (rgb_diff(ss, so) > 0).sum() <= 2
+        if want_ids:
+            for f in IDF:
+                assert (ids_s[f] == it[f]).all(), f
+        assert (zs.view(np.uint32) == zo.view(np.uint32)).all() and (rgb_diff(ss, so) > 0).sum() <= budget
     return s, z, so, zo
+
+
+def _wide_strict(refs):
+    from oracle import refbind
+    return refs("libref_wide_ids_strict.so") if refbind.available("libref_wide_ids_strict.so") else None
 
 
 def _compare_ids_only(oracle, ref, cam, sec, w, h):
@@ -282,13 +299,17 @@ def test_wide_reference_equals_unmodified_on_default_level(refs, default_level, 
 
 def test_maze_vs_wide_reference(oracle, refs):
     lv = levels.maze(dim=128, seed=1)
-    wide = refs("libref_wide_ids.so")
-    wide.level_set(lv.cells, lv.portals_i32(), lv.sx, lv.sz)
+    wide, wide_strict = refs("libref_wide_ids.so"), _wide_strict(refs)
+    for r in (wide, wide_strict):
+        if r is not None:
+            r.level_set(lv.cells, lv.portals_i32(), lv.sx, lv.sz)
     oracle_set_level(oracle, lv)
-    poses = levels.poses_random(lv, 6, seed=1)
+    poses = levels.poses_random(lv, 16, seed=1)          # the 16 poses of BASELINE configs[3]
+    # pose 10 at a finer grid: a quarter-turn portal seen through a thin column of pixels (see tests/test_gpu_parity.py)
+    _compare(oracle, wide, wide_strict, poses["cam"][10], float(poses["sec_current"][10]), 960, 540)
     crossed = 0
     for pz in poses:
-        s, z, so, zo = _compare(oracle, wide, None, pz["cam"], float(pz["sec_current"]), 256, 144)
+        s, z, so, zo = _compare(oracle, wide, wide_strict, pz["cam"], float(pz["sec_current"]), 256, 144)
         _, _, ids = oracle.trace_frame(pz["cam"], float(pz["sec_current"]), 64, 36, want_ids=True)
         crossed += int(ids["nportal"].sum())
     assert crossed > 0
@@ -376,12 +397,14 @@ def test_fuzz_wide_levels_vs_wide_reference(oracle, refs, seed):
     build of the reference: ids + zbuf bit-exact, sbuf within 1 LSB"""
     import fuzz_levels
     lv = fuzz_levels.random_wide_level(seed)
-    wide = refs("libref_wide_ids.so")
-    wide.level_set(lv.cells, lv.portals_i32(), lv.sx, lv.sz)
+    wide, wide_strict = refs("libref_wide_ids.so"), _wide_strict(refs)
+    for r in (wide, wide_strict):
+        if r is not None:
+            r.level_set(lv.cells, lv.portals_i32(), lv.sx, lv.sz)
     oracle_set_level(oracle, lv)
     crossed = 0
     for pose in fuzz_levels.random_poses(lv, seed, 3, dim=96):
-        _compare(oracle, wide, None, pose["cam"], float(pose["sec_current"]), 160, 96)
+        _compare(oracle, wide, wide_strict, pose["cam"], float(pose["sec_current"]), 160, 96)
         _, _, ids = oracle.trace_frame(pose["cam"], float(pose["sec_current"]), 160, 96, want_ids=True)
         crossed += int(ids["nportal"].sum())
     assert crossed > 0
