@@ -184,6 +184,7 @@ def main():
         os.makedirs(d_ids)
         _write(d_ids, "trace.h", instrument_trace(files["trace.h"]))
         cc("libref_ids.so", [d_ids, REF], ["REF_NO_BLUR", "REF_IDS"], REF_CFLAGS)
+        cc("libref_ids_strict.so", [d_ids, REF], ["REF_NO_BLUR", "REF_IDS"], STRICT_CFLAGS)
 
         wide = widen(files)
         d_w = os.path.join(tmp, "wide")

@@ -133,6 +133,12 @@ def _compare(oracle, ref, ref_strict, cam, sec, w, h, dim_ref=64):
     return s, z, so, zo
 
 
+def _strict(refs):
+    """the reference sources without -ffast-math: the instrumented build when it exists (ids of all segments)"""
+    from oracle import refbind
+    return refs("libref_ids_strict.so") if refbind.available("libref_ids_strict.so") else refs("libref_strict.so")
+
+
 def _wide_strict(refs):
     from oracle import refbind
     return refs("libref_wide_ids_strict.so") if refbind.available("libref_wide_ids_strict.so") else None
@@ -148,7 +154,7 @@ def _compare_ids_only(oracle, ref, cam, sec, w, h):
 
 
 def test_default_level_vs_reference(oracle, refs, default_level, tmp_path):
-    ref, strict, refb = refs("libref_ids.so"), refs("libref_strict.so"), refs("libref.so")
+    ref, strict, refb = refs("libref_ids.so"), _strict(refs), refs("libref.so")
     p = str(tmp_path / "level.txt")
     default_level.save_txt(p)
     for r in (ref, strict, refb):
@@ -196,7 +202,7 @@ def test_compile_time_switches_vs_reference(oracle, refs, default_level, tmp_pat
 def test_lowercase_portal_quirk_vs_reference(oracle, refs, default_level, tmp_path):
     """level.txt:5 has a lower-case 'm': the cell joins pair M and then BECOMES 'N' (level.h:144-161), so
     M at (4,3) leads into a cell that answers as the unpaired N.  Poses that look straight at both."""
-    ref, strict = refs("libref_ids.so"), refs("libref_strict.so")
+    ref, strict = refs("libref_ids.so"), _strict(refs)
     p = str(tmp_path / "level.txt")
     default_level.save_txt(p)
     for r in (ref, strict):
@@ -228,7 +234,7 @@ def test_flythrough_poses_vs_reference(oracle, refs, default_level, tmp_path):
 
 def test_mirror_hall_vs_reference(oracle, refs, tmp_path):
     lv = levels.mirror_hall()
-    ref, strict = refs("libref_ids.so"), refs("libref_strict.so")
+    ref, strict = refs("libref_ids.so"), _strict(refs)
     p = str(tmp_path / "hall.txt")
     lv.save_txt(p)
     ref.level_load(p)
@@ -252,7 +258,7 @@ def test_mirror_hall_vs_reference(oracle, refs, tmp_path):
 
 
 def test_spheres_vs_reference(oracle, refs, default_level, tmp_path):
-    ref, strict = refs("libref_ids.so"), refs("libref_strict.so")
+    ref, strict = refs("libref_ids.so"), _strict(refs)
     p = str(tmp_path / "level.txt")
     default_level.save_txt(p)
     lv = levels.game_spheres(levels.default_level(), sec=0.3)
@@ -318,7 +324,7 @@ def test_maze_vs_wide_reference(oracle, refs):
 def test_open_border_level_vs_reference(oracle, refs, tmp_path):
     """rays that leave the grid: get_cell folds the lookup to index 0 on that axis (util.h:151-158)"""
     lv = levels.open_border()
-    ref, strict = refs("libref_ids.so"), refs("libref_strict.so")
+    ref, strict = refs("libref_ids.so"), _strict(refs)
     p = str(tmp_path / "open.txt")
     lv.save_txt(p)
     ref.level_load(p)
@@ -364,7 +370,7 @@ def test_fuzz_random_levels_vs_reference(oracle, refs, tmp_path, seed):
     reference's level_load reads, and every frame matches (ids + zbuf bit-exact vs the shipped
     flags, sbuf bit-exact vs the strict build)"""
     import fuzz_levels
-    ref, strict = refs("libref_ids.so"), refs("libref_strict.so")
+    ref, strict = refs("libref_ids.so"), _strict(refs)
     txt = fuzz_levels.random_level_text(seed, open_edges=(seed % 4 == 3))
     p = str(tmp_path / "level.txt")
     open(p, "wb").write(txt)
