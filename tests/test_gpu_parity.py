@@ -307,6 +307,21 @@ def test_lowercase_portal_quirk(tracer, oracle, default_level):
         check_frame(tracer, oracle, cam, 0.5, 320, 200, label="quirk %g %g %g" % (x, z, yaw))
 
 
+def test_axis_aligned_rays(tracer, oracle, default_level):
+    """rays with exactly zero components (EPSILON clamp, trace.h:220-222): power-of-two frames from the
+    unrotated spawn camera, and the same camera turned by an exact quarter"""
+    tracer.level_upload(default_level)
+    tracer.level_prepare_render()
+    oracle_set_level(oracle, default_level)
+    cam = api.cam_spawn(default_level)
+    cam2 = cam.copy()
+    cam2[0:3] = (0.0, 0.0, 1.0)
+    cam2[8:11] = (-1.0, 0.0, 0.0)
+    for c in (cam, cam2):
+        for (w, h) in [(64, 32), (256, 128), (32, 64)]:
+            check_frame(tracer, oracle, c, 0.25, w, h, label="axis %dx%d" % (w, h))
+
+
 def test_compile_time_switches(tracer, oracle, default_level):
     """REFLECT 0 / 1 (pwn_trace_config) and REFLECT_BLUR off (PWN_F_NO_REFLECT_BLUR), defs.h:6-8"""
     tracer.level_upload(default_level)

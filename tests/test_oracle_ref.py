@@ -221,6 +221,28 @@ def test_lowercase_portal_quirk_vs_reference(oracle, refs, default_level, tmp_pa
     assert saw > 1000          # primary rays did cross M
 
 
+def test_axis_aligned_rays_vs_reference(oracle, refs, default_level, tmp_path):
+    """power-of-two frames from the unrotated spawn camera: the column x = w/2 - 1 has ray.x == 0 and
+    the row y = h/2 has ray.y == 0 exactly, so the EPSILON clamp of trace.h:220-222 and the
+    infinite/huge reciprocals behind it are on the path (they are almost never taken otherwise)"""
+    ref, strict = refs("libref_ids.so"), _strict(refs)
+    p = str(tmp_path / "level.txt")
+    default_level.save_txt(p)
+    for r in (ref, strict):
+        r.level_load(p)
+    oracle_set_level(oracle, default_level)
+    cam = api.cam_spawn(default_level)
+    for (w, h) in [(64, 32), (256, 128), (32, 64)]:
+        rb, rx, ry = api.ray_setup(cam, w, h)
+        assert rb[0] + np.float32(w // 2) * rx[0] == 0 and rb[1] + np.float32(h // 2) * ry[1] == 0
+        _compare(oracle, ref, strict, cam, 0.25, w, h)
+    # the same looking straight along -x (a quarter turn of the camera rows, exact)
+    cam2 = cam.copy()
+    cam2[0:3] = (0.0, 0.0, 1.0)
+    cam2[8:11] = (-1.0, 0.0, 0.0)
+    _compare(oracle, ref, strict, cam2, 0.25, 64, 32)
+
+
 def test_flythrough_poses_vs_reference(oracle, refs, default_level, tmp_path):
     ref = refs("libref_ids.so")
     p = str(tmp_path / "level.txt")
