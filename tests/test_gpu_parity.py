@@ -320,6 +320,11 @@ def test_axis_aligned_rays(tracer, oracle, default_level):
     for c in (cam, cam2):
         for (w, h) in [(64, 32), (256, 128), (32, 64)]:
             check_frame(tracer, oracle, c, 0.25, w, h, label="axis %dx%d" % (w, h))
+    for pos in ((9.0, 0.5, 4.0), (9.0, 0.0, 5.0), (10.0, 1.0, 4.5), (9.0, 0.5, 5.0)):
+        for yaw in (0.0, 0.8):
+            c3 = api.mat4_roty(cam, yaw)
+            c3[12:15] = pos
+            check_frame(tracer, oracle, c3, 0.25, 96, 64, label="on the grid lines")
 
 
 def test_compile_time_switches(tracer, oracle, default_level):

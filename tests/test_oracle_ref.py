@@ -241,6 +241,12 @@ def test_axis_aligned_rays_vs_reference(oracle, refs, default_level, tmp_path):
     cam2[0:3] = (0.0, 0.0, 1.0)
     cam2[8:11] = (-1.0, 0.0, 0.0)
     _compare(oracle, ref, strict, cam2, 0.25, 64, 32)
+    # the camera exactly on cell boundaries and on the floor / ceiling planes: zero distances to the first planes
+    for pos in ((9.0, 0.5, 4.0), (9.0, 0.0, 5.0), (10.0, 1.0, 4.5), (9.0, 0.5, 5.0)):
+        for yaw in (0.0, 0.8):
+            c3 = api.mat4_roty(cam, yaw)
+            c3[12:15] = pos
+            _compare(oracle, ref, strict, c3, 0.25, 96, 64)
 
 
 def test_flythrough_poses_vs_reference(oracle, refs, default_level, tmp_path):
