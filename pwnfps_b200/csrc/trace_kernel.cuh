@@ -646,7 +646,9 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 		}
 
 		// ================= shading =================
-		float cb, cg, cr, ca, refl;
+		// the shaded colour is the child's icol (trace.h:90): it is built in place
+		float &cb = icb, &cg = icg, &cr = icr, &ca = ica;
+		float refl;
 		if(!SPH || hkind == 0)
 		{
 			// trace_hit_wall, trace.h:108-154
@@ -746,30 +748,27 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 			seed = (seed * 25739u + 4u) & 0x7FFFFFFFu;
 		}
 
-		{
-			float (*sb)[K1_THREADS] = s_blend[seg];
-			sb[0][threadIdx.x] = cb; sb[1][threadIdx.x] = cg; sb[2][threadIdx.x] = cr; sb[3][threadIdx.x] = ca;
-			sb[4][threadIdx.x] = refl; sb[5][threadIdx.x] = fog;
-		}
+		// (indexed directly: through a pointer variable the compiler addresses shared memory generically
+		// and rebuilds the window base from the cluster CTA id at every bounce)
+		s_blend[seg][0][threadIdx.x] = cb; s_blend[seg][1][threadIdx.x] = cg; s_blend[seg][2][threadIdx.x] = cr;
+		s_blend[seg][3][threadIdx.x] = ca; s_blend[seg][4][threadIdx.x] = refl; s_blend[seg][5][threadIdx.x] = fog;
 		depth = seg + 1;
 
 		// child: trace_ray(hitctr+1, seed, lv, dist, &pos, &ray, col)  (trace.h:90)
 		fx = npx; fy = npy; fz = npz;
 		irx = nrx; iry = nry; irz = nrz;
-		icb = cb; icg = cg; icr = cr; ica = ca;
 	}
 
 	// ---- unwind the blends, deepest first (trace.h:91-101) ------------------------------
 	#pragma unroll 1
 	for(int lvl = depth - 1; lvl >= 0; lvl--)
 	{
-		float (*sb)[K1_THREADS] = s_blend[lvl];
-		const float refl = sb[4][threadIdx.x], fogl = sb[5][threadIdx.x];
+		const float refl = s_blend[lvl][4][threadIdx.x], fogl = s_blend[lvl][5][threadIdx.x];
 		const float k = __fsub_rn(1.0f, refl);
-		ob = __fadd_rn(__fmul_rn(refl, ob), __fmul_rn(k, sb[0][threadIdx.x]));
-		og = __fadd_rn(__fmul_rn(refl, og), __fmul_rn(k, sb[1][threadIdx.x]));
-		orr = __fadd_rn(__fmul_rn(refl, orr), __fmul_rn(k, sb[2][threadIdx.x]));
-		oa = __fadd_rn(__fmul_rn(refl, oa), __fmul_rn(k, sb[3][threadIdx.x]));
+		ob = __fadd_rn(__fmul_rn(refl, ob), __fmul_rn(k, s_blend[lvl][0][threadIdx.x]));
+		og = __fadd_rn(__fmul_rn(refl, og), __fmul_rn(k, s_blend[lvl][1][threadIdx.x]));
+		orr = __fadd_rn(__fmul_rn(refl, orr), __fmul_rn(k, s_blend[lvl][2][threadIdx.x]));
+		oa = __fadd_rn(__fmul_rn(refl, oa), __fmul_rn(k, s_blend[lvl][3][threadIdx.x]));
 		if(fogl != 0.0f)
 		{
 			const float f = libm_expf<LFMA>(__fmul_rn(-0.6f, fogl)), g = __fsub_rn(1.0f, f);
