@@ -207,6 +207,12 @@ __device__ __forceinline__ bool bit_of(uint32_t v, uint32_t mask)
 
 // surface colours, lanes b g r a (defs.h:17-19, trace.h:558)
 enum : int { SF_CEIL = 0, SF_FLOOR = 1, SF_WALL = 2, SF_STRAY = 3 };
+__constant__ float4 c_surface[4] = {
+	{30.0f, 30.0f, 0.0f, 0.0f},   // COL_CEIL
+	{1.0f, 1.0f, 1.0f, 0.0f},     // COL_FLOOR
+	{0.8f, 0.8f, 1.0f, 0.0f},     // COL_WALL
+	{5.0f, 0.0f, 5.0f, 0.0f}      // a third cell with a portal's letter (trace.h:558)
+};
 
 // Nearest sphere so far (trace.h:196-200: aux_dist, aux_pos, aux_norm, aux_col, aux_refl).  The
 // reference keeps thirteen floats; six registers carry the same information: the normal, the colour
@@ -653,11 +659,10 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 		{
 			// trace_hit_wall, trace.h:108-154
 			if(IDS) ops += W_WALL;
-			float sb, sg, sr;
-			if(hsurf == SF_CEIL) { sb = 30.0f; sg = 30.0f; sr = 0.0f; }
-			else if(hsurf == SF_FLOOR) { sb = 1.0f; sg = 1.0f; sr = 1.0f; }
-			else if(hsurf == SF_WALL) { sb = 0.8f; sg = 0.8f; sr = 1.0f; }
-			else { sb = 5.0f; sg = 0.0f; sr = 5.0f; }
+			// one indexed load from the constant bank instead of a four-way branch: the lanes of a warp hit
+			// ceilings, floors and walls side by side
+			const float4 sc = c_surface[hsurf];
+			const float sb = sc.x, sg = sc.y, sr = sc.z;
 			cb = __fmul_rn(icb, sb); cg = __fmul_rn(icg, sg); cr = __fmul_rn(icr, sr); ca = __fmul_rn(ica, 0.0f);
 			// diffuse = +-ray[axis(ldir)]: FXP FZP FXN FZN FYP FYN = 0..5
 			float diffuse = (ldir >= PWN_FYP) ? ry : ((ldir & 1) ? rz : rx);
