@@ -611,10 +611,17 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 				stepz = gz*WP;
 				ldx = (gx < 0 ? PWN_FXN : PWN_FXP); ldz = (gz < 0 ? PWN_FZN : PWN_FZP);
 				// step out of the destination portal cell (trace.h:624-647)
-				if(ldir == PWN_FXP) { ci++; px = __fadd_rn(px, 1.0f); if(IDS) cx++; }
-				else if(ldir == PWN_FZP) { ci += WP; pz = __fadd_rn(pz, 1.0f); if(IDS) cz++; }
-				else if(ldir == PWN_FXN) { ci--; px = __fsub_rn(px, 1.0f); if(IDS) cx--; }
-				else { ci -= WP; pz = __fsub_rn(pz, 1.0f); if(IDS) cz--; }
+				{
+					// FXP FZP FXN FZN = 0 1 2 3: bit 0 = along z, bit 1 = backwards (a - 1.0f and a + (-1.0f) are
+					// the same operation); selects instead of a four-way branch
+					const bool onz = (ldir & 1) != 0, neg = (ldir & 2) != 0;
+					const float one = neg ? -1.0f : 1.0f;
+					const int sgn = neg ? -1 : 1;
+					ci += onz ? sgn*WP : sgn;
+					px = onz ? px : __fadd_rn(px, one);
+					pz = onz ? __fadd_rn(pz, one) : pz;
+					if(IDS) { if(onz) cz += sgn; else cx += sgn; }
+				}
 				cell = __ldg(&L.cellmap[ci]);
 				if((cell & 15u) == CL_OOB) PWN_OOB_FIX(false);   // a portal on the rim: never outside before the step
 				PWN_SPHERE_EXIT(false, 0.0f)   // trace.h:668-673
