@@ -169,7 +169,7 @@ pwn_level *pwn_level_parse(const char *text, size_t len)
 			}
 			if(c >= 'A' && c <= 'Z')     /* level.h:163-178 */
 				portal_register(&lv->portals[c-'A'], x, z);
-			lv->cells[z*64 + x] = c;
+			lv->cells[z*64 + x] = (int32_t)(signed char)c;   /* `char data[64][64]` (defs.h:105): bytes >= 128 are negative there too */
 		}
 	}
 done_load:
@@ -215,7 +215,7 @@ static pwn_level *parse_extended(const char *text, size_t len)
 				c = (c-'a')+'A' + 1;
 			}
 			if(c >= 'A' && c <= 'Z') portal_register(&lv->portals[c-'A'], x, z);
-			lv->cells[z*w + x] = c;
+			lv->cells[z*w + x] = (int32_t)(signed char)c;
 		}
 		if(x == w)   /* a full row: drop the rest of its line, as a 64-wide row of the reference drops nothing */
 		{

@@ -442,3 +442,33 @@ def test_fuzz_wide_levels_vs_wide_reference(oracle, refs, seed):
         _, _, ids = oracle.trace_frame(pose["cam"], float(pose["sec_current"]), 160, 96, want_ids=True)
         crossed += int(ids["nportal"].sum())
     assert crossed > 0
+
+
+def test_loader_on_random_bytes_vs_reference(refs, tmp_path):
+    """the level.txt loader restatement against the reference's level_load on 300 random files: random
+    draws from the level alphabet with CR/LF noise, over-long and short rows, more than 64 rows, and
+    arbitrary bytes (>= 128 included: `char data[64][64]` is signed, so are the cells here)"""
+    ref = refs("libref_noblur.so")
+    rng = np.random.default_rng(0)
+    alphabet = np.frombuffer(b";;;;;;##$&\"><,^...  \n\n\r\nABCDEFabcdXYZyz*@!~\t0", np.uint8)
+    p = str(tmp_path / "level.txt")
+    for it in range(300):
+        n = int(rng.integers(0, 6000))
+        if it % 5 == 0:
+            txt = rng.integers(1, 256, n, dtype=np.uint8).tobytes()
+        else:
+            txt = alphabet[rng.integers(0, len(alphabet), n)].tobytes()
+        open(p, "wb").write(txt)
+        ref.level_load(p)
+        cells, pm = ref.level_get()
+        lv = api.level_parse(txt)
+        mine = lv.portals_i32()
+        assert (cells == lv.cells).all(), it
+        assert (pm[:, :4] == mine[:, :4]).all(), it
+        # rot12 / c1 / c2 come from the four neighbours of each end (level.h:194-221); for an end on the
+        # rim of the grid the reference reads outside `data` (util.h:140-149, unchecked): undefined, skipped
+        inner = np.ones(len(pm), bool)
+        for k in (0, 1, 2, 3):
+            inner &= (pm[:, k] == -1) | ((pm[:, k] >= 1) & (pm[:, k] <= 62))
+        assert (pm[inner] == mine[inner]).all(), it
+        assert ref.spawn() == (lv.sx, lv.sz), it
