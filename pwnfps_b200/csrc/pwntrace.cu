@@ -373,6 +373,7 @@ extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells
 		const uint32_t c = map[ci] & 15u;
 		if(!(c & 8u)) continue;   // rooms only
 		if(c == CL_RAISED) map[ci] |= 15u << CM_RZ_SHIFT;
+		if(c == CL_TWO || c == CL_TWO_FOG) map[ci] |= 15u << CM_TWO_SHIFT;
 		const long nb[4] = {1, wp, -1, -wp};   // FXP FZP FXN FZN (defs.h:25-33)
 		for(int d = 0; d < 4; d++)
 		{

@@ -55,6 +55,7 @@ enum : uint32_t
 	// per-face layout, one shift of the entry by the face code (done before the next cell is loaded)
 	// answers everything the slow path asks about the cell being left.
 	CM_SLOW_SHIFT = 4, CM_HWIN_SHIFT = 8, CM_RZ_SHIFT = 12, CM_REC_SHIFT = 16,
+	CM_TWO_SHIFT = 16,   // rooms have no portal record: on a 2-high room bits 16-19 repeat "2-high" once per face
 	// the value of `oobm` while the ray is outside the grid: it forces the slow bit on and masks the
 	// height-window bit off, each with the same single LOP3 that tests the bit
 	OOB_MARK = (1u << CM_SLOW_SHIFT) | (1u << CM_HWIN_SHIFT)
@@ -176,6 +177,16 @@ __device__ __forceinline__ uint32_t pack_lane(float v)
 	return (s >= 2147483648.0f) ? 0u : q;
 }
 
+// the lanes of a packed pixel whose scaled value is 2^31 or more become 0 (cvtps2dq's "indefinite" through the two packs)
+__device__ __noinline__ uint32_t pack_huge(float s0, float s1, float s2, float s3, uint32_t word)
+{
+	if(s0 >= 2147483648.0f) word &= 0xFFFFFF00u;
+	if(s1 >= 2147483648.0f) word &= 0xFFFF00FFu;
+	if(s2 >= 2147483648.0f) word &= 0xFF00FFFFu;
+	if(s3 >= 2147483648.0f) word &= 0x00FFFFFFu;
+	return word;
+}
+
 // col_ftoint (util.h:48-59) alone, for known-answer tests of the pack (pwn_debug_pack)
 __global__ void k_pack_eval(const float4 *in, uint32_t *out, int n)
 {
@@ -186,14 +197,9 @@ __global__ void k_pack_eval(const float4 *in, uint32_t *out, int n)
 }
 
 // The portal rotation exchanges x and z quantities.  Written as plain copies the exchange becomes a
-// cyclic register copy that ptxas resolves with moves at the head of EVERY walk iteration; written
-// as integer arithmetic (xor swap, xor with an opaque zero) the rare portal path pays for it instead.
-__device__ __forceinline__ void xswap(float &a, float &b)
-{
-	uint32_t x = __float_as_uint(a), y = __float_as_uint(b);
-	x ^= y; y ^= x; x ^= y;
-	a = __uint_as_float(x); b = __uint_as_float(y);
-}
+// cyclic register copy that ptxas resolves with moves at the head of EVERY walk iteration.  The ray
+// direction and the signs go through an xor with an opaque zero; the step state (wx/wz, iax/iaz) goes
+// through shared memory (PWN_XCHG in k_trace), which removes the copies altogether.
 __device__ __forceinline__ float xmov(float v, uint32_t zero) { return __uint_as_float(__float_as_uint(v) ^ zero); }
 
 // one bit of a map entry as a predicate.  Written in PTX so that the front end cannot rewrite the test
@@ -206,7 +212,7 @@ __device__ __forceinline__ bool bit_of(uint32_t v, uint32_t mask)
 }
 
 // surface colours, lanes b g r a (defs.h:17-19, trace.h:558)
-enum : int { SF_CEIL = 0, SF_FLOOR = 1, SF_WALL = 2, SF_STRAY = 3 };
+enum : int { SF_CEIL = 0, SF_FLOOR = 1, SF_WALL = 2, SF_STRAY = 3, SF_NONE = 4, SF_SPHERE = 5 };
 __constant__ float4 c_surface[4] = {
 	{30.0f, 30.0f, 0.0f, 0.0f},   // COL_CEIL
 	{1.0f, 1.0f, 1.0f, 0.0f},     // COL_FLOOR
@@ -236,6 +242,16 @@ __device__ __forceinline__ void sphere_normal(const LevelDev &L, float hx, float
 	nx = __fmul_rn(nx, ns); ny = __fmul_rn(ny, ns); nz = __fmul_rn(nz, ns);
 }
 
+// trace.h:220-222: a ray component nearer to zero than EPSILON (defs.h:1) becomes +-EPSILON
+__device__ __noinline__ float3 eps_clamp(float rx, float ry, float rz)
+{
+	const float EPS = 0.0000000000001f;
+	if(fabsf(rx) < EPS) rx = (rx < 0.0f ? -EPS : EPS);
+	if(fabsf(ry) < EPS) ry = (ry < 0.0f ? -EPS : EPS);
+	if(fabsf(rz) < EPS) rz = (rz < 0.0f ? -EPS : EPS);
+	return make_float3(rx, ry, rz);
+}
+
 // CTA = 32 x K1_ROWS pixels = four warps of 8x4 pixels (or of 32x1 when the frame is reached over NVLink)
 constexpr int K1_ROWS = 4;
 constexpr int K1_THREADS = 32*K1_ROWS;
@@ -262,6 +278,15 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 	const LevelDev &L = P.lv;
 	__shared__ float s_ray[3][K1_ROWS][32];
 	__shared__ float s_blend[2][6][K1_THREADS];
+	// a quarter-turn portal exchanges the x and z step state through shared memory: a register exchange
+	// makes ptxas keep copies of the exchanged values at the head of EVERY walk iteration
+	__shared__ float s_xchg[4][K1_THREADS];
+#define PWN_XCHG { const uint32_t q_ = (uint32_t)__cvta_generic_to_shared(&s_xchg[0][threadIdx.x]); \
+		asm volatile("st.shared.f32 [%0], %1; st.shared.f32 [%0+512], %2; st.shared.f32 [%0+1024], %3; st.shared.f32 [%0+1536], %4;" \
+			:: "r"(q_), "f"(wx), "f"(wz), "f"(iax), "f"(iaz) : "memory"); \
+		asm volatile("ld.shared.f32 %0, [%4]; ld.shared.f32 %1, [%4+512]; ld.shared.f32 %2, [%4+1024]; ld.shared.f32 %3, [%4+1536];" \
+			: "=f"(wz), "=f"(wx), "=f"(iaz), "=f"(iax) : "r"(q_) : "memory"); }
+static_assert(K1_THREADS*4 == 512, "PWN_XCHG offsets");
 
 	// ---- pixel of this thread: CTA = 32 x K1_ROWS pixels, warp = 8x4 (or 32x1) ----------------------
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -325,14 +350,15 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 		}
 		int cx = __float2int_rz(fx), cz = __float2int_rz(fz);   // real cell coordinates (IDS builds keep them current)
 		const float EPS = 0.0000000000001f;
-		if(fminf(fminf(fabsf(rx), fabsf(ry)), fabsf(rz)) < EPS)   // trace.h:220-222, almost never taken
-		{
-			if(fabsf(rx) < EPS) rx = (rx < 0.0f ? -EPS : EPS);
-			if(fabsf(ry) < EPS) ry = (ry < 0.0f ? -EPS : EPS);
-			if(fabsf(rz) < EPS) rz = (rz < 0.0f ? -EPS : EPS);
+		if(fminf(fminf(fabsf(rx), fabsf(ry)), fabsf(rz)) < EPS)   // trace.h:220-222, almost never taken: a real call keeps
+		{                                                         // the clamp out of the instruction stream of every segment
+			const float3 c3 = eps_clamp(rx, ry, rz);
+			rx = c3.x; ry = c3.y; rz = c3.z;
 		}
 		int gx = (irx < 0.0f ? -1 : 1), gz = (irz < 0.0f ? -1 : 1);
 		const bool up = !(iry < 0.0f);                          // gy > 0
+		uint32_t upmask = up ? 2u : 0u;
+		asm volatile("" : "+r"(upmask));   // a value of its own: ptxas would otherwise rebuild it from the ray at every step
 		float iax = rcp_emul(L, rx), iaz = rcp_emul(L, rz);   // iavel = rcpps(abs(ray)), trace.h:229-231
 		const float iay = rcp_emul(L, ry);
 		float px = fx, py = fy, pz = fz;
@@ -362,16 +388,20 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 		aux.dist = -1.0f;
 		aux.px = aux.py = aux.pz = 0.0f; aux.diff = 0.0f; aux.si = 0u;
 
-		int hkind = 2, hsurf = SF_WALL;   // 0 wall/floor/ceiling, 1 sphere, 2 exhausted
-		float hdist = 0.0f;               // what the reference stores to *dist
+		// how the walk ended: a surface (SF_CEIL..SF_STRAY), a sphere, or not at all (maxsteps, trace.h:677).
+		// What the reference stores to *dist is cdist as the walk left it, or the sphere's distance.
+		int hsurf = SF_NONE;
+#define hkind (hsurf < SF_NONE ? 0 : (hsurf == SF_SPHERE ? 1 : 2))
+#define hdist ((SPH && hsurf == SF_SPHERE) ? aux.dist : cdist)
 
 // the "sphere nearer than where we got to" exits (trace.h:313-319 and friends)
+#define PWN_SPHERE_MARK hsurf = SF_SPHERE; ldir = -1;
 #define PWN_SPHERE_EXIT(FOGC, FOGBEG) \
 		if(SPH && aux.dist != -1.0f && cdist > aux.dist) { \
-			hkind = 1; ldir = -1; hdist = aux.dist; \
+			PWN_SPHERE_MARK \
 			if((FOGC) && aux.dist > (FOGBEG)) fog = __fadd_rn(fog, __fsub_rn(aux.dist, (FOGBEG))); \
 			break; }
-#define PWN_WALL_EXIT(SURF) { hkind = 0; hsurf = (SURF); hdist = cdist; break; }
+#define PWN_WALL_EXIT(SURF) { hsurf = (SURF); break; }
 // The step just taken (along x if XSTEP) put the ray on the border of the padded map, or the ray
 // already was outside the grid: bring the real cell coordinates up to date and look the cell up
 // the way get_cell does (util.h:151-158).  Builds with IDS keep cx/cz current themselves.
@@ -381,6 +411,15 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 		oobm = (((unsigned)cx >= (unsigned)W) | ((unsigned)cz >= (unsigned)H)) ? (uint32_t)OOB_MARK : 0u; \
 		ci = (((unsigned)cz >= (unsigned)H ? 0 : cz) + 1)*WP + ((unsigned)cx >= (unsigned)W ? 0 : cx) + 1; \
 		cell = __ldg(&L.cellmap[ci]); } while(0)
+
+// the same, entered by either reason, with the two reasons tested once each
+#define PWN_OOB_RELOOK_ \
+		oobm = (((unsigned)cx >= (unsigned)W) | ((unsigned)cz >= (unsigned)H)) ? (uint32_t)OOB_MARK : 0u; \
+		ci = (((unsigned)cz >= (unsigned)H ? 0 : cz) + 1)*WP + ((unsigned)cx >= (unsigned)W ? 0 : cx) + 1; \
+		cell = __ldg(&L.cellmap[ci]);
+#define PWN_OOB_CHECK(XSTEP) \
+		if(oobm != 0u) { if(!IDS) { if(XSTEP) cx += gx; else cz += gz; } PWN_OOB_RELOOK_ } \
+		else if((cell & 15u) == CL_OOB) { const int row_ = ci / WP; if(!IDS) { cx = ci - row_*WP - 1; cz = row_ - 1; } PWN_OOB_RELOOK_ }
 
 		// ================= trace.h:250-675: the walk =================
 		#pragma unroll K1_WALK_UNROLL
@@ -437,17 +476,20 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 			if(cell & 8u)
 			{
 				// 1-high (trace.h:302-352) and 2-high (trace.h:354-441) rooms share the step
-				const bool two = bit_of(cell, 2u);
 				const bool fogc = bit_of(cell, 1u);
-				const bool up2 = two & up;
+				const bool up2 = bit_of(cell, upmask);   // 2-high and the ray goes up, in one bit test
+				const bool two = IDS ? bit_of(cell, 2u) : false;
 				if(IDS) ops += two ? W_TWO : W_ONE;
 				if(up2) wy = __fadd_rn(wy, iay);   // ceiling one unit further (trace.h:357)
 				const float fogbeg = cdist;        // trace.h:309,359 (read only when fogc)
 
 				// trace_ray_through (trace.h:156-184)
-				const bool yfirst = (wy < wx) & (wy < wz);
+				// the three-way pick as two minima: with no NaN among the distances (iavel is finite, trace.h:220-231)
+				// min(wx, wz) is the x/z pick, "y strictly first" is wy < that, and t is the smaller of the two
 				const bool xfirst = wx < wz;
-				const float t = yfirst ? wy : (xfirst ? wx : wz);
+				const float mxz = fminf(wx, wz);
+				const bool yfirst = wy < mxz;
+				const float t = fminf(wy, mxz);
 				cdist = __fadd_rn(cdist, t);
 				px = __fadd_rn(__fmul_rn(t, rx), px);
 				py = __fadd_rn(__fmul_rn(t, ry), py);
@@ -484,9 +526,9 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 					}
 					else
 					{
-					if(((cell & 15u) == CL_OOB) | (oobm != 0u)) PWN_OOB_FIX(xfirst);
+					PWN_OOB_CHECK(xfirst)
 					const uint32_t ncls = cell & 15u;
-					if(!two)
+					if(!bit_of(faceb, 1u << CM_TWO_SHIFT))
 					{
 						if((faceb & (1u << CM_RZ_SHIFT)) != 0u && (ncls == CL_TWO || ncls == CL_TWO_FOG))   // leaving '"': trace.h:343-351
 						{
@@ -559,7 +601,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 				if(ry >= 0.0f) wy = __fsub_rn(1.0f, wy);
 				wy = __fmul_rn(wy, iay);
 				cell = __ldg(&L.cellmap[ci]);
-				if(((cell & 15u) == CL_OOB) | (oobm != 0u)) PWN_OOB_FIX(xfirst);
+				PWN_OOB_CHECK(xfirst)
 				PWN_SPHERE_EXIT(false, 0.0f)   // trace.h:668-673: the ramp looked before it stepped
 			}
 			else if((cell & 15u) == CL_PORTAL)
@@ -588,8 +630,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 					pz = __fsub_rn(ccz, __fsub_rn(trx, ccx));
 					rx = xmov(rz, P.zero); rz = -trvx;
 					const int tg = gx; gx = gz ^ (int)P.zero; gz = -tg;
-					xswap(wx, wz);
-					xswap(iax, iaz);
+					PWN_XCHG
 				}
 				else if(rot == 2)
 				{
@@ -605,8 +646,7 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 					pz = __fadd_rn(ccz, __fsub_rn(trx, ccx));
 					rx = -rz; rz = xmov(trvx, P.zero);
 					const int tg = gx; gx = -gz; gz = tg ^ (int)P.zero;
-					xswap(wx, wz);
-					xswap(iax, iaz);
+					PWN_XCHG
 				}
 				stepz = gz*WP;
 				ldx = (gx < 0 ? PWN_FXN : PWN_FXP); ldz = (gz < 0 ? PWN_FZN : PWN_FZP);
@@ -637,8 +677,11 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 			// branches: after a room step it repeats the look the step has just taken, with nothing changed)
 		}
 #undef PWN_SPHERE_EXIT
+#undef PWN_SPHERE_MARK
 #undef PWN_WALL_EXIT
 #undef PWN_OOB_FIX
+#undef PWN_OOB_CHECK
+#undef PWN_OOB_RELOOK_
 
 		if(IDS && P.ids != nullptr)
 		{
@@ -770,6 +813,8 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 		fx = npx; fy = npy; fz = npz;
 		irx = nrx; iry = nry; irz = nrz;
 	}
+#undef hkind
+#undef hdist
 
 	// ---- unwind the blends, deepest first (trace.h:91-101) ------------------------------
 	#pragma unroll 1
@@ -802,7 +847,18 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 	}
 
 	// ---- col_ftoint (util.h:48-59): B | G<<8 | R<<16 | A<<24 ------------------------------
-	const uint32_t word = pack_lane(ob) | (pack_lane(og) << 8) | (pack_lane(orr) << 16) | (pack_lane(oa) << 24);
+	// (the one case cvt.rni.sat.u8 and the reference's pack disagree on, s >= 2^31, tested once for the four lanes)
+	uint32_t word;
+	{
+		const float s0 = __fmul_rn(ob, 255.0f), s1 = __fmul_rn(og, 255.0f), s2 = __fmul_rn(orr, 255.0f), s3 = __fmul_rn(oa, 255.0f);
+		uint32_t q0, q1, q2, q3;
+		asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q0) : "f"(s0));
+		asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q1) : "f"(s1));
+		asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q2) : "f"(s2));
+		asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q3) : "f"(s3));
+		word = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+		if(fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)) >= 2147483648.0f) word = pack_huge(s0, s1, s2, s3, word);
+	}
 	P.sbuf[pix] = word;
 	for(int p = 0; p < P.npeers; p++) P.peer[p][pix] = word;
 
