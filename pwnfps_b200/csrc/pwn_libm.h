@@ -230,7 +230,7 @@ PWN_HD float pwn_expf(float x, const uint64_t *tab, int fma_)
 {
 	const uint32_t top = PWN_ABSTOP12(pwn_asuint(x));
 	const double xd = (double)x;
-	if(top >= 0x42b)   /* |x| >= 88 */
+	if(!(fabsf(x) < 88.0f))   /* top >= 0x42b: |x| >= 88 or NaN, as one float compare */
 	{
 		if(pwn_asuint(x) == 0xff800000u) return 0.0f;
 		if(top >= 0x7f8) return x + x;

@@ -329,6 +329,11 @@ static_assert(K1_THREADS*4 == 512, "PWN_XCHG offsets");
 	float fx = P.from[0], fy = P.from[1], fz = P.from[2];
 	float icb = 1.0f, icg = 1.0f, icr = 1.0f, ica = 1.0f;   // icol (screen.h:24)
 
+	// ALPHA0: the alpha lane.  The surface colours have alpha 0 (defs.h:17-19, trace.h:558), so a wall, floor or
+	// ceiling shades to alpha = icol.a*0*diffuse = +0 exactly for every finite ray (icol.a is 1 or an earlier
+	// +0, diffuse is 0.1..1), and blending it in adds k*(+0) to refl*oa >= +0: nothing.  Only sphere colours
+	// carry an alpha of their own, so the builds without spheres leave those operations out; the fog term,
+	// which is what makes the alpha byte of a frame non-zero, stays.
 	// per-level blend state of the two bounce levels (trace.h:89-101)
 	// (colour, refl, fog) of a bounce level wait in shared memory from the bounce to the unwind: twelve
 	// values per pixel that would otherwise sit in registers through the walks of the later segments
@@ -713,13 +718,15 @@ static_assert(K1_THREADS*4 == 512, "PWN_XCHG offsets");
 			// ceilings, floors and walls side by side
 			const float4 sc = c_surface[hsurf];
 			const float sb = sc.x, sg = sc.y, sr = sc.z;
-			cb = __fmul_rn(icb, sb); cg = __fmul_rn(icg, sg); cr = __fmul_rn(icr, sr); ca = __fmul_rn(ica, 0.0f);
+			cb = __fmul_rn(icb, sb); cg = __fmul_rn(icg, sg); cr = __fmul_rn(icr, sr);
+			if(SPH) ca = __fmul_rn(ica, 0.0f);   // (without spheres the alpha lane of a shaded colour is +0 exactly, see ALPHA0)
 			// diffuse = +-ray[axis(ldir)]: FXP FZP FXN FZN FYP FYN = 0..5
 			float diffuse = (ldir >= PWN_FYP) ? ry : ((ldir & 1) ? rz : rx);
 			if(ldir == PWN_FXN || ldir == PWN_FZN || ldir == PWN_FYN) diffuse = -diffuse;
 			if(diffuse < 0.0f) diffuse = 0.0f;
 			diffuse = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, 0.1f), diffuse), 0.1f);
-			cb = __fmul_rn(cb, diffuse); cg = __fmul_rn(cg, diffuse); cr = __fmul_rn(cr, diffuse); ca = __fmul_rn(ca, diffuse);
+			cb = __fmul_rn(cb, diffuse); cg = __fmul_rn(cg, diffuse); cr = __fmul_rn(cr, diffuse);
+			if(SPH) ca = __fmul_rn(ca, diffuse);
 			refl = (ldir == PWN_FYN ? 0.7f : 0.25f);
 		}
 		else
@@ -734,7 +741,7 @@ static_assert(K1_THREADS*4 == 512, "PWN_XCHG offsets");
 		// ================= trace_hit_bounce, trace.h:3-106 =================
 		if(seg >= P.reflect || refl == 0.0f)   // hitctr >= REFLECT (trace.h:6-7; REFLECT == 2 as shipped, defs.h:8)
 		{
-			ob = cb; og = cg; orr = cr; oa = ca;
+			ob = cb; og = cg; orr = cr; oa = SPH ? ca : 0.0f;
 			break;
 		}
 
@@ -806,7 +813,8 @@ static_assert(K1_THREADS*4 == 512, "PWN_XCHG offsets");
 		// (indexed directly: through a pointer variable the compiler addresses shared memory generically
 		// and rebuilds the window base from the cluster CTA id at every bounce)
 		s_blend[seg][0][threadIdx.x] = cb; s_blend[seg][1][threadIdx.x] = cg; s_blend[seg][2][threadIdx.x] = cr;
-		s_blend[seg][3][threadIdx.x] = ca; s_blend[seg][4][threadIdx.x] = refl; s_blend[seg][5][threadIdx.x] = fog;
+		if(SPH) s_blend[seg][3][threadIdx.x] = ca;
+		s_blend[seg][4][threadIdx.x] = refl; s_blend[seg][5][threadIdx.x] = fog;
 		depth = seg + 1;
 
 		// child: trace_ray(hitctr+1, seed, lv, dist, &pos, &ray, col)  (trace.h:90)
@@ -825,7 +833,8 @@ static_assert(K1_THREADS*4 == 512, "PWN_XCHG offsets");
 		ob = __fadd_rn(__fmul_rn(refl, ob), __fmul_rn(k, s_blend[lvl][0][threadIdx.x]));
 		og = __fadd_rn(__fmul_rn(refl, og), __fmul_rn(k, s_blend[lvl][1][threadIdx.x]));
 		orr = __fadd_rn(__fmul_rn(refl, orr), __fmul_rn(k, s_blend[lvl][2][threadIdx.x]));
-		oa = __fadd_rn(__fmul_rn(refl, oa), __fmul_rn(k, s_blend[lvl][3][threadIdx.x]));
+		if(SPH) oa = __fadd_rn(__fmul_rn(refl, oa), __fmul_rn(k, s_blend[lvl][3][threadIdx.x]));
+		else oa = __fmul_rn(refl, oa);   // ALPHA0: + k*(+0) changes nothing, refl*oa is never -0
 		if(fogl != 0.0f)
 		{
 			const float f = libm_expf<LFMA>(__fmul_rn(-0.6f, fogl)), g = __fsub_rn(1.0f, f);
