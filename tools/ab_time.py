@@ -37,6 +37,19 @@ def main():
             b.synchronize()
             best = min(best, a.elapsed_time(b) / len(poses))
         out.append("%-22s %.4f ms/frame  %8.1f Mrays/s  sum %016x" % (name, best, w * h / best / 1e3, int(np.bitwise_xor.reduce(sums))))
+    # K1 and K2 as single launches (what bench.py's roofline times): per-launch events over 150 fly-through poses
+    tr.level_upload(lvd)
+    tr.level_prepare_render(lvd)
+    tr.frame_config(1920, 1080)
+    fl = api.flythrough(lvd, 600)[::4]
+    for rep in range(2):
+        k1 = k2 = 0.0
+        for i in range(len(fl)):
+            tr.trace_cam(fl["cam"][i], 1920, 1080, float(fl["sec_current"][i]), api.PWN_F_BLUR)
+            a, b = tr.last_kernel_ms()
+            k1 += a
+            k2 += b
+    out.append("single launches 1080p  K1 %.4f ms  K2 %.4f ms" % (k1 / len(fl), k2 / len(fl)))
     print(os.environ.get("PWN_LIBPWNTRACE", "in-tree"))
     print("\n".join(out))
 
