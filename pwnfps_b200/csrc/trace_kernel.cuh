@@ -277,16 +277,20 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 {
 	const LevelDev &L = P.lv;
 	__shared__ float s_ray[3][K1_ROWS][32];
-	__shared__ float s_blend[2][6][K1_THREADS];
+	// Per-thread scratch in shared memory, addressed from ONE register that holds this thread's 32-bit
+	// shared address (rows of K1_THREADS floats, the thread's word in each): rows 0-5 and 6-11 are the blend
+	// state of the two bounce levels, rows 12-15 the portal exchange.  The address is made opaque once, or
+	// the compiler rebuilds it from the CTA's shared window at every use (six instructions a time).
+	__shared__ float s_scr[16][K1_THREADS];
+	uint32_t sthr = (uint32_t)__cvta_generic_to_shared(&s_scr[0][threadIdx.x]);
+	asm volatile("" : "+r"(sthr));
+#define PWN_STS(A, OFF, V) asm volatile("st.shared.f32 [%0+" #OFF "], %1;" :: "r"(A), "f"(V) : "memory")
+#define PWN_LDS(V, A, OFF) asm volatile("ld.shared.f32 %0, [%1+" #OFF "];" : "=f"(V) : "r"(A) : "memory")
 	// a quarter-turn portal exchanges the x and z step state through shared memory: a register exchange
 	// makes ptxas keep copies of the exchanged values at the head of EVERY walk iteration
-	__shared__ float s_xchg[4][K1_THREADS];
-#define PWN_XCHG { const uint32_t q_ = (uint32_t)__cvta_generic_to_shared(&s_xchg[0][threadIdx.x]); \
-		asm volatile("st.shared.f32 [%0], %1; st.shared.f32 [%0+512], %2; st.shared.f32 [%0+1024], %3; st.shared.f32 [%0+1536], %4;" \
-			:: "r"(q_), "f"(wx), "f"(wz), "f"(iax), "f"(iaz) : "memory"); \
-		asm volatile("ld.shared.f32 %0, [%4]; ld.shared.f32 %1, [%4+512]; ld.shared.f32 %2, [%4+1024]; ld.shared.f32 %3, [%4+1536];" \
-			: "=f"(wz), "=f"(wx), "=f"(iaz), "=f"(iax) : "r"(q_) : "memory"); }
-static_assert(K1_THREADS*4 == 512, "PWN_XCHG offsets");
+#define PWN_XCHG { PWN_STS(sthr, 6144, wx); PWN_STS(sthr, 6656, wz); PWN_STS(sthr, 7168, iax); PWN_STS(sthr, 7680, iaz); \
+		PWN_LDS(wz, sthr, 6144); PWN_LDS(wx, sthr, 6656); PWN_LDS(iaz, sthr, 7168); PWN_LDS(iax, sthr, 7680); }
+static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 
 	// ---- pixel of this thread: CTA = 32 x K1_ROWS pixels, warp = 8x4 (or 32x1) ----------------------
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -722,7 +726,8 @@ static_assert(K1_THREADS*4 == 512, "PWN_XCHG offsets");
 			if(SPH) ca = __fmul_rn(ica, 0.0f);   // (without spheres the alpha lane of a shaded colour is +0 exactly, see ALPHA0)
 			// diffuse = +-ray[axis(ldir)]: FXP FZP FXN FZN FYP FYN = 0..5
 			float diffuse = (ldir >= PWN_FYP) ? ry : ((ldir & 1) ? rz : rx);
-			if(ldir == PWN_FXN || ldir == PWN_FZN || ldir == PWN_FYN) diffuse = -diffuse;
+			// FXN, FZN, FYN (2, 3, 5) face against their axis: bit ldir of 0b101100, moved up to the sign bit
+			diffuse = __uint_as_float(__float_as_uint(diffuse) ^ ((0x2Cu << (31 - ldir)) & 0x80000000u));
 			if(diffuse < 0.0f) diffuse = 0.0f;
 			diffuse = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, 0.1f), diffuse), 0.1f);
 			cb = __fmul_rn(cb, diffuse); cg = __fmul_rn(cg, diffuse); cr = __fmul_rn(cr, diffuse);
@@ -812,9 +817,12 @@ static_assert(K1_THREADS*4 == 512, "PWN_XCHG offsets");
 
 		// (indexed directly: through a pointer variable the compiler addresses shared memory generically
 		// and rebuilds the window base from the cluster CTA id at every bounce)
-		s_blend[seg][0][threadIdx.x] = cb; s_blend[seg][1][threadIdx.x] = cg; s_blend[seg][2][threadIdx.x] = cr;
-		if(SPH) s_blend[seg][3][threadIdx.x] = ca;
-		s_blend[seg][4][threadIdx.x] = refl; s_blend[seg][5][threadIdx.x] = fog;
+		{
+			const uint32_t sl = sthr + (uint32_t)seg*3072u;
+			PWN_STS(sl, 0, cb); PWN_STS(sl, 512, cg); PWN_STS(sl, 1024, cr);
+			if(SPH) PWN_STS(sl, 1536, ca);
+			PWN_STS(sl, 2048, refl); PWN_STS(sl, 2560, fog);
+		}
 		depth = seg + 1;
 
 		// child: trace_ray(hitctr+1, seed, lv, dist, &pos, &ray, col)  (trace.h:90)
@@ -828,12 +836,16 @@ static_assert(K1_THREADS*4 == 512, "PWN_XCHG offsets");
 	#pragma unroll 1
 	for(int lvl = depth - 1; lvl >= 0; lvl--)
 	{
-		const float refl = s_blend[lvl][4][threadIdx.x], fogl = s_blend[lvl][5][threadIdx.x];
+		const uint32_t sl = sthr + (uint32_t)lvl*3072u;
+		float refl, fogl, lb, lg, lr, la = 0.0f;
+		PWN_LDS(refl, sl, 2048); PWN_LDS(fogl, sl, 2560);
+		PWN_LDS(lb, sl, 0); PWN_LDS(lg, sl, 512); PWN_LDS(lr, sl, 1024);
+		if(SPH) PWN_LDS(la, sl, 1536);
 		const float k = __fsub_rn(1.0f, refl);
-		ob = __fadd_rn(__fmul_rn(refl, ob), __fmul_rn(k, s_blend[lvl][0][threadIdx.x]));
-		og = __fadd_rn(__fmul_rn(refl, og), __fmul_rn(k, s_blend[lvl][1][threadIdx.x]));
-		orr = __fadd_rn(__fmul_rn(refl, orr), __fmul_rn(k, s_blend[lvl][2][threadIdx.x]));
-		if(SPH) oa = __fadd_rn(__fmul_rn(refl, oa), __fmul_rn(k, s_blend[lvl][3][threadIdx.x]));
+		ob = __fadd_rn(__fmul_rn(refl, ob), __fmul_rn(k, lb));
+		og = __fadd_rn(__fmul_rn(refl, og), __fmul_rn(k, lg));
+		orr = __fadd_rn(__fmul_rn(refl, orr), __fmul_rn(k, lr));
+		if(SPH) oa = __fadd_rn(__fmul_rn(refl, oa), __fmul_rn(k, la));
 		else oa = __fmul_rn(refl, oa);   // ALPHA0: + k*(+0) changes nothing, refl*oa is never -0
 		if(fogl != 0.0f)
 		{
