@@ -202,6 +202,15 @@ __global__ void k_pack_eval(const float4 *in, uint32_t *out, int n)
 // through shared memory (PWN_XCHG in k_trace), which removes the copies altogether.
 __device__ __forceinline__ float xmov(float v, uint32_t zero) { return __uint_as_float(__float_as_uint(v) ^ zero); }
 
+// a pointer ptxas cannot trace back to the kernel parameters (both halves xor an opaque zero): it stays in a
+// register pair instead of being re-read from the constant bank at every use
+__device__ __forceinline__ const uint32_t *opaque_ptr(const uint32_t *p, uint32_t zero)
+{
+	const unsigned long long v = (unsigned long long)(uintptr_t)p;
+	const uint32_t lo = (uint32_t)v ^ zero, hi = (uint32_t)(v >> 32) ^ zero;
+	return (const uint32_t *)(uintptr_t)(((unsigned long long)hi << 32) | lo);
+}
+
 // one bit of a map entry as a predicate.  Written in PTX so that the front end cannot rewrite the test
 // into shift-and-compare chains: ptxas turns and + setp into a single LOP3 with a predicate result.
 __device__ __forceinline__ bool bit_of(uint32_t v, uint32_t mask)
@@ -291,6 +300,10 @@ __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTA
 #define PWN_XCHG { PWN_STS(sthr, 6144, wx); PWN_STS(sthr, 6656, wz); PWN_STS(sthr, 7168, iax); PWN_STS(sthr, 7680, iaz); \
 		PWN_LDS(wz, sthr, 6144); PWN_LDS(wx, sthr, 6656); PWN_LDS(iaz, sthr, 7168); PWN_LDS(iax, sthr, 7680); }
 static_assert(K1_THREADS*4 == 512, "scratch row offsets");
+
+	// the cell map's address in a register pair (without spheres there is room for it): read as a kernel
+	// parameter it is re-read from the constant bank at every cell step
+	const uint32_t *cmap = SPH ? L.cellmap : opaque_ptr(L.cellmap, P.zero);
 
 	// ---- pixel of this thread: CTA = 32 x K1_ROWS pixels, warp = 8x4 (or 32x1) ----------------------
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -389,7 +402,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 			ci = (((unsigned)cz >= (unsigned)H ? 0 : cz) + 1)*WP + ((unsigned)cx >= (unsigned)W ? 0 : cx) + 1;
 		}
 		int ldx = (gx < 0 ? PWN_FXN : PWN_FXP), ldz = (gz < 0 ? PWN_FZN : PWN_FZP);
-		uint32_t cell = __ldg(&L.cellmap[ci]);
+		uint32_t cell = __ldg(&cmap[ci]);
 		int ldir = PWN_FYN;
 		float cdist = 0.0f, fog = 0.0f;
 		int nstep = 0, nport = 0;
@@ -419,13 +432,13 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 		else if(!IDS) { if(XSTEP) cx += gx; else cz += gz; } \
 		oobm = (((unsigned)cx >= (unsigned)W) | ((unsigned)cz >= (unsigned)H)) ? (uint32_t)OOB_MARK : 0u; \
 		ci = (((unsigned)cz >= (unsigned)H ? 0 : cz) + 1)*WP + ((unsigned)cx >= (unsigned)W ? 0 : cx) + 1; \
-		cell = __ldg(&L.cellmap[ci]); } while(0)
+		cell = __ldg(&cmap[ci]); } while(0)
 
 // the same, entered by either reason, with the two reasons tested once each
 #define PWN_OOB_RELOOK_ \
 		oobm = (((unsigned)cx >= (unsigned)W) | ((unsigned)cz >= (unsigned)H)) ? (uint32_t)OOB_MARK : 0u; \
 		ci = (((unsigned)cz >= (unsigned)H ? 0 : cz) + 1)*WP + ((unsigned)cx >= (unsigned)W ? 0 : cx) + 1; \
-		cell = __ldg(&L.cellmap[ci]);
+		cell = __ldg(&cmap[ci]);
 #define PWN_OOB_CHECK(XSTEP) \
 		if(oobm != 0u) { if(!IDS) { if(XSTEP) cx += gx; else cz += gz; } PWN_OOB_RELOOK_ } \
 		else if((cell & 15u) == CL_OOB) { const int row_ = ci / WP; if(!IDS) { cx = ci - row_*WP - 1; cz = row_ - 1; } PWN_OOB_RELOOK_ }
@@ -523,7 +536,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 				}
 				if(up2) wy = __fsub_rn(wy, iay);   // trace.h:392
 				const uint32_t faceb = cell >> ldir;   // the bits of the face just crossed, in the positions of face 0
-				cell = __ldg(&L.cellmap[ci]);
+				cell = __ldg(&cmap[ci]);
 
 				// slow transitions only (the cell's slow bit for the face just crossed, or a ray
 				// outside the grid): leaving the grid, raised floors, 2-high room into anything else
@@ -609,7 +622,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 				wy = py;
 				if(ry >= 0.0f) wy = __fsub_rn(1.0f, wy);
 				wy = __fmul_rn(wy, iay);
-				cell = __ldg(&L.cellmap[ci]);
+				cell = __ldg(&cmap[ci]);
 				PWN_OOB_CHECK(xfirst)
 				PWN_SPHERE_EXIT(false, 0.0f)   // trace.h:668-673: the ramp looked before it stepped
 			}
@@ -671,7 +684,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 					pz = onz ? __fadd_rn(pz, one) : pz;
 					if(IDS) { if(onz) cz += sgn; else cx += sgn; }
 				}
-				cell = __ldg(&L.cellmap[ci]);
+				cell = __ldg(&cmap[ci]);
 				if((cell & 15u) == CL_OOB) PWN_OOB_FIX(false);   // a portal on the rim: never outside before the step
 				PWN_SPHERE_EXIT(false, 0.0f)   // trace.h:668-673
 			}
