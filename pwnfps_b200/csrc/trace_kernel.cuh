@@ -401,7 +401,10 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 			oobm = OOB_MARK;
 			ci = (((unsigned)cz >= (unsigned)H ? 0 : cz) + 1)*WP + ((unsigned)cx >= (unsigned)W ? 0 : cx) + 1;
 		}
-		int ldx = (gx < 0 ? PWN_FXN : PWN_FXP), ldz = (gz < 0 ? PWN_FZN : PWN_FZP);
+		// the faces the ray crosses: FXP/FXN = 0/2 and FZP/FZN = 1/3 for a sign of +1/-1, as arithmetic (the FMA
+		// pipe has room, the ALU pipe that would do the selects has not)
+		static_assert(PWN_FXP == 0 && PWN_FZP == 1 && PWN_FXN == 2 && PWN_FZN == 3, "face codes");
+		int ldx = 1 - gx, ldz = 2 - gz;
 		uint32_t cell = __ldg(&cmap[ci]);
 		int ldir = PWN_FYN;
 		float cdist = 0.0f, fog = 0.0f;
@@ -671,7 +674,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 					PWN_XCHG
 				}
 				stepz = gz*WP;
-				ldx = (gx < 0 ? PWN_FXN : PWN_FXP); ldz = (gz < 0 ? PWN_FZN : PWN_FZP);
+				ldx = 1 - gx; ldz = 2 - gz;
 				// step out of the destination portal cell (trace.h:624-647)
 				{
 					// FXP FZP FXN FZN = 0 1 2 3: bit 0 = along z, bit 1 = backwards (a - 1.0f and a + (-1.0f) are
