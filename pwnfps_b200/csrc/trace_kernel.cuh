@@ -166,18 +166,11 @@ __device__ __forceinline__ float randfs(uint32_t &seed)
 	return __fsub_rn(__fmul_rn((float)r, __uint_as_float(0x3A0B79B3u)), 1.0f);
 }
 
-// cvtps2dq + packssdw + packuswb on one lane (util.h:48-59).  cvtps2dq rounds to nearest even and gives
-// 0x80000000 for NaN and for |s| >= 2^31, which the two saturating packs turn into 0; everything else
-// saturates to 0..255.  cvt.rni.sat.u8 does the same in one F2IP except for s >= 2^31 (255 instead of 0).
-__device__ __forceinline__ uint32_t pack_lane(float v)
-{
-	const float s = __fmul_rn(v, 255.0f);
-	uint32_t q;
-	asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q) : "f"(s));
-	return (s >= 2147483648.0f) ? 0u : q;
-}
-
-// the lanes of a packed pixel whose scaled value is 2^31 or more become 0 (cvtps2dq's "indefinite" through the two packs)
+// col_ftoint (util.h:48-59): cvtps2dq + packssdw + packuswb, B | G<<8 | R<<16 | A<<24.  cvtps2dq rounds to
+// nearest even and gives 0x80000000 for NaN and for |s| >= 2^31, which the two saturating packs turn into 0;
+// everything else saturates to 0..255.  cvt.rni.sat.u8 does the same in one F2IP except for s >= 2^31 (255
+// instead of 0): that one case is tested once for the four lanes and fixed behind a real call, which ptxas
+// does not flatten into predicated instructions on every pixel's path.
 __device__ __noinline__ uint32_t pack_huge(float s0, float s1, float s2, float s3, uint32_t word)
 {
 	if(s0 >= 2147483648.0f) word &= 0xFFFFFF00u;
@@ -187,13 +180,26 @@ __device__ __noinline__ uint32_t pack_huge(float s0, float s1, float s2, float s
 	return word;
 }
 
-// col_ftoint (util.h:48-59) alone, for known-answer tests of the pack (pwn_debug_pack)
+__device__ __forceinline__ uint32_t pack_word(float b, float g, float r, float a)
+{
+	const float s0 = __fmul_rn(b, 255.0f), s1 = __fmul_rn(g, 255.0f), s2 = __fmul_rn(r, 255.0f), s3 = __fmul_rn(a, 255.0f);
+	uint32_t q0, q1, q2, q3;
+	asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q0) : "f"(s0));
+	asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q1) : "f"(s1));
+	asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q2) : "f"(s2));
+	asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q3) : "f"(s3));
+	uint32_t word = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+	if(fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)) >= 2147483648.0f) word = pack_huge(s0, s1, s2, s3, word);   // (fmaxf skips NaN lanes)
+	return word;
+}
+
+// col_ftoint alone, for known-answer tests of the pack (pwn_debug_pack): the code K1 ends with
 __global__ void k_pack_eval(const float4 *in, uint32_t *out, int n)
 {
 	const int i = blockIdx.x*blockDim.x + threadIdx.x;
 	if(i >= n) return;
 	const float4 v = in[i];
-	out[i] = pack_lane(v.x) | (pack_lane(v.y) << 8) | (pack_lane(v.z) << 16) | (pack_lane(v.w) << 24);
+	out[i] = pack_word(v.x, v.y, v.z, v.w);
 }
 
 // The portal rotation exchanges x and z quantities.  Written as plain copies the exchange becomes a
@@ -884,18 +890,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 	}
 
 	// ---- col_ftoint (util.h:48-59): B | G<<8 | R<<16 | A<<24 ------------------------------
-	// (the one case cvt.rni.sat.u8 and the reference's pack disagree on, s >= 2^31, tested once for the four lanes)
-	uint32_t word;
-	{
-		const float s0 = __fmul_rn(ob, 255.0f), s1 = __fmul_rn(og, 255.0f), s2 = __fmul_rn(orr, 255.0f), s3 = __fmul_rn(oa, 255.0f);
-		uint32_t q0, q1, q2, q3;
-		asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q0) : "f"(s0));
-		asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q1) : "f"(s1));
-		asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q2) : "f"(s2));
-		asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q3) : "f"(s3));
-		word = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
-		if(fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)) >= 2147483648.0f) word = pack_huge(s0, s1, s2, s3, word);
-	}
+	const uint32_t word = pack_word(ob, og, orr, oa);
 	P.sbuf[pix] = word;
 	for(int p = 0; p < P.npeers; p++) P.peer[p][pix] = word;
 
