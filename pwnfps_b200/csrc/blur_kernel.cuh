@@ -67,7 +67,9 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 	// the row's stream (seed = cy*cy + 415135, screen.h:82) advanced to draw 32*g + 2*j
 	const uint2 jg = __ldg(&P.jump[g]);
 	uint32_t seed = jg.x*((uint32_t)y*(uint32_t)y + 415135u) + jg.y;
-	seed = (c_jumpA[j]*seed + c_jumpC[j]) & 0x7FFFFFFFu;
+	// (the jumps are left unmasked: bit 31 of a seed reaches only bit 31 of the next product, and every draw
+	// masks before it takes the remainder)
+	seed = c_jumpA[j]*seed + c_jumpC[j];
 
 	const float z = __fsub_rn(P.zbuf[pix], 1.0f);
 	const float fbx = (float)x, fby = (float)y;
@@ -80,7 +82,7 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 		const int sx = cvtt_clamp(__fadd_rn(fbx, __fmul_rn(__fmul_rn(blur_randfs(seed), P.fstr), z)), P.dimx - 1);
 		const int sy = cvtt_clamp(__fadd_rn(fby, __fmul_rn(__fmul_rn(blur_randfs(seed), P.fstr), z)), P.dimy - 1);
 		s[i] = __ldg(&P.src[(size_t)sy*P.rwidth + sx]);
-		seed = (a6*seed + c6) & 0x7FFFFFFFu;
+		seed = a6*seed + c6;
 	}
 	// pavgb: per byte (a+b+1)>>1 (screen.h:112-115)
 	P.dst[pix] = pavgb4(pavgb4(s[0], s[1]), pavgb4(s[2], s[3]));
