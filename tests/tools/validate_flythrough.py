@@ -2,7 +2,8 @@
 """tests/tools/validate_flythrough.py -- one-off full-size parity run of BASELINE configs[1]:
 all 600 poses of the scripted fly-through at 1920x1080, blur on, device (pose pipeline, as the
 bench runs it) against the CPU oracle, frame by frame, by checksum; plus the 16 seeded poses of
-the 10k-sector maze at 3840x2160 (configs[3]).  Prints one summary line per config."""
+the 10k-sector maze at 3840x2160 (configs[3]), 8 poses of its 64-pose batch at 7680x4320 (configs[4]) and the
+mirror hall (configs[2]).  Prints one summary line per config."""
 import os
 import sys
 import time
@@ -90,6 +91,8 @@ def main():
     nbad = run("configs[1] default level fly-through", lv, api.flythrough(lv, 600), 1920, 1080, tr, o)
     mz = levels.maze(dim=128, seed=1)
     nbad += run("configs[3] 10k-sector maze", mz, levels.poses_random(mz, 16, seed=1), 3840, 2160, tr, o)
+    # configs[4]: the same maze at 7680x4320, every 8th pose of the 64-pose batch the multi-GPU bench shards (seed 9)
+    nbad += run("configs[4] 10k-sector maze 8K", mz, levels.poses_random(mz, 64, seed=9)[::8], 7680, 4320, tr, o)
     hall = levels.mirror_hall()
     cam0 = api.cam_spawn(hall)
     px = np.zeros(8, api.POSE_DTYPE)
