@@ -378,35 +378,45 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 		}
 		int cx = __float2int_rz(fx), cz = __float2int_rz(fz);   // real cell coordinates (IDS builds keep them current)
 		const float EPS = 0.0000000000001f;
-		if(fminf(fminf(fabsf(rx), fabsf(ry)), fabsf(rz)) < EPS)   // trace.h:220-222, almost never taken: a real call keeps
-		{                                                         // the clamp out of the instruction stream of every segment
-			const float3 c3 = eps_clamp(rx, ry, rz);
-			rx = c3.x; ry = c3.y; rz = c3.z;
-		}
-		int gx = (irx < 0.0f ? -1 : 1), gz = (irz < 0.0f ? -1 : 1);
-		const bool up = !(iry < 0.0f);                          // gy > 0
+		// The reference tests the signs twice: gx/gy/gz from the un-normalised ray (trace.h:225-227) and "ray >= 0"
+		// on the normalised, clamped one (trace.h:233-238).  A component the clamp leaves alone is non-zero and has
+		// the sign of its un-normalised value (the scale is positive), so the second test is the negation of the
+		// first; only behind the clamp can the two disagree (a negative component that underflowed to -0 becomes
+		// +EPSILON), and there the second test is made for real.  Everything that reads the signs sits in front of
+		// the clamp's call, so each is tested once and no predicate has to live across the call.
+		const bool xneg = irx < 0.0f, yneg = iry < 0.0f, zneg = irz < 0.0f;
+		int gx = (xneg ? -1 : 1), gz = (zneg ? -1 : 1);
+		const bool up = !yneg;                                  // gy > 0
 		uint32_t upmask = up ? 2u : 0u;
 		asm volatile("" : "+r"(upmask));   // a value of its own: ptxas would otherwise rebuild it from the ray at every step
-		float iax = rcp_emul(L, rx), iaz = rcp_emul(L, rz);   // iavel = rcpps(abs(ray)), trace.h:229-231
-		const float iay = rcp_emul(L, ry);
-		float px = fx, py = fy, pz = fz;
-		float wx = __fsub_rn(px, (float)cx), wy = py, wz = __fsub_rn(pz, (float)cz);
-		if(rx >= 0.0f) wx = __fsub_rn(1.0f, wx);
-		if(ry >= 0.0f) wy = __fsub_rn(1.0f, wy);
-		if(rz >= 0.0f) wz = __fsub_rn(1.0f, wz);
-		wx = __fmul_rn(wx, iax); wy = __fmul_rn(wy, iay); wz = __fmul_rn(wz, iaz);
-
+		const float w0x = __fsub_rn(fx, (float)cx), w0z = __fsub_rn(fz, (float)cz);
+		float wx = xneg ? w0x : __fsub_rn(1.0f, w0x), wy = yneg ? fy : __fsub_rn(1.0f, fy), wz = zneg ? w0z : __fsub_rn(1.0f, w0z);
 		// linear index into the padded map.  While a coordinate is outside the grid the lookup
 		// folds to index 0 on that axis (util.h:151-158): such rays (oobm != 0) take the slow path
 		// of every step, which tracks the real (cx, cz) and recomputes the index from them
-		int stepz = gz*WP;   // index step of a z move; an x move steps by gx
 		uint32_t oobm = 0u;
 		int ci = (cz + 1)*WP + cx + 1;
-		if(((unsigned)cx >= (unsigned)W) | ((unsigned)cz >= (unsigned)H))
-		{
-			oobm = OOB_MARK;
-			ci = (((unsigned)cz >= (unsigned)H ? 0 : cz) + 1)*WP + ((unsigned)cx >= (unsigned)W ? 0 : cx) + 1;
+		const bool outside = ((unsigned)cx >= (unsigned)W) | ((unsigned)cz >= (unsigned)H);
+		// the two rare cases of the setup share ONE branch (the clamp is the identity on a ray that does not need it)
+		if((fminf(fminf(fabsf(rx), fabsf(ry)), fabsf(rz)) < EPS) | outside)   // trace.h:220-222, almost never taken: a real
+		{                                                         // call keeps the clamp out of the instruction stream of every segment
+			const float3 c3 = eps_clamp(rx, ry, rz);
+			rx = c3.x; ry = c3.y; rz = c3.z;
+			wx = (rx >= 0.0f) ? __fsub_rn(1.0f, w0x) : w0x;
+			wy = (ry >= 0.0f) ? __fsub_rn(1.0f, fy) : fy;
+			wz = (rz >= 0.0f) ? __fsub_rn(1.0f, w0z) : w0z;
+			if(outside)
+			{
+				oobm = OOB_MARK;
+				ci = (((unsigned)cz >= (unsigned)H ? 0 : cz) + 1)*WP + ((unsigned)cx >= (unsigned)W ? 0 : cx) + 1;
+			}
 		}
+		float iax = rcp_emul(L, rx), iaz = rcp_emul(L, rz);   // iavel = rcpps(abs(ray)), trace.h:229-231
+		const float iay = rcp_emul(L, ry);
+		float px = fx, py = fy, pz = fz;
+		wx = __fmul_rn(wx, iax); wy = __fmul_rn(wy, iay); wz = __fmul_rn(wz, iaz);
+
+		int stepz = gz*WP;   // index step of a z move; an x move steps by gx
 		// the faces the ray crosses: FXP/FXN = 0/2 and FZP/FZN = 1/3 for a sign of +1/-1, as arithmetic (the FMA
 		// pipe has room, the ALU pipe that would do the selects has not)
 		static_assert(PWN_FXP == 0 && PWN_FZP == 1 && PWN_FXN == 2 && PWN_FZN == 3, "face codes");
