@@ -361,6 +361,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 	// (colour, refl, fog) of a bounce level wait in shared memory from the bounce to the unwind: twelve
 	// values per pixel that would otherwise sit in registers through the walks of the later segments
 	float ob, og, orr, oa;   // colour coming back from the deepest segment
+	bool exhausted = false;
 	int depth = 0;           // bounce levels to unwind
 
 	const int W = L.w, H = L.h, WP = L.wp;
@@ -738,7 +739,10 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 
 		if(hkind == 2)
 		{
-			ob = rx; og = ry; orr = rz; oa = 0.0f;   // the ray comes back as the colour
+			// the ray comes back as the colour (trace.h:677-678).  It goes through the scratch words: written as
+			// register copies, ptxas hoists the copies above this branch, into every segment's path
+			PWN_STS(sthr, 6144, rx); PWN_STS(sthr, 6656, ry); PWN_STS(sthr, 7168, rz);
+			exhausted = true;
 			break;
 		}
 
@@ -778,7 +782,6 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 		// ================= trace_hit_bounce, trace.h:3-106 =================
 		if(seg >= P.reflect || refl == 0.0f)   // hitctr >= REFLECT (trace.h:6-7; REFLECT == 2 as shipped, defs.h:8)
 		{
-			ob = cb; og = cg; orr = cr; oa = SPH ? ca : 0.0f;
 			break;
 		}
 
@@ -864,6 +867,10 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 #undef hkind
 #undef hdist
 
+	// the colour the deepest segment returns: its shaded hit (built in place in icol), or its ray if the walk
+	// ran out of steps (trace.h:677-678)
+	if(exhausted) { PWN_LDS(ob, sthr, 6144); PWN_LDS(og, sthr, 6656); PWN_LDS(orr, sthr, 7168); oa = 0.0f; }
+	else { ob = icb; og = icg; orr = icr; oa = SPH ? ica : 0.0f; }
 	// ---- unwind the blends, deepest first (trace.h:91-101) ------------------------------
 	#pragma unroll 1
 	for(int lvl = depth - 1; lvl >= 0; lvl--)
