@@ -56,7 +56,7 @@ __device__ __forceinline__ uint32_t pavgb4(uint32_t a, uint32_t b)
 // one output pixel of the blur pass (screen.h:91-117)
 __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 {
-	const size_t pix = (size_t)y*P.rwidth + x;
+	const uint32_t pix = (uint32_t)y*(uint32_t)P.rwidth + (uint32_t)x;   // (a frame has fewer than 2^31 pixels: pwn_frame_config)
 	const int g = x >> 2, j = x & 3;
 	if((x & ~3) >= P.dimx - 3)
 	{
@@ -81,7 +81,7 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 	{
 		const int sx = cvtt_clamp(__fadd_rn(fbx, __fmul_rn(__fmul_rn(blur_randfs(seed), P.fstr), z)), P.dimx - 1);
 		const int sy = cvtt_clamp(__fadd_rn(fby, __fmul_rn(__fmul_rn(blur_randfs(seed), P.fstr), z)), P.dimy - 1);
-		s[i] = __ldg(&P.src[(size_t)sy*P.rwidth + sx]);
+		s[i] = __ldg(&P.src[(uint32_t)sy*(uint32_t)P.rwidth + (uint32_t)sx]);
 		seed = a6*seed + c6;
 	}
 	// pavgb: per byte (a+b+1)>>1 (screen.h:112-115)

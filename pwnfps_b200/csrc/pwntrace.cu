@@ -501,6 +501,9 @@ extern "C" int pwn_frame_config(pwn_ctx *ctx, int rwidth, int rheight, int want_
 {
 	CTX_ENTER(ctx);
 	if(rwidth <= 0 || rheight <= 0) return fail(PWN_E_ARG, "pwn_frame_config: %dx%d", rwidth, rheight);
+	// (K1 indexes the frame with 32 bits; three planes of 2^31 pixels would not fit a B200 anyway)
+	if((unsigned long long)rwidth*(unsigned long long)rheight >= (1ull << 31))
+		return fail(PWN_E_LIMIT, "pwn_frame_config: %dx%d has 2^31 pixels or more", rwidth, rheight);
 	CU(cudaStreamSynchronize(ctx->stream));
 	CU(cudaStreamSynchronize(ctx->copy_stream));
 	if(rwidth != ctx->rwidth || rheight != ctx->rheight)

@@ -340,7 +340,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 	}
 	__syncthreads();
 	if(x >= P.dimx || y >= P.dimy) return;
-	const size_t pix = (size_t)y*P.rwidth + x;
+	const uint32_t pix = (uint32_t)y*(uint32_t)P.rwidth + (uint32_t)x;   // (pwn_frame_config keeps rwidth*rheight below 2^31)
 	float irx = s_ray[0][ty][tx], iry = s_ray[1][ty][tx], irz = s_ray[2][ty][tx];
 
 	// screen.h:19-21 (uint32 wrap)
@@ -730,7 +730,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 			pwn_ids rec;
 			rec.cell = cz*W + cx; rec.ldir = (int16_t)ldir; rec.kind = (int16_t)hkind;
 			rec.nstep = nstep; rec.nportal = nport;
-			P.ids[pix*3 + seg] = rec;
+			P.ids[(size_t)pix*3 + seg] = rec;
 		}
 
 		// zbuf keeps the PRIMARY distance: bounces save/zero/restore *dist (trace.h:86-87,103);
@@ -872,8 +872,9 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 	if(exhausted) { PWN_LDS(ob, sthr, 6144); PWN_LDS(og, sthr, 6656); PWN_LDS(orr, sthr, 7168); oa = 0.0f; }
 	else { ob = icb; og = icg; orr = icr; oa = SPH ? ica : 0.0f; }
 	// ---- unwind the blends, deepest first (trace.h:91-101) ------------------------------
-	#pragma unroll 1
-	for(int lvl = depth - 1; lvl >= 0; lvl--)
+	#pragma unroll
+	for(int lvl = 1; lvl >= 0; lvl--)
+	if(lvl < depth)
 	{
 		const uint32_t sl = sthr + (uint32_t)lvl*3072u;
 		float refl, fogl, lb, lg, lr, la = 0.0f;
