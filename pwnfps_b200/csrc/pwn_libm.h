@@ -63,54 +63,6 @@ PWN_HD double pwn_asdouble(uint64_t u) { double f; memcpy(&f, &u, 8); return f; 
 #define PWN_SC_S3 -0x1.994eb3774cf24p-13
 #define PWN_SC_PI63 0x1.921FB54442D18p-62
 
-/* expf (e_expf.c): __exp2f_data with N = 32 */
-#define PWN_EXP_SHIFT 0x1.8p+52
-#define PWN_EXP_INVLN2N 0x1.71547652b82fep+5      /* 32/ln2 */
-#define PWN_EXP_C0 0x1.c6af84b912394p-20           /* poly_scaled */
-#define PWN_EXP_C1 0x1.ebfce50fac4f3p-13
-#define PWN_EXP_C2 0x1.62e42ff0c52d6p-6
-
-/*
- * On the device the double constants are read from the constant bank: as literals each costs two
- * register moves in front of the DFMA that uses it (FP64 instructions take no 64-bit immediate),
- * from the bank it is an operand of the DFMA itself or one 64-bit load.
- */
-#if defined(__CUDACC__) && defined(PWN_LIBM_CONST_BANK)
-__constant__ double pwn_kd[15] = { PWN_SC_HPI_INV, PWN_SC_HPI, PWN_SC_C1, PWN_SC_C2, PWN_SC_C3, PWN_SC_C4, PWN_SC_S1, PWN_SC_S2, PWN_SC_S3, PWN_SC_PI63, PWN_EXP_SHIFT, PWN_EXP_INVLN2N, PWN_EXP_C0, PWN_EXP_C1, PWN_EXP_C2 };
-#if defined(__CUDA_ARCH__)
-#undef PWN_SC_HPI_INV
-#undef PWN_SC_HPI
-#undef PWN_SC_C1
-#undef PWN_SC_C2
-#undef PWN_SC_C3
-#undef PWN_SC_C4
-#undef PWN_SC_S1
-#undef PWN_SC_S2
-#undef PWN_SC_S3
-#undef PWN_SC_PI63
-#undef PWN_EXP_SHIFT
-#undef PWN_EXP_INVLN2N
-#undef PWN_EXP_C0
-#undef PWN_EXP_C1
-#undef PWN_EXP_C2
-#define PWN_SC_HPI_INV pwn_kd[0]
-#define PWN_SC_HPI pwn_kd[1]
-#define PWN_SC_C1 pwn_kd[2]
-#define PWN_SC_C2 pwn_kd[3]
-#define PWN_SC_C3 pwn_kd[4]
-#define PWN_SC_C4 pwn_kd[5]
-#define PWN_SC_S1 pwn_kd[6]
-#define PWN_SC_S2 pwn_kd[7]
-#define PWN_SC_S3 pwn_kd[8]
-#define PWN_SC_PI63 pwn_kd[9]
-#define PWN_EXP_SHIFT pwn_kd[10]
-#define PWN_EXP_INVLN2N pwn_kd[11]
-#define PWN_EXP_C0 pwn_kd[12]
-#define PWN_EXP_C1 pwn_kd[13]
-#define PWN_EXP_C2 pwn_kd[14]
-#endif
-#endif
-
 /* sinf_poly, sine branch (s_sincosf.h): s + x7*s1 */
 PWN_HD double pwn_sin_poly(double x, double x2, int fma_)
 {
@@ -264,7 +216,11 @@ PWN_HD float pwn_cosf(float y, int fma_)
 	0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull, \
 	0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull }
 
-/* (PWN_EXP_SHIFT, PWN_EXP_INVLN2N, PWN_EXP_C0..C2: with the other constants at the top of the file) */
+#define PWN_EXP_SHIFT 0x1.8p+52
+#define PWN_EXP_INVLN2N 0x1.71547652b82fep+5      /* 32/ln2 */
+#define PWN_EXP_C0 0x1.c6af84b912394p-20           /* poly_scaled */
+#define PWN_EXP_C1 0x1.ebfce50fac4f3p-13
+#define PWN_EXP_C2 0x1.62e42ff0c52d6p-6
 
 /*
  * expf (e_expf.c, !TOINT_INTRINSICS).  `tab` is PWN_EXP2F_TAB wherever the caller keeps it.
