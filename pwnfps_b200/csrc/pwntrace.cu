@@ -69,6 +69,8 @@ struct pwn_ctx
 
 	// level
 	uint32_t *d_cellmap = nullptr;
+	std::vector<uint32_t> h_cellmap;   // host copy: pwn_parts_upload stages a copy with the "cell holds spheres" bits
+	uint32_t *d_cellmap_sph = nullptr; // that copy on the device (inside d_parts_blob); what the sphere builds of K1 walk
 	PortalRec *d_portals = nullptr;
 	int w = 0, h = 0;
 	bool have_level = false;
@@ -359,7 +361,7 @@ extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells
 			r.flags = rot | (kind << 8) | ((uint32_t)peek_of(xcell) << 16);
 			r.ccx = (float)dcx + 0.5f; r.ccz = (float)dcz + 0.5f;   // (cx + 0.5f), trace.h:584
 			r.dcx = dcx; r.dcz = dcz;
-			if(recs.size() >= (1u << 16)) return fail(PWN_E_LIMIT, "more than 65536 portal cells");
+			if(recs.size() >= (1u << 15)) return fail(PWN_E_LIMIT, "more than 32768 portal cells");   // bit 31 of an entry is CM_SPH_BIT
 			entry |= (uint32_t)recs.size() << CM_REC_SHIFT;
 			recs.push_back(r);
 		}
@@ -400,6 +402,8 @@ extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells
 	CU(cudaMemcpy(ctx->d_cellmap, map.data(), map.size()*sizeof(uint32_t), cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(ctx->d_portals, recs.data(), recs.size()*sizeof(PortalRec), cudaMemcpyHostToDevice));
 	ctx->w = w; ctx->h = h;
+	ctx->h_cellmap = map;
+	ctx->d_cellmap_sph = nullptr;
 	ctx->have_level = true;
 	ctx->nsph = 0;   // the per-cell sphere lists belong to the previous grid: pwn_parts_upload rebuilds them
 	return PWN_OK;
@@ -454,7 +458,9 @@ extern "C" int pwn_parts_upload(pwn_ctx *ctx, int nsph, const pwn_sphere *sph)
 			const size_t b_pos = 0, b_col = b_pos + align16((size_t)nsph*sizeof(float4)), b_rr = b_col + align16((size_t)nsph*sizeof(float4));
 			const size_t b_off = b_rr + align16((size_t)nsph*sizeof(float2)), b_idx = b_off + align16((ncell + 1)*sizeof(uint32_t));
 			const size_t b_pk = b_idx + align16(idx.size()*sizeof(uint32_t));
-			const size_t total = b_pk + align16(ncell*sizeof(uint32_t));
+			const size_t b_map = b_pk + align16(ncell*sizeof(uint32_t));
+			const size_t total = b_map + align16(ncell*sizeof(uint32_t));
+			if(ctx->h_cellmap.size() != ncell) return fail(PWN_E_STATE, "pwn_parts_upload: no host copy of the cell map");
 			if(idx.size() >= (1u << 24)) return fail(PWN_E_LIMIT, "more than 2^24 sphere list entries");
 			if(ctx->ev_parts == nullptr) CU(cudaEventCreateWithFlags(&ctx->ev_parts, cudaEventDisableTiming));
 			else CU(cudaEventSynchronize(ctx->ev_parts));      // the previous upload has left the staging block
@@ -478,17 +484,21 @@ extern "C" int pwn_parts_upload(pwn_ctx *ctx, int nsph, const pwn_sphere *sph)
 			}
 			memcpy(hs + b_off, off.data(), (ncell + 1)*sizeof(uint32_t));
 			memcpy(hs + b_idx, idx.data(), idx.size()*sizeof(uint32_t));
-			uint32_t *pk = (uint32_t *)(hs + b_pk);
+			// per cell: the packed list handle, and the map entry again with CM_SPH_BIT where the list is not empty --
+			// the walk then learns from the entry it has loaded anyway whether the cell's list is worth a look
+			uint32_t *pk = (uint32_t *)(hs + b_pk), *mp = (uint32_t *)(hs + b_map);
 			for(size_t c = 0; c < ncell; c++)
 			{
 				const uint32_t cnt = off[c + 1] - off[c];
 				pk[c] = off[c] | ((cnt < 255u ? cnt : 255u) << 24);
+				mp[c] = ctx->h_cellmap[c] | (cnt ? (uint32_t)CM_SPH_BIT : 0u);
 			}
 			CU(cudaMemcpyAsync(ds, hs, total, cudaMemcpyHostToDevice, ctx->stream));
 			CU(cudaEventRecord(ctx->ev_parts, ctx->stream));
 			ctx->d_sph_pos = (float4 *)(ds + b_pos); ctx->d_sph_col = (float4 *)(ds + b_col); ctx->d_sph_rr = (float2 *)(ds + b_rr);
 			ctx->d_parts_off = (uint32_t *)(ds + b_off); ctx->d_parts_idx = (uint32_t *)(ds + b_idx);
 			ctx->d_parts_pk = (uint32_t *)(ds + b_pk);
+			ctx->d_cellmap_sph = (uint32_t *)(ds + b_map);
 		}
 	}
 	ctx->nsph = nsph;
@@ -624,7 +634,7 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 
 	TraceParams P;
 	memset(&P, 0, sizeof(P));
-	P.lv.cellmap = ctx->d_cellmap; P.lv.portals = ctx->d_portals; P.lv.w = ctx->w; P.lv.h = ctx->h; P.lv.wp = ctx->w + 2;
+	P.lv.cellmap = (ctx->nsph > 0 && ctx->d_cellmap_sph) ? ctx->d_cellmap_sph : ctx->d_cellmap; P.lv.portals = ctx->d_portals; P.lv.w = ctx->w; P.lv.h = ctx->h; P.lv.wp = ctx->w + 2;
 	P.lv.rcp_tab = ctx->d_rcp; P.lv.rsqrt_tab = ctx->d_rsqrt;
 	P.lv.rcp_shift = 23 - ctx->rcp_bits; P.lv.rsqrt_shift = 23 - ctx->rsqrt_bits;
 	P.lv.rsqrt_mask = (2u << ctx->rsqrt_bits) - 1u;

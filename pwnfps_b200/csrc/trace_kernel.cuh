@@ -56,6 +56,8 @@ enum : uint32_t
 	// answers everything the slow path asks about the cell being left.
 	CM_SLOW_SHIFT = 4, CM_HWIN_SHIFT = 8, CM_RZ_SHIFT = 12, CM_REC_SHIFT = 16,
 	CM_TWO_SHIFT = 16,   // rooms have no portal record: on a 2-high room bits 16-19 repeat "2-high" once per face
+	CM_REC_MASK = 0x7FFFu,   // a portal record index has 15 bits: bit 31 of every entry is
+	CM_SPH_BIT = 1u << 31,   // "the cell's sphere list is not empty", set per frame in the copy of the map the sphere builds walk
 	// the value of `oobm` while the ray is outside the grid: it forces the slow bit on and masks the
 	// height-window bit off, each with the same single LOP3 that tests the bit
 	OOB_MARK = (1u << CM_SLOW_SHIFT) | (1u << CM_HWIN_SHIFT)
@@ -471,9 +473,9 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 
 			if(SPH)   // trace.h:252-296
 			{
-				const uint32_t pk = __ldg(&L.parts_pk[ci]);
-				if((pk >> 24) != 0u && !oobm)   // (outside the grid the reference looks at no list, trace.h:252)
+				if((int32_t)cell < 0 && !oobm)   // CM_SPH_BIT (outside the grid the reference looks at no list, trace.h:252)
 				{
+					const uint32_t pk = __ldg(&L.parts_pk[ci]);
 					uint32_t i = pk & 0xFFFFFFu, e = i + (pk >> 24);
 					if((pk >> 24) == 255u) e = __ldg(&L.parts_off[ci + 1]);
 					for(; i < e; i++)
@@ -588,7 +590,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 						if(py < 0.0f || py > 1.0f)   // trace.h:404-440
 						{
 							uint32_t pk;
-							if(ncls == CL_PORTAL) pk = oobm ? PK_WALL : ((__ldg(&L.portals[cell >> CM_REC_SHIFT].flags) >> 16) & 255u);
+							if(ncls == CL_PORTAL) pk = oobm ? PK_WALL : ((__ldg(&L.portals[(cell >> CM_REC_SHIFT) & (SPH ? CM_REC_MASK : 0xFFFFu)].flags) >> 16) & 255u);
 							else pk = (ncls == CL_TWO || ncls == CL_TWO_FOG) ? PK_PASS : (ncls == CL_RAISED ? PK_RAISED : PK_WALL);
 							if(pk != PK_PASS)
 							{
@@ -649,7 +651,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 			else if((cell & 15u) == CL_PORTAL)
 			{
 				// trace.h:508-650
-				const uint4 pa = __ldg(reinterpret_cast<const uint4 *>(&L.portals[cell >> CM_REC_SHIFT]));
+				const uint4 pa = __ldg(reinterpret_cast<const uint4 *>(&L.portals[(cell >> CM_REC_SHIFT) & (SPH ? CM_REC_MASK : 0xFFFFu)]));
 				uint32_t pkind = (pa.w >> 8) & 255u;
 				if(oobm && pkind == PR_OK) pkind = PR_STRAY;   // outside the grid no end matches (trace.h:530,539)
 				if(pkind != PR_OK)
@@ -657,7 +659,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 					PWN_SPHERE_EXIT(false, 0.0f)
 					PWN_WALL_EXIT(pkind == PR_UNPAIRED ? SF_WALL : SF_STRAY)
 				}
-				const uint4 pb = __ldg(reinterpret_cast<const uint4 *>(&L.portals[cell >> CM_REC_SHIFT]) + 1);
+				const uint4 pb = __ldg(reinterpret_cast<const uint4 *>(&L.portals[(cell >> CM_REC_SHIFT) & (SPH ? CM_REC_MASK : 0xFFFFu)]) + 1);
 				ci = (int)pa.x;
 				if(IDS) { cx = (int)pb.z; cz = (int)pb.w; ops += W_PORTAL; nport++; }
 				px = __fadd_rn(px, __uint_as_float(pa.y));
