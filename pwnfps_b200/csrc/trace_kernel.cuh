@@ -429,7 +429,10 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 		float cdist = 0.0f, fog = 0.0f;
 		int nstep = 0, nport = 0;
 		Aux aux;
-		aux.dist = -1.0f;
+		// "no sphere yet" is +inf here, not the reference's -1 (trace.h:196): then "a sphere, and nearer than where the
+		// walk has got to" is ONE compare at every step, and "none yet, or nearer than the one so far" one at every
+		// test.  A hit at exactly -1, which the reference then takes for "none", is stored as +inf for the same effect.
+		aux.dist = __int_as_float(0x7F800000);
 		aux.px = aux.py = aux.pz = 0.0f; aux.diff = 0.0f; aux.si = 0u;
 
 		// how the walk ended: a surface (SF_CEIL..SF_STRAY), a sphere, or not at all (maxsteps, trace.h:677).
@@ -441,7 +444,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 // the "sphere nearer than where we got to" exits (trace.h:313-319 and friends)
 #define PWN_SPHERE_MARK hsurf = SF_SPHERE; ldir = -1;
 #define PWN_SPHERE_EXIT(FOGC, FOGBEG) \
-		if(SPH && aux.dist != -1.0f && cdist > aux.dist) { \
+		if(SPH && cdist > aux.dist) { \
 			PWN_SPHERE_MARK \
 			if((FOGC) && aux.dist > (FOGBEG)) fog = __fadd_rn(fog, __fsub_rn(aux.dist, (FOGBEG))); \
 			break; }
@@ -497,10 +500,10 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 								const float sdist2 = __fsub_rn(1.0f, __fdiv_rn(calcrad2, rad2));
 								const float sd = __fsub_rn(__fsqrt_rn(dist2), __fsqrt_rn(sdist2));
 								const float ad = __fadd_rn(sd, cdist);
-								if(aux.dist == -1.0f || ad < aux.dist)
+								if(ad < aux.dist)
 								{
 									if(IDS) ops += W_SPH_HIT;
-									aux.dist = ad;
+									aux.dist = (ad == -1.0f) ? __int_as_float(0x7F800000) : ad;
 									aux.px = __fadd_rn(px, __fmul_rn(sd, rx));
 									aux.py = __fadd_rn(py, __fmul_rn(sd, ry));
 									aux.pz = __fadd_rn(pz, __fmul_rn(sd, rz));
