@@ -576,6 +576,21 @@ def test_error_paths(tracer, default_level):
     with pytest.raises(api.PwnError):
         tracer.level_upload(api.Level(cells, default_level.portals))
     tracer.level_upload(default_level)
+    tracer.shard_config(1, 0)
+    # device-layout limits: a frame of 2^31 pixels (K1 and K2 index it with 32 bits) is refused before anything is
+    # allocated, and so is a level with more portal cells than a map entry can name (15 bits beside the sphere bit)
+    with pytest.raises(api.PwnError) as e:
+        tracer.frame_config(65536, 32768)
+    assert e.value.code == -5
+    tracer.frame_config(64, 64)
+    cells = np.full((200, 200), ord("A"), np.int32)
+    cells[0, :] = cells[-1, :] = cells[:, 0] = cells[:, -1] = ord(" ")
+    portals = np.zeros(1, api.PORTAL_DTYPE)
+    portals[0] = (1, 1, 2, 1, 0, ord(";"), ord(";"))
+    with pytest.raises(api.PwnError) as e:
+        tracer.level_upload(api.Level(cells, portals, 1, 1))
+    assert e.value.code == -5
+    tracer.level_upload(default_level)
 
 
 def test_sharded_blur_allgather_in_one_process(tracer, default_level):
