@@ -157,6 +157,8 @@ int pwn_debug_pack(pwn_ctx *ctx, const float *bgra, uint32_t *packed, int n);
  * a w*h plane of cell classes and one transform record per portal cell.
  * cells: h rows of w int32 codes, row z then column x (lv->data[z][x]).
  * portals: nportals entries indexed by PWN_PORTAL_INDEX (lv->pmap[]).
+ * Device-layout limits (PWN_E_LIMIT): at most 16384 cells per axis and 32768 portal CELLS
+ * (the reference's own limits are 64x64 cells and 26 letters, defs.h:96-111).
  */
 int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells, int nportals, const pwn_portal *portals);
 
@@ -164,6 +166,7 @@ int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells, int nport
 int pwn_parts_upload(pwn_ctx *ctx, int nsph, const pwn_sphere *sph);
 
 /* ---- frame buffers (the globals sbuf/tsbuf/zbuf, main.c:31-33,395-400) ------------ */
+/* (PWN_E_LIMIT for rwidth*rheight >= 2^31: the kernels index a frame with 32 bits) */
 int pwn_frame_config(pwn_ctx *ctx, int rwidth, int rheight, int want_ids);
 /* zero sbuf/zbuf (and ids) on the device: what a fresh malloc'd+memset frame is to the reference */
 int pwn_frame_clear(pwn_ctx *ctx);
