@@ -325,6 +325,7 @@ def run_ours(args, rank, world, local_rank):
         "achieved": achieved, "peak": peak_issue, "unit": "Tlaneop/s", "frac": achieved / peak_issue,
         "peak_how": "148 SMs x 128 FP32 lanes x %.0f MHz max boost (1 lane-op per slot; FMA-counted peak is 2x)" % peaks["sm_max_mhz"],
         "frac_at_measured_clock": achieved / (SM_COUNT * FP32_LANES * sm_mhz * 1e6 / 1e12),
+        "peak_fma": 2.0 * peak_issue, "frac_of_fma_peak": achieved / (2.0 * peak_issue),   # both peaks
         "peak_measured": peak_measured, "frac_of_measured_peak": (achieved / peak_measured) if peak_measured else None,
         "peak_measured_how": "k_fp32_peak: 8 independent non-fused FMUL+FADD chains per thread, 148x8 CTAs x 256 threads, best of 4",
         "ops_per_pixel": ops_per_frame / (w * h), "k1_ms_per_launch": k1_ms, "k2_ms_per_launch": k2_ms,
