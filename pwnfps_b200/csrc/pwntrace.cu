@@ -217,7 +217,16 @@ extern "C" int pwn_math_tables(pwn_ctx *ctx, const uint32_t *rcp_tab, int rcp_bi
 	CU(cudaMalloc(&ctx->d_rcp, nr*sizeof(uint32_t)));
 	CU(cudaMalloc(&ctx->d_rsqrt, ns*sizeof(uint32_t)));
 	CU(cudaMemcpy(ctx->d_rcp, rcp_tab, nr*sizeof(uint32_t), cudaMemcpyHostToDevice));
-	CU(cudaMemcpy(ctx->d_rsqrt, rsqrt_tab, ns*sizeof(uint32_t), cudaMemcpyHostToDevice));
+	// The device's copy of the rsqrt table is re-indexed and re-biased so that rsqrt_emul needs neither the flip of
+	// the exponent's low bit nor the "+1 before halving" (trace_kernel.cuh): entry i2 = [E & 1 | top mantissa bits]
+	// holds the host entry of the other parity, minus (E & 1) << 23, plus the 0x20000000 of the result exponent.
+	// (E + 1) >> 1 == (E >> 1) + (E & 1) for every E, so the result is the same word for every positive input.
+	{
+		std::vector<uint32_t> st2(ns);
+		for(size_t i2 = 0; i2 < ns; i2++)
+			st2[i2] = rsqrt_tab[i2 ^ ((size_t)1 << rsqrt_bits)] - ((uint32_t)((i2 >> rsqrt_bits) & 1) << 23) + 0x20000000u;
+		CU(cudaMemcpy(ctx->d_rsqrt, st2.data(), ns*sizeof(uint32_t), cudaMemcpyHostToDevice));
+	}
 	ctx->rcp_bits = rcp_bits; ctx->rsqrt_bits = rsqrt_bits;
 	ctx->have_tables = true;
 	return PWN_OK;

@@ -148,16 +148,15 @@ __device__ __forceinline__ float rcp_emul(const LevelDev &L, float x)
 	return __uint_as_float(t - (u & 0x7F800000u) + 0x3F800000u);
 }
 
-// rsqrtps(x), x > 0 normal.  The table index is [parity of the unbiased exponent | top mantissa
-// bits]; with E the biased exponent that parity is !(E & 1), so the index is read straight from
-// the bit pattern with the exponent's low bit flipped, and the result exponent is
-// floor((E - 127)/2) = ((E + 1) >> 1) - 64.
+// rsqrtps(x), x > 0.  The host's table is indexed by [parity of the unbiased exponent | top mantissa bits] and the
+// result exponent is floor((E - 127)/2) = ((E + 1) >> 1) - 64, E the biased exponent.  pwn_math_tables stores the
+// table re-indexed by [E & 1 | top mantissa bits] -- the bit pattern as it is -- with (E & 1) << 23 and the
+// exponent bias already taken out of each entry, which leaves a shift, a mask and a subtract around the load.
 __device__ __forceinline__ float rsqrt_emul(const LevelDev &L, float x)
 {
 	const uint32_t u = __float_as_uint(x);
-	const uint32_t idx = ((u ^ 0x00800000u) >> L.rsqrt_shift) & L.rsqrt_mask;
-	const uint32_t t = __ldg(&L.rsqrt_tab[idx]);
-	return __uint_as_float(t - (((u + 0x00800000u) >> 1) & 0x7F800000u) + 0x20000000u);
+	const uint32_t t = __ldg(&L.rsqrt_tab[(u >> L.rsqrt_shift) & L.rsqrt_mask]);
+	return __uint_as_float(t - ((u >> 1) & 0x7F800000u));
 }
 
 // util.h:1-16 with the shipped -ffast-math folding of randfs: r*fl(2/3759) - 1
