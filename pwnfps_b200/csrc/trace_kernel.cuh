@@ -228,7 +228,9 @@ __device__ __forceinline__ bool bit_of(uint32_t v, uint32_t mask)
 }
 
 // surface colours, lanes b g r a (defs.h:17-19, trace.h:558)
-enum : int { SF_CEIL = 0, SF_FLOOR = 1, SF_WALL = 2, SF_STRAY = 3, SF_NONE = 4, SF_SPHERE = 5 };
+// (the codes are the byte offsets of the colours in c_surface: the indexed load takes them as they are)
+enum : int { SF_CEIL = 0, SF_FLOOR = 16, SF_WALL = 32, SF_STRAY = 48, SF_NONE = 64, SF_SPHERE = 80 };
+#define PWN_SURFACE(H) c_surface[(H) >> 4]
 __constant__ float4 c_surface[4] = {
 	{30.0f, 30.0f, 0.0f, 0.0f},   // COL_CEIL
 	{1.0f, 1.0f, 1.0f, 0.0f},     // COL_FLOOR
@@ -760,7 +762,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 			if(IDS) ops += W_WALL;
 			// one indexed load from the constant bank instead of a four-way branch: the lanes of a warp hit
 			// ceilings, floors and walls side by side
-			const float4 sc = c_surface[hsurf];
+			const float4 sc = PWN_SURFACE(hsurf);
 			const float sb = sc.x, sg = sc.y, sr = sc.z;
 			cb = __fmul_rn(icb, sb); cg = __fmul_rn(icg, sg); cr = __fmul_rn(icr, sr);
 			if(SPH) ca = __fmul_rn(ica, 0.0f);   // (without spheres the alpha lane of a shaded colour is +0 exactly, see ALPHA0)
