@@ -51,7 +51,8 @@ enum
 	PWN_E_STATE = -4,      /* call order: level, tables or frame not set up yet  */
 	PWN_E_LIMIT = -5,      /* level exceeds a device-layout limit                */
 	PWN_E_HOSTMATH = -6,   /* host rcpps/rsqrtps is not a pure mantissa-bucket table */
-	PWN_E_UNSUPPORTED = -7 /* input outside what the reference host can produce  */
+	PWN_E_UNSUPPORTED = -7,/* input outside what the reference host can produce  */
+	PWN_E_PEER = -8        /* sharded frame: a peer GPU missed the device barrier */
 };
 
 /* defs.h:25-33 */
@@ -144,6 +145,14 @@ int pwn_host_math_probe(int *rcp_bits, int *rsqrt_bits, uint32_t *rcp_tab, size_
  */
 int pwn_host_libm_probe(int *fma_build, int *exact);
 int pwn_libm_config(pwn_ctx *ctx, int fma_build);
+/*
+ * What the context's emulation is pinned to: table widths, the libm variant in use, and whether
+ * pwn_math_tables_from_host found this host's libm to be exactly that variant (1), neither of the two
+ * (0: pwn_math_tables_from_host then also leaves a warning in pwn_last_error -- frames are bit-exact against
+ * a glibc 2.39 host, not necessarily against this one), or -1 when tables / variant were handed in.
+ * Any pointer may be NULL.
+ */
+int pwn_math_status(pwn_ctx *ctx, int *rcp_bits, int *rsqrt_bits, int *libm_fma, int *libm_exact);
 /* test hook (host only, no GPU): the restatement itself over an array */
 void pwn_host_libm_eval(const float *in, float *s, float *c, float *e, size_t n, int fma_build);
 /* test hook: sin, cos, exp of n floats evaluated by the device functions K1 uses */
@@ -223,6 +232,12 @@ int pwn_write_frame(pwn_ctx *ctx, const uint32_t *sbuf, const float *zbuf);
  */
 int pwn_trace_screen(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags,
 	uint32_t *sbuf_host, float *zbuf_host);
+/*
+ * pwn_trace_screen traces (and blurs) a frame in row chunks so that the copy of chunk k to the host runs under
+ * the kernels of chunk k+1; only the traced window [0,dimx) x [0,dimy) of the host buffers is written, as in the
+ * reference.  nchunks: 1..8, or 0 = automatic (4 for frames of half a megapixel and more, else 1).
+ */
+int pwn_screen_chunks(pwn_ctx *ctx, int nchunks);
 
 /*
  * screen_upscale (screen.h:126-149) on the device: every pixel of the dimx x dimy frame in
@@ -279,7 +294,11 @@ int pwn_frame_ipc_close(pwn_ctx *ctx, uint64_t base_dev);
  * base_dev[s] = device address of shard s's frame allocation in THIS process (pwn_frame_ipc_import
  * of the handle shard s exported; the own entry is ignored).  All shards must configure the same
  * frame size and call pwn_trace_shard_blur the same number of times.  nshards == 0 clears.
- * A shard that never arrives ends the wait after 4 s; pwn_frame_peers_status then reports 1.
+ * A shard that never arrives ends the wait after 4 s: the next pwn_sync / pwn_read_frame / pwn_read_bands of
+ * the waiting shard then fails with PWN_E_PEER (once per incident; the frame holds stale bands), and
+ * pwn_frame_peers_status reports 1 until pwn_frame_peers is called again.  A shard whose own trace cannot be
+ * launched still meets its peers at both barriers of that frame, so the others neither wait nor fall out of step,
+ * and returns its error.
  */
 int pwn_frame_peers(pwn_ctx *ctx, int nshards, const uint64_t *base_dev);
 int pwn_trace_shard_blur(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags);

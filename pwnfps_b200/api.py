@@ -63,6 +63,7 @@ ABI_SYMBOLS = [
     "pwn_screen_upscale", "pwn_surface_device_ptr", "pwn_last_upscale_ms", "pwn_trace_config",
     "pwn_frame_peers", "pwn_trace_shard_blur", "pwn_frame_peers_status",
     "pwn_host_register", "pwn_host_unregister", "pwn_debug_pack", "pwn_write_frame", "pwn_read_bands",
+    "pwn_math_status", "pwn_screen_chunks",
 ]
 
 
@@ -125,6 +126,8 @@ def lib():
     L.pwn_host_unregister.argtypes = [vp]
     L.pwn_trace_shard_blur.argtypes = [vp, vp, i, i, f, u]
     L.pwn_frame_peers_status.argtypes = [vp, C.POINTER(i)]
+    L.pwn_math_status.argtypes = [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]
+    L.pwn_screen_chunks.argtypes = [vp, i]
     _lib = L
     return L
 
@@ -481,6 +484,12 @@ class Tracer:
     def libm_config(self, fma_build):
         _check(self.L.pwn_libm_config(self.h, int(fma_build)))
 
+    def math_status(self):
+        """(rcp_bits, rsqrt_bits, libm_fma, libm_exact) -- pwn_math_status"""
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(self.L.pwn_math_status(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
     def debug_libm(self, x):
         x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
         s, c, e = np.empty_like(x), np.empty_like(x), np.empty_like(x)
@@ -574,6 +583,10 @@ class Tracer:
                                        PWN_F_BLUR if blur else 0, sbuf.ctypes.data,
                                        zbuf.ctypes.data if zbuf is not None else None))
         return sbuf
+
+    def screen_chunks(self, nchunks=0):
+        """row chunks per frame of trace_screen_centred (0 = automatic)"""
+        _check(self.L.pwn_screen_chunks(self.h, nchunks))
 
     def trace_poses(self, poses, dimx, dimy, flags=0, out=None, want_sums=False):
         poses = np.ascontiguousarray(poses, dtype=POSE_DTYPE)

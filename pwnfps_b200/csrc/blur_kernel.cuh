@@ -22,6 +22,11 @@ struct BlurParams
 	int y0, y1;            // rows to produce
 	int nshards, shard;    // rows y0 + the 32-row bands b with b % nshards == shard (1, 0: all rows)
 	float fstr;            // 0.002f * dimy (screen.h:86), computed on the host in float
+	// pwn_trace_screen blurs a frame in row chunks while later chunks are still being traced: rows [0, ylimit) of src
+	// are final.  A pixel with a sample below them is not written but queued (defer_list[atomicAdd(defer_count)] =
+	// pixel index) for k_blur_fix, which runs when the whole frame has been traced.
+	int ylimit;
+	uint32_t *defer_count, *defer_list;
 };
 
 // s -> A*s + C (mod 2^31) composed n times for n = 0, 2, 4, 6 (a pixel's offset inside its group)
@@ -54,6 +59,7 @@ __device__ __forceinline__ uint32_t pavgb4(uint32_t a, uint32_t b)
 }
 
 // one output pixel of the blur pass (screen.h:91-117)
+template <bool DEFER>
 __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 {
 	const uint32_t pix = (uint32_t)y*(uint32_t)P.rwidth + (uint32_t)x;   // (a frame has fewer than 2^31 pixels: pwn_frame_config)
@@ -76,6 +82,31 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 	// six draws separate this pixel's pair in sample i from its pair in sample i+1
 	const uint32_t a6 = c_jumpA[3], c6 = c_jumpC[3];
 	uint32_t s[4];
+	if(DEFER)
+	{
+		uint32_t at[4];
+		int ymax = 0;
+		#pragma unroll
+		for(int i = 0; i < 4; i++)
+		{
+			const int sx = cvtt_clamp(__fadd_rn(fbx, __fmul_rn(__fmul_rn(blur_randfs(seed), P.fstr), z)), P.dimx - 1);
+			const int sy = cvtt_clamp(__fadd_rn(fby, __fmul_rn(__fmul_rn(blur_randfs(seed), P.fstr), z)), P.dimy - 1);
+			at[i] = (uint32_t)sy*(uint32_t)P.rwidth + (uint32_t)sx;
+			ymax = max(ymax, sy);
+			seed = a6*seed + c6;
+		}
+		if(ymax >= P.ylimit)   // a sample in a row that is still being traced: k_blur_fix finishes this pixel
+		{
+			P.defer_list[atomicAdd(P.defer_count, 1u)] = pix;
+			return;
+		}
+		// (plain loads: later rows of src are written by a trace that runs beside this kernel, and the
+		// non-coherent path may only be used for data nobody writes during the launch)
+		#pragma unroll
+		for(int i = 0; i < 4; i++) s[i] = P.src[at[i]];
+	}
+	else
+	{
 	#pragma unroll
 	for(int i = 0; i < 4; i++)
 	{
@@ -84,17 +115,31 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 		s[i] = __ldg(&P.src[(uint32_t)sy*(uint32_t)P.rwidth + (uint32_t)sx]);
 		seed = a6*seed + c6;
 	}
+	}
 	// pavgb: per byte (a+b+1)>>1 (screen.h:112-115)
 	P.dst[pix] = pavgb4(pavgb4(s[0], s[1]), pavgb4(s[2], s[3]));
 }
 
+template <bool DEFER>
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ BlurParams P)
 {
 	const int x = blockIdx.x*blockDim.x + threadIdx.x;
 	const int lrow = blockIdx.y;
 	const int y = P.y0 + ((lrow >> 5)*P.nshards + P.shard)*32 + (lrow & 31);
 	if(x >= P.dimx || y >= P.y1) return;
-	blur_pixel(P, x, y);
+	blur_pixel<DEFER>(P, x, y);
+}
+
+// the pixels k_blur<true> queued, once the whole pre-blur frame is there
+__global__ void __launch_bounds__(256) k_blur_fix(const __grid_constant__ BlurParams P)
+{
+	const uint32_t n = *P.defer_count;
+	for(uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x)
+	{
+		const uint32_t pix = P.defer_list[i];
+		const uint32_t y = pix / (uint32_t)P.rwidth;
+		blur_pixel<false>(P, (int)(pix - y*(uint32_t)P.rwidth), (int)y);
+	}
 }
 
 // ---- barrier between the GPUs of a sharded frame, on the device ---------------------------------

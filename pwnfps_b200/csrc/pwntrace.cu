@@ -66,6 +66,8 @@ struct pwn_ctx
 	cudaStream_t stream = nullptr, copy_stream = nullptr;
 	cudaEvent_t ev_k1a = nullptr, ev_k1b = nullptr, ev_k2b = nullptr;
 	cudaEvent_t ev_done[3] = {nullptr, nullptr, nullptr}, ev_copied[3] = {nullptr, nullptr, nullptr};
+	cudaEvent_t ev_chunk[16] = {};   // pwn_trace_screen: "chunk c traced" (0-7) and "chunk c blurred" (8-15)
+	uint32_t *h_defer = nullptr;     // pinned: how many pixels the chunked blur had to leave to k_blur_fix
 
 	// level
 	uint32_t *d_cellmap = nullptr;
@@ -107,12 +109,16 @@ struct pwn_ctx
 
 	int nshards = 1, shard = 0;
 	int reflect = 2;           // REFLECT as shipped (defs.h:8)
+	int screen_chunks = 0;     // pwn_trace_screen: row chunks per frame, 0 = automatic
 	// sharded frame with the blur pass: the other shards' frame allocations (pwn_frame_peers)
 	char *peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	int npeer_shards = 0;
 	uint32_t epoch = 0;
+	bool barrier_pending = false;  // a sharded frame's barriers are in the stream and their error word has not been looked at
+	unsigned peer_timeouts = 0;    // sharded frames that ended in a barrier time-out since pwn_frame_peers
 	bool allgather_now = false;   // launch_trace: trace into the pre-blur buffer here and on every peer, no blur
 	int libm_fma = 1;          // glibc build the reference host would run: 1 "_fma", 0 "_sse2"
+	int libm_exact = -1;       // pwn_host_libm_probe's verdict: 1 the host runs exactly that build, 0 neither, -1 tables were handed in
 	unsigned long long launches = 0;
 	bool timed = false;        // events of the last trace are valid
 	bool timed_blur = false;
@@ -157,6 +163,9 @@ extern "C" int pwn_create(pwn_ctx **out, int device)
 		CU(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
 	}
+	for(int i = 0; i < 16; i++) CU(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
+	CU(cudaHostAlloc((void **)&ctx->h_defer, 64, cudaHostAllocDefault));
+	ctx->h_defer[0] = 0;
 
 	// LCG jumps for K2 (util.h:1-6: s -> 25739 s + 4): entries 0..3 = the map composed 0, 2, 4, 6 times
 	uint32_t ja[8] = {1u, 0, 0, 0, 0, 0, 0, 0}, jc[8] = {0u, 0, 0, 0, 0, 0, 0, 0};
@@ -196,6 +205,8 @@ extern "C" int pwn_destroy(pwn_ctx *ctx)
 	cudaEvent_t evs[] = {ctx->ev_k3a, ctx->ev_k3b, ctx->ev_k1a, ctx->ev_k1b, ctx->ev_k2b, ctx->ev_done[0], ctx->ev_done[1], ctx->ev_done[2],
 		ctx->ev_copied[0], ctx->ev_copied[1], ctx->ev_copied[2]};
 	for(cudaEvent_t e : evs) if(e) cudaEventDestroy(e);
+	for(cudaEvent_t e : ctx->ev_chunk) if(e) cudaEventDestroy(e);
+	if(ctx->h_defer) cudaFreeHost(ctx->h_defer);
 	if(ctx->stream) cudaStreamDestroy(ctx->stream);
 	if(ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
 	cudaGetLastError();
@@ -244,7 +255,25 @@ extern "C" int pwn_math_tables_from_host(pwn_ctx *ctx)
 	int fma_build = 1, exact = 0;
 	pwn_host_libm_probe(&fma_build, &exact);
 	ctx->libm_fma = fma_build;
-	return pwn_math_tables(ctx, rt.data(), rb, st.data(), sb);
+	ctx->libm_exact = exact;
+	rc = pwn_math_tables(ctx, rt.data(), rb, st.data(), sb);
+	if(rc != PWN_OK) return rc;
+	// neither of the two glibc 2.39 builds the device restates: the floor and fog shading can then differ from this
+	// host's reference build in the last bit.  Not an error (the frame is still a valid frame of the reference on a
+	// glibc 2.39 host); the caller can ask (pwn_math_status) and refuse.
+	if(!exact) snprintf(g_err, sizeof(g_err), "warning: this host's libm is neither glibc 2.39's _fma nor its _sse2 build of sinf/cosf/expf; "
+		"the device uses the %s variant, bounce shading may differ from this host's reference build in the last bit", fma_build ? "_fma" : "_sse2");
+	return PWN_OK;
+}
+
+extern "C" int pwn_math_status(pwn_ctx *ctx, int *rcp_bits, int *rsqrt_bits, int *libm_fma, int *libm_exact)
+{
+	if(ctx == nullptr) return fail(PWN_E_ARG, "null context");
+	if(rcp_bits) *rcp_bits = ctx->rcp_bits;
+	if(rsqrt_bits) *rsqrt_bits = ctx->rsqrt_bits;
+	if(libm_fma) *libm_fma = ctx->libm_fma;
+	if(libm_exact) *libm_exact = ctx->libm_exact;
+	return PWN_OK;
 }
 
 extern "C" int pwn_libm_config(pwn_ctx *ctx, int fma_build)
@@ -252,6 +281,7 @@ extern "C" int pwn_libm_config(pwn_ctx *ctx, int fma_build)
 	if(ctx == nullptr) return fail(PWN_E_ARG, "null context");
 	if(fma_build != 0 && fma_build != 1) return fail(PWN_E_ARG, "pwn_libm_config: variant %d", fma_build);
 	ctx->libm_fma = fma_build;
+	ctx->libm_exact = -1;
 	return PWN_OK;
 }
 
@@ -447,12 +477,18 @@ extern "C" int pwn_parts_upload(pwn_ctx *ctx, int nsph, const pwn_sphere *sph)
 		if(pass == 1) { idx.assign(off[ncell] ? off[ncell] : 1, 0); cur.assign(off.begin(), off.end() - 1); }
 		for(int i = 0; i < nsph; i++)
 		{
-			const int cx1 = cvtt_host(sph[i].pos[0] - sph[i].r), cz1 = cvtt_host(sph[i].pos[2] - sph[i].r);
-			const int cx2 = cvtt_host(sph[i].pos[0] + sph[i].r), cz2 = cvtt_host(sph[i].pos[2] + sph[i].r);
+			int cx1 = cvtt_host(sph[i].pos[0] - sph[i].r), cz1 = cvtt_host(sph[i].pos[2] - sph[i].r);
+			int cx2 = cvtt_host(sph[i].pos[0] + sph[i].r), cz2 = cvtt_host(sph[i].pos[2] + sph[i].r);
+			// the reference writes out of bounds for cells outside the grid (level.h:1-39); only the cells inside are
+			// ever looked at (trace.h:252), so the box is cut to the grid first -- a far-away or huge sphere would
+			// otherwise walk up to 2^64 cells here
+			if(cx1 < 0) cx1 = 0;
+			if(cz1 < 0) cz1 = 0;
+			if(cx2 > w - 1) cx2 = w - 1;
+			if(cz2 > h - 1) cz2 = h - 1;
 			for(int z = cz1; z <= cz2; z++)
 			for(int x = cx1; x <= cx2; x++)
 			{
-				if(x < 0 || x >= w || z < 0 || z >= h) continue;   // the reference writes out of bounds here
 				const size_t ci = (size_t)(z + 1)*wp + x + 1;
 				if(pass == 0) off[ci + 1]++;
 				else idx[cur[ci]++] = (uint32_t)i;
@@ -590,13 +626,15 @@ static BlurParams blur_params(pwn_ctx *ctx, const uint32_t *src, const float *z,
 	B.dimx = dimx; B.dimy = dimy; B.rwidth = ctx->rwidth; B.y0 = 0; B.y1 = dimy;
 	B.nshards = 1; B.shard = 0;
 	B.fstr = 0.002f * (float)dimy;   // screen.h:86
+	B.ylimit = dimy; B.defer_count = nullptr; B.defer_list = nullptr;
 	return B;
 }
 
 static int launch_blur(pwn_ctx *ctx, const BlurParams &B, int nrows = -1)
 {
 	dim3 grid((B.dimx + 255)/256, nrows < 0 ? B.dimy : nrows), block(256);
-	k_blur<<<grid, block, 0, ctx->stream>>>(B);
+	if(B.defer_count != nullptr && B.ylimit < B.dimy) k_blur<true><<<grid, block, 0, ctx->stream>>>(B);
+	else k_blur<false><<<grid, block, 0, ctx->stream>>>(B);
 	CU(cudaGetLastError());
 	ctx->launches++;
 	return PWN_OK;
@@ -624,7 +662,8 @@ static void launch_k1(const TraceParams &P, dim3 grid, cudaStream_t st, bool ids
 // K1 for one frame into frame set f (+ the blur of `prev`'s frame riding along, pose batches),
 // then, for a single blurred frame, K2
 static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], const float rayb[4], const float rdx[4], const float rdy[4],
-	int dimx, int dimy, float sec, unsigned flags, bool timing, const FrameSet *prev = nullptr, bool defer_blur = false)
+	int dimx, int dimy, float sec, unsigned flags, bool timing, const FrameSet *prev = nullptr, bool defer_blur = false,
+	int band0 = 0, int nbands_launch = -1)
 {
 	if(!ctx->have_level) return fail(PWN_E_STATE, "trace before pwn_level_upload");
 	if(!ctx->have_tables) return fail(PWN_E_STATE, "trace before pwn_math_tables");
@@ -683,9 +722,13 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 	if(blurp) P.prev = blur_params(ctx, prev->tsbuf, prev->zbuf, prev->sbuf, dimx, dimy);
 
 	ctx->timed = ctx->timed_blur = false;
-	if(P.nbands_local > 0)
+	// (a launch may cover only bands [band0, band0 + nbands_launch) of the shard's: pwn_trace_screen's row chunks)
+	P.band0 = band0;
+	int nb_launch = P.nbands_local - band0;
+	if(nbands_launch >= 0 && nbands_launch < nb_launch) nb_launch = nbands_launch;
+	if(nb_launch > 0)
 	{
-		dim3 grid((dimx + 31)/32, P.nbands_local*(32/K1_ROWS));
+		dim3 grid((dimx + 31)/32, nb_launch*(32/K1_ROWS));
 		if(timing) CU(cudaEventRecord(ctx->ev_k1a, ctx->stream));
 		const bool ids = P.ids != nullptr;
 		if(ctx->nsph > 0) { if(ctx->libm_fma) launch_k1<true, true>(P, grid, ctx->stream, ids, blurp); else launch_k1<true, false>(P, grid, ctx->stream, ids, blurp); }
@@ -717,6 +760,8 @@ extern "C" int pwn_frame_peers(pwn_ctx *ctx, int nshards, const uint64_t *base_d
 	if(ctx == nullptr) return fail(PWN_E_ARG, "null context");
 	for(int t = 0; t < 8; t++) ctx->peer_base[t] = nullptr;
 	ctx->npeer_shards = 0;
+	ctx->barrier_pending = false;
+	ctx->peer_timeouts = 0;
 	if(nshards == 0) return PWN_OK;
 	if(nshards < 2 || nshards > 8 || base_dev == nullptr) return fail(PWN_E_ARG, "pwn_frame_peers: %d shards (2..8)", nshards);
 	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "pwn_frame_peers before pwn_frame_config");
@@ -754,20 +799,25 @@ extern "C" int pwn_trace_shard_blur(pwn_ctx *ctx, const float cam[16], int dimx,
 	float rayb[4], rdx[4], rdy[4];
 	pwn_ray_setup(cam, dimx, dimy, rayb, rdx, rdy);
 	const FrameSet &f = ctx->fs[0];
+	// The epoch counts the calls, whatever becomes of them: a shard whose trace cannot be launched still meets its
+	// peers at both barriers of this frame (they would otherwise spin into the time-out, and every later frame would
+	// be one epoch out of step) and reports the failure to its own caller.
 	ctx->epoch++;
+	ctx->barrier_pending = true;
 	// K1: own bands into the pre-blur buffer of every shard (and zbuf here)
 	ctx->allgather_now = true;
-	int rc = launch_trace(ctx, f, cam + 12, rayb, rdx, rdy, dimx, dimy, sec_current, (flags | PWN_F_BLUR) & ~PWN_F_IDS, true);
+	const int rc_trace = launch_trace(ctx, f, cam + 12, rayb, rdx, rdy, dimx, dimy, sec_current, (flags | PWN_F_BLUR) & ~PWN_F_IDS, true);
 	ctx->allgather_now = false;
-	if(rc != PWN_OK) return rc;
+	char trace_err[sizeof(g_err)];
+	if(rc_trace != PWN_OK) memcpy(trace_err, g_err, sizeof(g_err));
 	if(!ctx->timed) { CU(cudaEventRecord(ctx->ev_k1a, ctx->stream)); CU(cudaEventRecord(ctx->ev_k1b, ctx->stream)); ctx->timed = true; }
 	// A: every shard's bands have landed everywhere
-	rc = launch_barrier(ctx, 0);
+	int rc = launch_barrier(ctx, 0);
 	if(rc != PWN_OK) return rc;
 	// K2 on the own bands, straight into shard 0's frame
 	const int nbands = (dimy + 31)/32;
 	const int nb_local = nbands > ctx->shard ? (nbands - ctx->shard + ctx->nshards - 1)/ctx->nshards : 0;
-	if(nb_local > 0)
+	if(nb_local > 0 && rc_trace == PWN_OK)
 	{
 		uint32_t *dst = (flags & PWN_F_LOCAL_BANDS) ? f.sbuf : (uint32_t *)(ctx->peer_base[0] + f.off_sbuf);
 		BlurParams B = blur_params(ctx, f.tsbuf, f.zbuf, dst, dimx, dimy);
@@ -781,7 +831,25 @@ extern "C" int pwn_trace_shard_blur(pwn_ctx *ctx, const float cam[16], int dimx,
 	if(rc != PWN_OK) return rc;
 	CU(cudaEventRecord(ctx->ev_k2b, ctx->stream));
 	ctx->timed_blur = true;
+	if(rc_trace != PWN_OK) { memcpy(g_err, trace_err, sizeof(g_err)); return rc_trace; }
 	return PWN_OK;
+}
+
+// After a sharded frame the stream has run two device-side barriers.  A peer that never arrived left the error word
+// set (k_peer_barrier): the calls that hand the frame to the host look at it once the stream has drained, clear it, and
+// fail -- the frame then holds stale bands of the late shard.
+static int check_peer_barriers(pwn_ctx *ctx)
+{
+	if(!ctx->barrier_pending) return PWN_OK;
+	ctx->barrier_pending = false;
+	uint32_t v = 0;
+	CU(cudaMemcpyAsync(&v, ctx->fs[0].flags + 16, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	if(v == 0u) return PWN_OK;
+	ctx->peer_timeouts++;
+	CU(cudaMemsetAsync(ctx->fs[0].flags + 16, 0, 4, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return fail(PWN_E_PEER, "sharded frame %u: a peer shard did not reach the device barrier within 4 s; the frame is incomplete", ctx->epoch);
 }
 
 extern "C" int pwn_read_bands(pwn_ctx *ctx, int dimx, int dimy, uint32_t *sbuf_host_frame)
@@ -799,7 +867,7 @@ extern "C" int pwn_read_bands(pwn_ctx *ctx, int dimx, int dimy, uint32_t *sbuf_h
 		CU(cudaMemcpyAsync(sbuf_host_frame + off, f.sbuf + off, (size_t)rows*ctx->rwidth*4, cudaMemcpyDeviceToHost, ctx->stream));
 	}
 	CU(cudaStreamSynchronize(ctx->stream));
-	return PWN_OK;
+	return check_peer_barriers(ctx);
 }
 
 extern "C" int pwn_frame_peers_status(pwn_ctx *ctx, int *timed_out)
@@ -810,7 +878,7 @@ extern "C" int pwn_frame_peers_status(pwn_ctx *ctx, int *timed_out)
 	uint32_t v = 0;
 	CU(cudaMemcpyAsync(&v, ctx->fs[0].flags + 16, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
-	*timed_out = (int)v;
+	*timed_out = (v != 0u || ctx->peer_timeouts != 0) ? 1 : 0;
 	return PWN_OK;
 }
 
@@ -851,7 +919,7 @@ extern "C" int pwn_sync(pwn_ctx *ctx)
 	CTX_ENTER(ctx);
 	CU(cudaStreamSynchronize(ctx->stream));
 	CU(cudaStreamSynchronize(ctx->copy_stream));
-	return PWN_OK;
+	return check_peer_barriers(ctx);
 }
 
 extern "C" int pwn_read_frame(pwn_ctx *ctx, uint32_t *sbuf, float *zbuf, pwn_ids *ids)
@@ -868,7 +936,7 @@ extern "C" int pwn_read_frame(pwn_ctx *ctx, uint32_t *sbuf, float *zbuf, pwn_ids
 		CU(cudaMemcpyAsync(ids, ctx->d_ids, n*3*sizeof(pwn_ids), cudaMemcpyDeviceToHost, ctx->stream));
 	}
 	CU(cudaStreamSynchronize(ctx->stream));
-	return PWN_OK;
+	return check_peer_barriers(ctx);
 }
 
 extern "C" int pwn_write_frame(pwn_ctx *ctx, const uint32_t *sbuf, const float *zbuf)
@@ -883,52 +951,115 @@ extern "C" int pwn_write_frame(pwn_ctx *ctx, const uint32_t *sbuf, const float *
 	return PWN_OK;
 }
 
+// device -> host copy of rows [y0, y1) of a plane, the traced window only: the reference's trace leaves everything
+// outside [0,dimx) x [0,dimy) of the host's buffers untouched
+static int copy_rows_out(pwn_ctx *ctx, void *host, const void *dev, int dimx, int y0, int y1, cudaStream_t st)
+{
+	if(y1 <= y0) return PWN_OK;
+	const size_t pitch = (size_t)ctx->rwidth*4, off = (size_t)y0*pitch;
+	if(dimx == ctx->rwidth) CU(cudaMemcpyAsync((char *)host + off, (const char *)dev + off, (size_t)(y1 - y0)*pitch, cudaMemcpyDeviceToHost, st));
+	else CU(cudaMemcpy2DAsync((char *)host + off, pitch, (const char *)dev + off, pitch, (size_t)dimx*4, (size_t)(y1 - y0), cudaMemcpyDeviceToHost, st));
+	return PWN_OK;
+}
+
+// The frame is traced in up to PWN_SCREEN_CHUNKS row chunks so that the copies to the host run under the kernels:
+// chunk c's zbuf rows leave as soon as K1(c) is done; with the blur pass, chunk c is blurred after K1(c+1) -- its
+// gathers reach rows below it by 0.002*dimy*(z-1) (screen.h:86,100-102), which the next chunk covers unless a surface
+// is very far away; a pixel whose samples reach further still is queued and finished by k_blur_fix once the whole
+// frame is traced, and (only then) the frame is copied again.  One kernel stream, one copy stream.
+#ifndef PWN_SCREEN_CHUNKS
+#define PWN_SCREEN_CHUNKS 4
+#endif
+extern "C" int pwn_screen_chunks(pwn_ctx *ctx, int nchunks)
+{
+	if(ctx == nullptr) return fail(PWN_E_ARG, "null context");
+	if(nchunks < 0 || nchunks > 8) return fail(PWN_E_ARG, "pwn_screen_chunks: %d (0 = automatic, 1..8)", nchunks);
+	ctx->screen_chunks = nchunks;
+	return PWN_OK;
+}
+
 extern "C" int pwn_trace_screen(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags,
 	uint32_t *sbuf_host, float *zbuf_host)
 {
 	CTX_ENTER(ctx);
 	if(cam == nullptr || sbuf_host == nullptr) return fail(PWN_E_ARG, "pwn_trace_screen: null pointer");
 	if(dimx <= 0 || dimy <= 0) return fail(PWN_E_ARG, "pwn_trace_screen: bad size");
+	if(ctx->nshards != 1) return fail(PWN_E_STATE, "pwn_trace_screen on a sharded context");
 	flags &= ~PWN_F_IDS;
 	const bool blur = (flags & PWN_F_BLUR) != 0;
 	float rayb[4], rdx[4], rdy[4];
 	pwn_ray_setup(cam, dimx, dimy, rayb, rdx, rdy);
-	// K1 alone (with the blur flag it writes the pre-blur buffer and leaves the blur to this function)
-	int rc = launch_trace(ctx, ctx->fs[0], cam + 12, rayb, rdx, rdy, dimx, dimy, sec_current, flags, true, nullptr, true);
-	if(rc != PWN_OK) return rc;
-	const size_t n = (size_t)ctx->rwidth*ctx->rheight;
 	const FrameSet &f = ctx->fs[0];
-	if(!ctx->timed) CU(cudaEventRecord(ctx->ev_k1b, ctx->stream));
-	// zbuf is final when K1 ends: its copy starts then, on the copy stream, under the blur pass
-	CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k1b, 0));
-	if(zbuf_host) CU(cudaMemcpyAsync(zbuf_host, f.zbuf, n*4, cudaMemcpyDeviceToHost, ctx->copy_stream));
-	if(!blur)
-		CU(cudaMemcpyAsync(sbuf_host, f.sbuf, n*4, cudaMemcpyDeviceToHost, ctx->copy_stream));
-	else
+	const uint32_t *sb_dev = ctx->r_sbuf ? ctx->r_sbuf : f.sbuf, *tsb_dev = ctx->r_tsbuf ? ctx->r_tsbuf : f.tsbuf;
+	const float *zb_dev = ctx->r_zbuf ? ctx->r_zbuf : f.zbuf;
+	// chunks of whole 32-row bands; small frames are not worth the extra launches
+	const int nbands = (dimy + 31)/32;
+	int nchunk = PWN_SCREEN_CHUNKS;
+	if((long long)dimx*dimy < 1024ll*512ll) nchunk = 1;
+	if(ctx->screen_chunks > 0) nchunk = ctx->screen_chunks;
+	if(nchunk > nbands/2) nchunk = nbands/2 > 0 ? nbands/2 : 1;
+	if(nchunk > 8) nchunk = 8;
+	const int bpc = (nbands + nchunk - 1)/nchunk;    // bands per chunk
+	nchunk = (nbands + bpc - 1)/bpc;
+	uint32_t *defer_count = f.flags + 32;
+	if(blur && nchunk > 1) CU(cudaMemsetAsync(defer_count, 0, 4, ctx->stream));
+	auto rows_of = [&](int c, int &y0, int &y1) { y0 = c*bpc*32; y1 = (c + 1)*bpc*32; if(y1 > dimy) y1 = dimy; };
+	auto blur_chunk = [&](int c) -> int {
+		int y0, y1, ny0, ny1;
+		rows_of(c, y0, y1);
+		BlurParams B = blur_params(ctx, tsb_dev, zb_dev, const_cast<uint32_t *>(sb_dev), dimx, dimy);
+		B.y0 = y0; B.y1 = y1;
+		if(c + 1 < nchunk) { rows_of(c + 1, ny0, ny1); B.ylimit = ny1; B.defer_count = defer_count; B.defer_list = ctx->fs[1].sbuf; }
+		int rc = launch_blur(ctx, B, y1 - y0);
+		if(rc != PWN_OK) return rc;
+		CU(cudaEventRecord(ctx->ev_chunk[8 + c], ctx->stream));
+		CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[8 + c], 0));
+		return copy_rows_out(ctx, sbuf_host, sb_dev, dimx, y0, y1, ctx->copy_stream);
+	};
+	CU(cudaEventRecord(ctx->ev_k1a, ctx->stream));
+	for(int c = 0; c < nchunk; c++)
 	{
-		// K2, then the copy.  (Measured at 1080p: K2 in four row slabs, each copied while the next is
-		// blurred, gains 1% into page-locked memory -- 0.296 instead of 0.300 ms -- and loses 38% into
-		// pageable memory, where every copy is staged; the loop is kept for one slab.)
-		const int nslab = 1;
-		const int rows = ((dimy + nslab - 1)/nslab + 31) & ~31;
-		for(int k = 0, y0 = 0; y0 < dimy; k++, y0 += rows)
+		int y0, y1;
+		rows_of(c, y0, y1);
+		// K1 alone (with the blur flag it writes the pre-blur buffer and leaves the blur to this function)
+		int rc = launch_trace(ctx, f, cam + 12, rayb, rdx, rdy, dimx, dimy, sec_current, flags, false, nullptr, true, c*bpc, bpc);
+		if(rc != PWN_OK) return rc;
+		CU(cudaEventRecord(ctx->ev_chunk[c], ctx->stream));
+		CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[c], 0));
+		// zbuf rows are final when their K1 ends; without the blur pass so are the sbuf rows
+		if(!blur) { rc = copy_rows_out(ctx, sbuf_host, sb_dev, dimx, y0, y1, ctx->copy_stream); if(rc != PWN_OK) return rc; }
+		else if(c > 0) { rc = blur_chunk(c - 1); if(rc != PWN_OK) return rc; }
+		if(zbuf_host) { rc = copy_rows_out(ctx, zbuf_host, zb_dev, dimx, y0, y1, ctx->copy_stream); if(rc != PWN_OK) return rc; }
+	}
+	CU(cudaEventRecord(ctx->ev_k1b, ctx->stream));
+	ctx->timed = true;
+	ctx->h_defer[0] = 0;
+	if(blur)
+	{
+		int rc = blur_chunk(nchunk - 1);
+		if(rc != PWN_OK) return rc;
+		if(nchunk > 1)
 		{
-			const int y1 = (y0 + rows < dimy) ? y0 + rows : dimy;
-			BlurParams B = blur_params(ctx, f.tsbuf, f.zbuf, f.sbuf, dimx, dimy);
-			B.y0 = y0; B.y1 = y1;
-			rc = launch_blur(ctx, B, y1 - y0);
-			if(rc != PWN_OK) return rc;
-			CU(cudaEventRecord(ctx->ev_done[k % 3], ctx->stream));
-			CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[k % 3], 0));
-			// the last slab takes the rows below the traced window with it (the host gets the whole frame)
-			const size_t w0 = (size_t)y0*ctx->rwidth, w1 = (y1 == dimy) ? n : (size_t)y1*ctx->rwidth;
-			CU(cudaMemcpyAsync(sbuf_host + w0, f.sbuf + w0, (w1 - w0)*4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+			BlurParams B = blur_params(ctx, tsb_dev, zb_dev, const_cast<uint32_t *>(sb_dev), dimx, dimy);
+			B.defer_count = defer_count; B.defer_list = ctx->fs[1].sbuf;
+			k_blur_fix<<<296, 256, 0, ctx->stream>>>(B);
+			CU(cudaGetLastError());
+			ctx->launches++;
+			CU(cudaMemcpyAsync(ctx->h_defer, defer_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
 		}
 		CU(cudaEventRecord(ctx->ev_k2b, ctx->stream));
-		ctx->timed_blur = ctx->timed;
+		ctx->timed_blur = true;
 	}
-	CU(cudaStreamSynchronize(ctx->copy_stream));
 	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaStreamSynchronize(ctx->copy_stream));
+	if(ctx->h_defer[0] != 0)
+	{
+		// (rare: a surface so far away that its blur samples reach beyond the next chunk) the chunks went out before
+		// k_blur_fix had finished those pixels: the blurred frame goes out again
+		int rc = copy_rows_out(ctx, sbuf_host, sb_dev, dimx, 0, dimy, ctx->stream);
+		if(rc != PWN_OK) return rc;
+		CU(cudaStreamSynchronize(ctx->stream));
+	}
 	return PWN_OK;
 }
 

@@ -108,6 +108,7 @@ struct TraceParams
 	int dimx, dimy, rwidth;
 	int nshards, shard;        // 32-row bands b with b % nshards == shard
 	int nbands_local;          // bands this shard owns
+	int band0;                 // first of them this launch traces (pwn_trace_screen traces a frame in row chunks)
 	uint32_t *sbuf;            // pre-blur or final frame (BGRA8)
 	float *zbuf;
 	pwn_ids *ids;              // [rwidth*rheight][3] or null
@@ -319,7 +320,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 	const int tx = P.rowtile ? lane : (warp & 3)*8 + (lane & 7);
 	const int ty = P.rowtile ? warp : (warp >> 2)*4 + (lane >> 3);
 	const int x = blockIdx.x*32 + tx;
-	const int lrow0 = blockIdx.y*K1_ROWS;
+	const int lrow0 = (blockIdx.y + P.band0*(32/K1_ROWS))*K1_ROWS;
 	// local row -> global row through the band interleave (8 | 32: a CTA never straddles bands)
 	const int y0 = ((lrow0 >> 5)*P.nshards + P.shard)*32 + (lrow0 & 31);
 	const int y = y0 + ty;
@@ -903,14 +904,11 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 
 	if(IDS && P.opcount != nullptr)
 	{
-		unsigned long long tot = ops;
+		// (a sum over whatever lanes are here: partial warps at the frame's edges have holes in the mask, which a
+		// shuffle butterfly would mis-add; a lane's count is far below 2^32/32)
 		const unsigned m = __activemask();
-		for(int o = 16; o > 0; o >>= 1)
-		{
-			const unsigned long long v = __shfl_xor_sync(m, tot, o);
-			if(m & (1u << ((threadIdx.x & 31) ^ o))) tot += v;
-		}
-		if((threadIdx.x & 31) == (__ffs(m) - 1)) atomicAdd(P.opcount, tot);
+		const unsigned tot = __reduce_add_sync(m, ops);
+		if((threadIdx.x & 31) == (__ffs(m) - 1)) atomicAdd(P.opcount, (unsigned long long)tot);
 	}
 
 	// ---- col_ftoint (util.h:48-59): B | G<<8 | R<<16 | A<<24 ------------------------------
@@ -927,7 +925,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 	{
 		asm volatile("griddepcontrol.wait;" ::: "memory");
 		asm volatile("griddepcontrol.launch_dependents;");
-		blur_pixel(P.prev, x, y);
+		blur_pixel<false>(P.prev, x, y);
 	}
 }
 

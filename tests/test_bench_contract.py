@@ -23,6 +23,8 @@ def test_reference_arm_line():
     assert line["metric"] == "primary_mrays_per_s" and line["unit"] == "Mrays/s" and line["higher_is_better"] is True
     assert line["steps"] == 1 and line["n_gpus"] == 1 and line["value"] > 0
     assert "workload" in line["config"]
+    import bench
+    assert line["config"] == bench.headline_config(1)          # the same `config` object as our own arm prints
     cb = line["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["sample"] and cb["value"] == line["value"]
     e = line["e2e"]
@@ -39,7 +41,8 @@ def test_own_arm_line():
               "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "clocks", "e2e", "gpu_launches"):
         assert k in line, k
     assert line["metric"] == "primary_mrays_per_s" and line["steps"] == 2 and line["warmup"] >= 3 and line["n_gpus"] == 1
-    assert line["value"] > 5000 and line["gpu_launches"] >= 2 * 600
+    assert line["value"] > 5000 and line["gpu_launches"] >= 2 * 64
+    assert "configs[4]" in line["config"]["workload"] and line["config"]["resolution"] == [7680, 4320]
     r = line["roofline"]
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert k in r, k
@@ -47,6 +50,8 @@ def test_own_arm_line():
     cb = line["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
     e = line["e2e"]
-    assert 0 < e["value"] <= line["value"] * 1.05 and e["d2h_bytes_per_step"] == 600 * 1920 * 1080 * 4 and e["h2d_bytes_per_step"] > 0
+    assert 0 < e["value"] <= line["value"] * 1.05 and e["d2h_bytes_per_step"] == 64 * 7680 * 4320 * 4 and e["h2d_bytes_per_step"] > 0
     c = line["clocks"]
     assert c["sm_mhz"] and c["sm_max_mhz"] and "reasons" in c
+    sf = e["single_frame_call"]
+    assert sf["8k_maze"]["registered"]["ms_per_frame"] > 0 and sf["1080p_default_level"]["registered_with_zbuf"]["ms_per_frame"] > 0

@@ -68,6 +68,14 @@ def check_frame(tracer, oracle, cam, sec, w, h, exact_rgb=None, label=""):
     # with the host's libm restated on the device the whole frame is bit-exact, alpha byte included
     assert bad.sum() == 0, (label, int(bad.sum()))
     assert (s == so).all(), (label, int((s != so).sum()))
+    # the PRODUCTION instantiation (flags 0 -> k_trace<., false, ., false>, what the shim and the bench run): the ids
+    # build above differs from it in real code (cx/cz reconstruction when a ray leaves the grid, register allocation),
+    # so every case is traced a second time without PWN_F_IDS and must give the same frame, bit for bit
+    tracer.frame_clear()
+    tracer.trace_cam(cam, w, h, sec, 0)
+    sp, zp, _ = tracer.read_frame()
+    assert (zp.view(np.uint32) == zo.view(np.uint32)).all(), (label, "production zbuf")
+    assert (sp == so).all(), (label, "production sbuf", int((sp != so).sum()))
     return {"rgb_exact": float((d == 0).mean()), "rgb_le1": float(frac_ok), "ids_bounce_mismatch": float(bad.mean()),
             "sbuf": s, "zbuf": z, "osbuf": so, "ozbuf": zo}
 
@@ -701,3 +709,167 @@ def test_fuzz_wide_levels(tracer, oracle):
         oracle_set_level(oracle, lv)
         for k, pose in enumerate(fuzz_levels.random_poses(lv, seed, 3, dim=96)):
             check_frame(tracer, oracle, pose["cam"], float(pose["sec_current"]), 320, 192, label="wide fuzz %d/%d" % (seed, k))
+
+
+def check_poses(tracer, oracle, poses, w, h, label=""):
+    """The pose pipeline (pwn_trace_poses) against the oracle, frame by frame, blur off and on: blur off runs the
+    production k_trace<SPH, false, ., false>; blur on runs the fused k_trace<SPH, false, ., true> (trace of frame i +
+    blur of frame i-1 in one launch, chained by programmatic dependent launch) and one closing k_blur."""
+    n = len(poses)
+    tracer.frame_config(w, h)
+    want = []
+    for pz in poses:
+        so, zo, _ = oracle.trace_frame(pz["cam"], float(pz["sec_current"]), w, h)
+        want.append((so, oracle.blur(so, zo, w, h)))
+    for blur in (False, True):
+        tracer.frame_clear()      # exhausted walks leave zbuf as it was (trace.h:677): every frame set starts from zero
+        out = np.zeros((n, h, w), np.uint32)
+        sums = tracer.trace_poses(poses, w, h, api.PWN_F_BLUR if blur else 0, out=out, want_sums=True)
+        for i in range(n):
+            ref = want[i][1 if blur else 0]
+            assert (out[i] == ref).all(), (label, "blur" if blur else "plain", i, int((out[i] != ref).sum()))
+            assert int(sums[i]) == int(api.checksum_ref(ref, w, h)), (label, i)
+
+
+def test_pose_pipeline_production_kernels(tracer, oracle):
+    """k_trace<0,0,.,0>, k_trace<0,0,.,1>, k_trace<1,0,.,0> and k_trace<1,0,.,1> -- the instantiations the bench, the
+    shim and pwn_trace_poses run -- on every level family the ids build is tested on: mirror hall (deep portal
+    chains, exhausted walks), 10k-sector maze, open border (rays leave and re-enter the grid: the cx/cz
+    reconstruction exists only in these builds), fuzz levels with and without spheres, the game's 14 spheres,
+    300 spheres in one cell, 3000 on the maze"""
+    import fuzz_levels
+    hall = levels.mirror_hall()
+    cam0 = api.cam_spawn(hall)
+    hp = np.zeros(3, api.POSE_DTYPE)          # three poses: one per frame set, so that zbuf starts clean for each
+    for k, yaw in enumerate((1.5707964, 0.4, 4.6)):
+        hp["cam"][k] = api.mat4_roty(cam0, yaw)
+        hp["sec_current"][k] = 0.5 + 0.25 * k
+    last = hall.portals[16]
+    cam = np.eye(4, dtype=np.float32)
+    cam[3, :3] = (last["x1"] - 2.5, 0.5, last["z1"] + 0.5)
+    hp["cam"][2] = api.mat4_roty(cam.reshape(16), 1.5707964)      # the endless hall: exhausted walks
+    mz = levels.maze(dim=128, seed=1)
+    ob = levels.open_border()
+    op = np.zeros(4, api.POSE_DTYPE)
+    for k, (x, z, yaw) in enumerate([(4.5, 6.5, 1.6), (60.5, 62.5, 0.3), (-3.5, 2.5, 1.57), (70.5, 61.5, 4.0)]):
+        c = np.eye(4, dtype=np.float32)
+        c[3, :3] = (x, 0.5, z)
+        op["cam"][k] = api.mat4_roty(c.reshape(16), yaw)
+        op["sec_current"][k] = 0.25
+    cases = [("hall", hall, hp), ("maze", mz, levels.poses_random(mz, 5, seed=1)), ("open border", ob, op)]
+    for seed in (3, 7, 16, 31):               # 3, 7, 31: open edges; 7, 16, 31: ten random spheres
+        lv = api.level_parse(fuzz_levels.random_level_text(seed, open_edges=(seed % 4 == 3)))
+        if seed % 3 == 1:
+            fuzz_levels.random_spheres(lv, seed, 10)
+        cases.append(("fuzz %d" % seed, lv, fuzz_levels.random_poses(lv, seed, 3)))
+    g = levels.game_spheres(levels.default_level(), sec=0.3)
+    gp = np.zeros(3, api.POSE_DTYPE)
+    for k, yaw in enumerate((0.0, 0.35, -0.4)):
+        gp["cam"][k] = api.mat4_roty(api.cam_spawn(g), yaw)
+        gp["sec_current"][k] = 0.3
+    cases.append(("14 spheres", g, gp))
+    crowd = levels.default_level()
+    rnd = np.random.default_rng(12)
+    for _ in range(300):
+        crowd.sphere_add(np.float32(0.02 + 0.03 * rnd.random()), np.float32(0.3),
+                         np.float32(crowd.sx + 0.1 + 0.8 * rnd.random()), np.float32(0.1 + 0.8 * rnd.random()),
+                         np.float32(crowd.sz + 2 + 0.1 + 0.8 * rnd.random()),
+                         np.float32(rnd.random()), np.float32(rnd.random()), np.float32(rnd.random()))
+    cases.append(("300 spheres in a cell", crowd, gp[:2]))
+    ms = levels.scatter_spheres(levels.maze(dim=128, seed=1), 3000, seed=2)
+    cases.append(("maze 3000 spheres", ms, levels.poses_random(ms, 3, seed=3)))
+    try:
+        for name, lv, poses in cases:
+            tracer.level_upload(lv)
+            tracer.level_prepare_render(lv)
+            oracle_set_level(oracle, lv)
+            check_poses(tracer, oracle, poses, 320, 192, label=name)
+    finally:
+        lv = levels.default_level()
+        tracer.level_upload(lv)
+        tracer.level_prepare_render(lv)
+
+
+@pytest.mark.parametrize("config", ["C3 hall 1080p", "C4 maze 4K", "C5 maze 8K"])
+def test_baseline_configs_at_full_size_vs_oracle(tracer, oracle, config):
+    """BASELINE configs[2..4] at their stated sizes, one frame each, the production kernels against the oracle:
+    sbuf and zbuf of the plain frame bit for bit, the blurred frame (single-frame path and the pose pipeline) by
+    checksum and bit for bit"""
+    if config.startswith("C3"):
+        lv = levels.mirror_hall()
+        (w, h) = (1920, 1080)
+        poses = np.zeros(2, api.POSE_DTYPE)
+        for k in range(2):
+            poses["cam"][k] = api.mat4_roty(api.cam_spawn(lv), 1.5707964 + 0.4 * k)
+            poses["sec_current"][k] = 0.25 * k
+    else:
+        lv = levels.maze(dim=128, seed=1)
+        (w, h) = (3840, 2160) if config.startswith("C4") else (7680, 4320)
+        poses = levels.poses_random(lv, 16, seed=1)[[3, 10]].copy() if config.startswith("C4") else levels.poses_random(lv, 64, seed=9)[[0, 33]].copy()
+    tracer.level_upload(lv)
+    tracer.level_prepare_render(lv)
+    oracle_set_level(oracle, lv)
+    tracer.frame_config(w, h)
+    tracer.shard_config(1, 0)
+    tracer.frame_clear()
+    want = []
+    for pz in poses:
+        so, zo, _ = oracle.trace_frame(pz["cam"], float(pz["sec_current"]), w, h)
+        want.append((so, zo, oracle.blur(so, zo, w, h)))
+    pz = poses[0]
+    tracer.trace_cam(pz["cam"], w, h, float(pz["sec_current"]), 0)
+    s, z, _ = tracer.read_frame()
+    assert (z.view(np.uint32) == want[0][1].view(np.uint32)).all(), config
+    assert (s == want[0][0]).all(), (config, int((s != want[0][0]).sum()))
+    tracer.trace_cam(pz["cam"], w, h, float(pz["sec_current"]), api.PWN_F_BLUR)
+    sb, _, _ = tracer.read_frame(want_z=False)
+    assert (sb == want[0][2]).all(), (config, "blur", int((sb != want[0][2]).sum()))
+    tracer.frame_clear()
+    sums = tracer.trace_poses(poses, w, h, api.PWN_F_BLUR, want_sums=True)
+    for i in range(len(poses)):
+        assert int(sums[i]) == int(api.checksum_ref(want[i][2], w, h)), (config, "pose pipeline", i)
+    sums = tracer.trace_poses(poses, w, h, 0, want_sums=True)
+    for i in range(len(poses)):
+        assert int(sums[i]) == int(api.checksum_ref(want[i][0], w, h)), (config, "pose pipeline, plain", i)
+    tracer.frame_config(64, 64)          # release the 8K frame sets
+
+
+def test_trace_screen_chunked_pipeline(tracer, oracle):
+    """pwn_trace_screen traces and blurs a frame in row chunks with the copies to the host under the kernels.  Every
+    chunk count gives the frame of the unchunked call, also when blur samples reach beyond the next chunk (far
+    surfaces of the endless hall: those pixels go through k_blur_fix and the frame is copied again), only the traced
+    window of the host buffers is written, zbuf comes back too."""
+    lv = levels.mirror_hall()
+    tracer.level_upload(lv)
+    tracer.level_prepare_render(lv)
+    oracle_set_level(oracle, lv)
+    last = lv.portals[16]
+    cam = np.eye(4, dtype=np.float32)
+    cam[3, :3] = (last["x1"] - 2.5, 0.5, last["z1"] + 0.5)
+    cam_end = api.mat4_roty(cam.reshape(16), 1.5707964)
+    cam_hall = api.mat4_roty(api.cam_spawn(lv), 1.5707964)
+    try:
+        for (cam, sec, rw, rh, w, h) in [(cam_hall, 0.5, 640, 512, 640, 512), (cam_end, 0.0, 640, 512, 640, 512),
+                                         (cam_hall, 0.25, 704, 520, 650, 500), (cam_hall, 0.25, 1920, 1080, 1920, 1080)]:
+            tracer.frame_config(rw, rh)
+            so, zo, _ = oracle.trace_frame(cam, sec, w, h, rwidth=rw)
+            bo = oracle.blur(so, zo, w, h, rwidth=rw)
+            far = int((zo > 64.0).sum())
+            for blur in (False, True):
+                for nch in (1, 2, 8, 0):
+                    tracer.screen_chunks(nch)
+                    tracer.frame_clear()
+                    sb = np.full((rh, rw), 0xDEADBEEF, np.uint32)
+                    zb = np.full((rh, rw), -7.0, np.float32)
+                    tracer.trace_screen_centred(lv, 0, 0, w, h, cam, sec, blur=blur, sbuf=sb, zbuf=zb)
+                    want = bo if blur else so
+                    assert (sb[:h, :w] == want[:, :w]).all(), (w, h, blur, nch, far, int((sb[:h, :w] != want[:, :w]).sum()))
+                    assert (zb[:h, :w].view(np.uint32) == zo[:, :w].view(np.uint32)).all(), (w, h, blur, nch)
+                    # nothing outside the traced window is touched (screen.h:14-15: the trace indexes from (0,0))
+                    assert (sb[h:] == 0xDEADBEEF).all() and (sb[:, w:] == 0xDEADBEEF).all()
+                    assert (zb[h:] == -7.0).all() and (zb[:, w:] == -7.0).all()
+            print("chunked %dx%d: %d pixels farther than 64 units" % (w, h, far))
+    finally:
+        tracer.screen_chunks(0)
+    with pytest.raises(api.PwnError):
+        tracer.screen_chunks(9)
