@@ -15,6 +15,9 @@ Variants (all from ref_harness.c):
   libref_wide.so       build-time WIDENED copy (LV_DIM x LV_DIM int cells, PM_MAX
   libref_wide_ids.so   portals) for the levels that exceed 64x64 / 26 letters
   libref_strict.so     same sources, -O2 and no -ffast-math (diagnostic)
+  libref_tick.so       main.c:188-379 -- one game tick of player motion (yaw, move, wall push-back,
+  libref_tick_strict.so  gravity, raised floors, portal traversal) -- extracted at build time into the
+                       body of ref_player_tick(); shipped flags and strict flags
   libref_shim.so       the reference host (defs.h util.h level.h) with the PRODUCT's drop-in
   libref_shim_noblur.so  pwn_screen.h in place of trace.h + screen.h, linked to libpwntrace.so
 
@@ -136,6 +139,24 @@ def widen(files):
     return out
 
 
+def extract_tick():
+    """main.c:188-379: the part of mainloop()'s for(;;) body between the event switch and the end of the loop.
+    It reads and writes only `cam`, `gravity`, the eight key flags, `tdiff` and `lv` (get_cell,
+    celltype_is_solid, lv->pmap) -- no SDL, no Lua -- so it compiles as the body of a function that declares
+    those names (ref_harness.c, -DREF_TICK)."""
+    with open(os.path.join(REF, "main.c"), "r", newline="") as f:
+        m = f.read().split("\n")
+    _expect(m, 186, "}")
+    _expect(m, 188, "mat4_roty(&cam, tdiff*3.0f*(k_turnleft - k_turnright));")
+    _expect(m, 196, "int cx1 = (int)cam.v.w.v.x;")
+    _expect(m, 267, "cam.v.w.m = _mm_add_ps(cam.v.w.m, gravity.m);")
+    _expect(m, 296, 'printf("TRAVERSE %c\\n", c2);')
+    _expect(m, 377, "cam.v.z.v.z = rvzz;")
+    _expect(m, 379, "}")
+    _expect(m, 380, "}")
+    return m[187:379]
+
+
 def cc(out_name, inc_dirs, defines, cflags, libs=()):
     cmd = ["gcc"] + cflags + ["-shared", "-fPIC"]
     for i in inc_dirs:
@@ -146,7 +167,7 @@ def cc(out_name, inc_dirs, defines, cflags, libs=()):
 
 
 VARIANTS = ["libref.so", "libref_noblur.so", "libref_ids.so", "libref_wide.so",
-            "libref_wide_ids.so", "libref_strict.so"]
+            "libref_wide_ids.so", "libref_strict.so", "libref_tick.so"]
 
 
 def main():
@@ -179,6 +200,13 @@ def main():
             shim_lib = ["-L" + pkg, "-lpwntrace", "-Wl,-rpath,$ORIGIN/../../pwnfps_b200"]
             cc("libref_shim.so", shim_inc, ["REF_SHIM"], REF_CFLAGS, shim_lib)
             cc("libref_shim_noblur.so", shim_inc, ["REF_SHIM", "REF_NO_BLUR"], REF_CFLAGS, shim_lib)
+
+        # one game tick of the player (main.c:188-379) as a function
+        d_tick = os.path.join(tmp, "tick")
+        os.makedirs(d_tick)
+        _write(d_tick, "tick_body.inc", extract_tick())
+        cc("libref_tick.so", [d_tick, REF], ["REF_NO_BLUR", "REF_TICK"], REF_CFLAGS)
+        cc("libref_tick_strict.so", [d_tick, REF], ["REF_NO_BLUR", "REF_TICK"], STRICT_CFLAGS)
 
         d_ids = os.path.join(tmp, "ids")
         os.makedirs(d_ids)

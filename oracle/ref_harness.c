@@ -22,6 +22,8 @@
  *                      trace.h + screen.h: the reference host driving libpwntrace.so
  *   -DREF_WIDE         the including TU is the build-time *widened* copy
  *                      (LV_DIM x LV_DIM grid, PM_MAX portals)
+ *   -DREF_TICK         also builds ref_player_tick(): main.c:188-379, extracted at build time by
+ *                      oracle/make_ref.py into tick_body.inc (temporary directory)
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load the resulting library.
@@ -404,3 +406,34 @@ void ref_libm(const float *in, float *s, float *c, float *e, size_t n)
 	size_t i;
 	for(i = 0; i < n; i++) { s[i] = sinf(in[i]); c[i] = cosf(in[i]); e[i] = expf(in[i]); }
 }
+
+#ifdef REF_TICK
+/*
+ * One game tick of player motion: the reference's own statements, main.c:188-379 (yaw, velocity, move,
+ * wall push-back, gravity, raised-floor steps, portal traversal), extracted at build time into
+ * tick_body.inc.  The block reads and writes only the names declared here -- the locals of mainloop()
+ * it uses (main.c:46-48,70-77), with `lv` the level loaded into this library.
+ *   cam16     mat4 cam, rows x y z w (in/out)        gravity4  vec4 gravity (in/out)
+ *   keys      k_turnleft, k_turnright, k_turnup, k_turndown, k_moveforward, k_moveback, k_moveleft, k_moveright
+ */
+int ref_player_tick(float *cam16, float *gravity4, const int *keys, float tdiff)
+{
+	mat4 cam;
+	vec4 gravity;
+	level *lv = lvroot;
+	if(lv == NULL) return -1;
+	int k_turnleft = keys[0], k_turnright = keys[1], k_turnup = keys[2], k_turndown = keys[3];
+	int k_moveforward = keys[4], k_moveback = keys[5], k_moveleft = keys[6], k_moveright = keys[7];
+	(void)k_turnup; (void)k_turndown;
+	memcpy(&cam, cam16, sizeof(cam));
+	memcpy(&gravity, gravity4, sizeof(gravity));
+#define printf(...) ((void)0)      /* the block announces every traversal on stdout (main.c:297) */
+	{
+#include "tick_body.inc"
+	}
+#undef printf
+	memcpy(cam16, &cam, sizeof(cam));
+	memcpy(gravity4, &gravity, sizeof(gravity));
+	return 0;
+}
+#endif

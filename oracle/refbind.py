@@ -57,6 +57,8 @@ class Ref:
         lib.ref_rcpps.argtypes = [_f32p, _f32p, C.c_size_t]
         lib.ref_rsqrtps.argtypes = [_f32p, _f32p, C.c_size_t]
         lib.ref_libm.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_size_t]
+        if hasattr(lib, "ref_player_tick"):
+            lib.ref_player_tick.argtypes = [_f32p, _f32p, _i32p, C.c_float]
         if hasattr(lib, "ref_screen_upscale"):
             lib.ref_screen_upscale.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         self.flags = lib.ref_flags()
@@ -120,6 +122,11 @@ class Ref:
         if t < 0:
             raise RuntimeError("ref_time_frames failed (%g)" % t)
         return t
+
+    def player_tick(self, cam16, gravity4, keys8, tdiff):
+        """main.c:188-379 on (cam, gravity) in place; keys8 = turnleft turnright turnup turndown forward back left right"""
+        if self.lib.ref_player_tick(cam16, gravity4, np.ascontiguousarray(keys8, dtype=np.int32), float(tdiff)) != 0:
+            raise RuntimeError("ref_player_tick: no level loaded")
 
     def max_threads(self):
         return self.lib.ref_max_threads()

@@ -165,6 +165,8 @@ def host():
     H.pwn_cam_spawn.restype = None
     H.pwn_mat4_roty.argtypes = [C.c_void_p, C.c_float]
     H.pwn_mat4_roty.restype = None
+    H.pwn_player_tick.argtypes = [C.c_void_p, C.POINTER(_CLevel), C.c_void_p, C.c_float]
+    H.pwn_player_tick.restype = None
     H.pwn_flythrough.argtypes = [C.POINTER(_CLevel), C.c_int, C.c_void_p]
     H.pwn_flythrough.restype = C.c_int
     H.pwn_save_ppm.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -353,6 +355,36 @@ def flythrough(lv, nframes):
     if rc != 0:
         raise PwnError(rc, "flythrough failed")
     return poses
+
+
+class Player:
+    """pwn_player (host/pwn_camera.h): `cam` (16 floats, rows x y z w) and `gravity` (4 floats) of main.c:47-48, and
+    one game tick of player motion (main.c:188-379) per tick() call."""
+
+    def __init__(self, lv):
+        self.state = np.zeros(20, np.float32)
+        self._clv = lv._to_c()
+        host().pwn_cam_spawn(lv.sx, lv.sz, self.state.ctypes.data)
+
+    @property
+    def cam(self):
+        return self.state[:16]
+
+    @property
+    def gravity(self):
+        return self.state[16:]
+
+    def tick(self, keys6, tdiff):
+        """keys6 = turnleft turnright moveforward moveback moveleft moveright (pwn_keys)"""
+        k = np.ascontiguousarray(keys6, dtype=np.int32)
+        assert k.size == 6
+        host().pwn_player_tick(self.state.ctypes.data, self._clv, k.ctypes.data, float(tdiff))
+
+    def __del__(self):
+        try:
+            host().pwn_level_free(self._clv)
+        except Exception:
+            pass
 
 
 class Game:

@@ -1,8 +1,9 @@
 /*
  * pwn_camera.c -- scripted camera for the headless harness (see pwn_camera.h).
- * Player motion restates main.c:188-379: yaw 3 rad/s, move 5 units/s, wall push-back
- * with PLAYER_BBOX 0.2 (defs.h:7), gravity, raised-floor steps and portal traversal
- * with the same quarter-turn maths as the ray version (trace.h:578-617).
+ * Player motion follows main.c:188-379 (yaw 3 rad/s, move 5 units/s, wall push-back with
+ * PLAYER_BBOX 0.2, defs.h:7, gravity, raised-floor steps, portal traversal), written around a
+ * height-window table for the cells and a crossing record for the portals, and pinned bit for bit
+ * to the reference's own block extracted at build time (oracle/make_ref.py -> libref_tick*.so).
  */
 #include <math.h>
 #include <string.h>
@@ -32,20 +33,28 @@ void pwn_mat4_roty(float cam[16], float ang)
 	cam[10] = vc*vzz - vs*vzx;
 }
 
-/* util.h:112-126 */
-static int celltype_is_solid(const pwn_level *lv, int32_t c, int32_t oldcell, float y)
+/*
+ * Can the player stand in a cell of code `c`, coming from a cell of code `from`, at height y?
+ * (what celltype_is_solid answers, util.h:112-126, as a table of height windows: a cell is open for
+ * lo <= y < hi)
+ */
+static int cell_blocks(const pwn_level *lv, int32_t c, int32_t from, float y)
 {
-	if(c == '"' && (oldcell == '#' || oldcell == '&')) return y < 1.0f || y >= 2.0f;
-	if(c == '#' || c == '&') return y < 0.0f || y >= 2.0f;
-	if(c == ';' || c == '$' || c == '"') return y < 0.0f || y >= 1.0f;
-	if(c == '>' || c == '<' || c == '^' || c == ',') return y < 0.0f || y >= 1.0f;
-	if(PWN_IS_PORTAL(c))
+	float lo = 0.0f, hi;
+	switch(c)
 	{
-		int pi = PWN_PORTAL_INDEX(c);
-		if(pi < 0 || pi >= lv->nportals) return 1;
-		return lv->portals[pi].x2 != -1 ? 0 : 1;
+		case '#': case '&': hi = 2.0f; break;
+		case '"': hi = 1.0f; if(from == '#' || from == '&') { lo = 1.0f; hi = 2.0f; } break;
+		case ';': case '$': case '>': case '<': case '^': case ',': hi = 1.0f; break;
+		default:
+			if(PWN_IS_PORTAL(c))
+			{
+				const int pi = PWN_PORTAL_INDEX(c);
+				return !(pi >= 0 && pi < lv->nportals && lv->portals[pi].x2 != -1);   /* a paired portal is open at any height */
+			}
+			return 1;
 	}
-	return 1;
+	return y < lo || y >= hi;
 }
 
 void pwn_player_init(pwn_player *pl, const pwn_level *lv)
@@ -54,114 +63,120 @@ void pwn_player_init(pwn_player *pl, const pwn_level *lv)
 	pwn_cam_spawn(lv->sx, lv->sz, pl->cam);
 }
 
+/* the far side of a portal as the player crosses it: which cell he comes out of, how far he is moved, and by how
+ * many quarter turns he and his view are rotated about that cell's centre (main.c:301-326) */
+typedef struct crossing
+{
+	int ok;            /* the cell entered is one of the pair's two ends */
+	int shiftx, shiftz;
+	float cx, cz;      /* centre of the cell on the far side */
+	int quarter;       /* 0..3 */
+} crossing;
+
+static crossing portal_crossing(const pwn_portal *pm, int x, int z)
+{
+	crossing k;
+	memset(&k, 0, sizeof(k));
+	if(pm->x2 == -1) return k;
+	const int at1 = (pm->x1 == x && pm->z1 == z), at2 = (pm->x2 == x && pm->z2 == z);
+	if(!at1 && !at2) return k;
+	const int dir = at1 ? 1 : -1;            /* end 1 -> end 2 or back */
+	k.ok = 1;
+	k.shiftx = dir*(pm->x2 - pm->x1);
+	k.shiftz = dir*(pm->z2 - pm->z1);
+	k.cx = (float)(at1 ? pm->x2 : pm->x1) + 0.5f;
+	k.cz = (float)(at1 ? pm->z2 : pm->z1) + 0.5f;
+	k.quarter = (-dir*pm->rot12) & 3;
+	return k;
+}
+
+/* (x, z) turned by `quarter` quarter turns: exact, only signs and an exchange */
+static void turn_vec(int quarter, float *x, float *z)
+{
+	const float ox = *x, oz = *z;
+	switch(quarter)
+	{
+		case 1: *x = oz; *z = -ox; break;
+		case 2: *x = -ox; *z = -oz; break;
+		case 3: *x = -oz; *z = ox; break;
+		default: break;
+	}
+}
+
+/*
+ * One tick of the player (main.c:188-379).  Order of events as in the reference: yaw, move by the view's z and x
+ * axes, push back out of walls, fall, step onto / off raised floors, walk through portals.  Every float
+ * expression keeps the reference's operand order -- the tick is compared bit for bit with the reference's own
+ * block (oracle/_ref/libref_tick_strict.so, tests/test_level.py).
+ */
 void pwn_player_tick(pwn_player *pl, const pwn_level *lv, const pwn_keys *k, float tdiff)
 {
-	float *cam = pl->cam, *w = pl->cam + 12;
+	float *cam = pl->cam, *pos = pl->cam + 12;
+	const float *axx = cam, *axz = cam + 8;      /* view x and z axes */
 	int i;
 
-	pwn_mat4_roty(cam, tdiff*3.0f*(k->turnleft - k->turnright));   /* main.c:188 */
+	pwn_mat4_roty(cam, tdiff*3.0f*(k->turnleft - k->turnright));
 
-	int cx1 = (int)w[0], cz1 = (int)w[2];
+	const int ox = (int)pos[0], oz = (int)pos[2];       /* the cell the tick starts in */
+	const int32_t here = pwn_level_get_cell(lv, ox, oz);
 
-	float vel[4];
-	float fwd = tdiff*5.0f*(k->moveforward - k->moveback);
-	float side = tdiff*5.0f*(k->moveleft - k->moveright);
-	for(i = 0; i < 4; i++) vel[i] = cam[8+i]*fwd + cam[0+i]*side;
-	for(i = 0; i < 4; i++) w[i] += vel[i];
+	/* move: all four lanes, as the SSE original does */
+	const float ahead = tdiff*5.0f*(k->moveforward - k->moveback), aside = tdiff*5.0f*(k->moveleft - k->moveright);
+	float step[4];
+	for(i = 0; i < 4; i++) step[i] = axz[i]*ahead + axx[i]*aside;
+	for(i = 0; i < 4; i++) pos[i] += step[i];
 
-	float px1 = w[0], py1 = w[1], pz1 = w[2];
-
-	/* push-backs, main.c:215-264 */
-	int gx1 = (vel[0] < 0.0f ? -1 : 1);
-	int gz1 = (vel[2] < 0.0f ? -1 : 1);
-	float bx1 = px1 + gx1*PLAYER_BBOX;
-	float bz1 = pz1 + gz1*PLAYER_BBOX;
-	int bcx = (int)bx1, bcz = (int)bz1;
-	int32_t oldcell = pwn_level_get_cell(lv, cx1, cz1);
-
-	if(cx1 != bcx && cz1 != bcz)
+	/* push-back: the leading corner of the bounding box decides which walls are hit */
 	{
-		int solx = celltype_is_solid(lv, pwn_level_get_cell(lv, bcx, cz1), oldcell, py1);
-		int solz = celltype_is_solid(lv, pwn_level_get_cell(lv, cx1, bcz), oldcell, py1);
-		int solc = celltype_is_solid(lv, pwn_level_get_cell(lv, bcx, bcz), oldcell, py1);
-		if(solx && solz)
+		const int dx = (step[0] < 0.0f ? -1 : 1), dz = (step[2] < 0.0f ? -1 : 1);
+		const float y = pos[1];
+		const int nx = (int)(pos[0] + dx*PLAYER_BBOX), nz = (int)(pos[2] + dz*PLAYER_BBOX);
+		const int leftx = (nx != ox), leftz = (nz != oz);
+		int hitx = 0, hitz = 0;
+		if(leftx && leftz)
 		{
-			w[0] = cx1 + 0.5f + (0.5f-PLAYER_BBOX)*gx1;
-			w[2] = cz1 + 0.5f + (0.5f-PLAYER_BBOX)*gz1;
+			const int wx = cell_blocks(lv, pwn_level_get_cell(lv, nx, oz), here, y);
+			const int wz = cell_blocks(lv, pwn_level_get_cell(lv, ox, nz), here, y);
+			const int wc = cell_blocks(lv, pwn_level_get_cell(lv, nx, nz), here, y);
+			hitx = wx;
+			hitz = wz || (!wx && wc);      /* a bare corner pushes back along z */
 		}
-		else if(solx) w[0] = cx1 + 0.5f + (0.5f-PLAYER_BBOX)*gx1;
-		else if(solz) w[2] = cz1 + 0.5f + (0.5f-PLAYER_BBOX)*gz1;
-		else if(solc) w[2] = cz1 + 0.5f + (0.5f-PLAYER_BBOX)*gz1;
-	}
-	else if(cx1 != bcx)
-	{
-		if(celltype_is_solid(lv, pwn_level_get_cell(lv, bcx, bcz), oldcell, py1))
-			w[0] = cx1 + 0.5f + (0.5f-PLAYER_BBOX)*gx1;
-	}
-	else if(cz1 != bcz)
-	{
-		if(celltype_is_solid(lv, pwn_level_get_cell(lv, bcx, bcz), oldcell, py1))
-			w[2] = cz1 + 0.5f + (0.5f-PLAYER_BBOX)*gz1;
+		else if(leftx) hitx = cell_blocks(lv, pwn_level_get_cell(lv, nx, nz), here, y);
+		else if(leftz) hitz = cell_blocks(lv, pwn_level_get_cell(lv, nx, nz), here, y);
+		if(hitx) pos[0] = ox + 0.5f + (0.5f-PLAYER_BBOX)*dx;
+		if(hitz) pos[2] = oz + 0.5f + (0.5f-PLAYER_BBOX)*dz;
 	}
 
-	/* gravity, main.c:266-274 */
-	for(i = 0; i < 4; i++) w[i] += pl->gravity[i];
+	/* fall */
+	for(i = 0; i < 4; i++) pos[i] += pl->gravity[i];
 	pl->gravity[1] -= 3.0f*tdiff*tdiff;
-	if(w[1] < 0.4f) { w[1] = 0.4f; pl->gravity[1] = 0.0f; }
+	if(pos[1] < 0.4f) { pos[1] = 0.4f; pl->gravity[1] = 0.0f; }
 
-	/* cell change, main.c:276-379 */
-	int cx2 = (int)w[0], cz2 = (int)w[2];
-	if(cx1 != cx2 || cz1 != cz2)
+	/* a new cell: raised floors and portals */
+	const int tx = (int)pos[0], tz = (int)pos[2];
+	if(tx == ox && tz == oz) return;
+	const int32_t there = pwn_level_get_cell(lv, tx, tz);
+	const int two_here = (here == '#' || here == '&'), two_there = (there == '#' || there == '&');
+	if(two_here && there == '"') pos[1] -= 1.0f;
+	else if(here == '"' && two_there) pos[1] += 1.0f;
+	else if(PWN_IS_PORTAL(there) && PWN_PORTAL_INDEX(there) < lv->nportals)
 	{
-		int32_t c1 = pwn_level_get_cell(lv, cx1, cz1);
-		int32_t c2 = pwn_level_get_cell(lv, cx2, cz2);
-		if((c1 == '#' || c1 == '&') && c2 == '"') w[1] -= 1.0f;
-		else if(c1 == '"' && (c2 == '#' || c2 == '&')) w[1] += 1.0f;
-		else if(PWN_IS_PORTAL(c2) && PWN_PORTAL_INDEX(c2) < lv->nportals)
+		const crossing c = portal_crossing(&lv->portals[PWN_PORTAL_INDEX(there)], tx, tz);
+		if(!c.ok) return;                  /* unpaired, or a third cell with the letter: nothing happens */
+		float x = pos[0], z = pos[2];
+		x += (tx - ox) + c.shiftx;         /* one cell further, then across */
+		z += (tz - oz) + c.shiftz;
+		/* about the centre of the far cell; s = +1 / -1 for one / three quarter turns (a product with +-1 is exact) */
+		if(c.quarter == 2) { x = c.cx*2.0f - x; z = c.cz*2.0f - z; }
+		else if(c.quarter != 0)
 		{
-			const pwn_portal *pm = &lv->portals[PWN_PORTAL_INDEX(c2)];
-			int rot = 0;
-			float rx = w[0], rz = w[2];
-			float rcx = cx2, rcz = cz2;
-			float rvxx = cam[0], rvxz = cam[2], rvzx = cam[8], rvzz = cam[10];
-			if(pm->x2 == -1) { }
-			else if(pm->x1 == cx2 && pm->z1 == cz2)
-			{
-				rx += (cx2-cx1) + (pm->x2-pm->x1);
-				rz += (cz2-cz1) + (pm->z2-pm->z1);
-				rcx = pm->x2; rcz = pm->z2;
-				rot = (-pm->rot12) & 3;
-			}
-			else if(pm->x2 == cx2 && pm->z2 == cz2)
-			{
-				rx += (cx2-cx1) - (pm->x2-pm->x1);
-				rz += (cz2-cz1) - (pm->z2-pm->z1);
-				rcx = pm->x1; rcz = pm->z1;
-				rot = pm->rot12 & 3;
-			}
-			float trx = rx, trz = rz, txx = rvxx, txz = rvxz, tzx = rvzx, tzz = rvzz;
-			switch(rot)
-			{
-				case 1:
-					rx = (rcx + 0.5f) + (trz-(rcz + 0.5f));
-					rz = (rcz + 0.5f) - (trx-(rcx + 0.5f));
-					rvxx = txz; rvxz = -txx; rvzx = tzz; rvzz = -tzx;
-					break;
-				case 2:
-					rx = (rcx + 0.5f)*2.0f - rx;
-					rz = (rcz + 0.5f)*2.0f - rz;
-					rvxx = -txx; rvxz = -txz; rvzx = -tzx; rvzz = -tzz;
-					break;
-				case 3:
-					rx = (rcx + 0.5f) - (trz-(rcz + 0.5f));
-					rz = (rcz + 0.5f) + (trx-(rcx + 0.5f));
-					rvxx = -txz; rvxz = txx; rvzx = -tzz; rvzz = tzx;
-					break;
-				default: break;
-			}
-			w[0] = rx; w[2] = rz;
-			cam[0] = rvxx; cam[2] = rvxz; cam[8] = rvzx; cam[10] = rvzz;
+			const float s = (c.quarter == 1 ? 1.0f : -1.0f), fx = x, fz = z;
+			x = c.cx + s*(fz - c.cz);
+			z = c.cz - s*(fx - c.cx);
 		}
+		pos[0] = x; pos[2] = z;
+		turn_vec(c.quarter, &cam[0], &cam[2]);
+		turn_vec(c.quarter, &cam[8], &cam[10]);
 	}
 }
 

@@ -46,11 +46,20 @@ def test_device_libm_is_the_hosts_glibc(tracer, oracle):
 
 
 def check_frame(tracer, oracle, cam, sec, w, h, exact_rgb=None, label=""):
+    so, zo, io = oracle.trace_frame(cam, sec, w, h, want_ids=True)
     tracer.frame_config(w, h, want_ids=True)
+    # the PRODUCTION instantiation first (flags 0 -> k_trace<., false, ., false>, what the shim and the bench run): the
+    # ids build below differs from it in real code (cx/cz reconstruction when a ray leaves the grid, register
+    # allocation), so every case is traced without PWN_F_IDS too and must give the same frame, bit for bit
+    tracer.frame_clear()
+    tracer.trace_cam(cam, w, h, sec, 0)
+    sp, zp, _ = tracer.read_frame()
+    assert (zp.view(np.uint32) == zo.view(np.uint32)).all(), (label, "production zbuf")
+    assert (sp == so).all(), (label, "production sbuf", int((sp != so).sum()))
+    # then the ids build (its records stay in the ids buffer for the caller)
     tracer.frame_clear()
     tracer.trace_cam(cam, w, h, sec, api.PWN_F_IDS)
     s, z, ids = tracer.read_frame(want_ids=True)
-    so, zo, io = oracle.trace_frame(cam, sec, w, h, want_ids=True)
     # primary segment: bit-exact
     assert (z.view(np.uint32) == zo.view(np.uint32)).all(), label
     for f in IDF:
@@ -68,14 +77,6 @@ def check_frame(tracer, oracle, cam, sec, w, h, exact_rgb=None, label=""):
     # with the host's libm restated on the device the whole frame is bit-exact, alpha byte included
     assert bad.sum() == 0, (label, int(bad.sum()))
     assert (s == so).all(), (label, int((s != so).sum()))
-    # the PRODUCTION instantiation (flags 0 -> k_trace<., false, ., false>, what the shim and the bench run): the ids
-    # build above differs from it in real code (cx/cz reconstruction when a ray leaves the grid, register allocation),
-    # so every case is traced a second time without PWN_F_IDS and must give the same frame, bit for bit
-    tracer.frame_clear()
-    tracer.trace_cam(cam, w, h, sec, 0)
-    sp, zp, _ = tracer.read_frame()
-    assert (zp.view(np.uint32) == zo.view(np.uint32)).all(), (label, "production zbuf")
-    assert (sp == so).all(), (label, "production sbuf", int((sp != so).sum()))
     return {"rgb_exact": float((d == 0).mean()), "rgb_le1": float(frac_ok), "ids_bounce_mismatch": float(bad.mean()),
             "sbuf": s, "zbuf": z, "osbuf": so, "ozbuf": zo}
 

@@ -200,3 +200,208 @@ def test_extended_text_format(tmp_path):
     assert lv2.cells[1, 13] == 0x100 + 27
     with pytest.raises(api.PwnError):
         api.level_parse(b"!pwnlv 10 10 30\n..@..\n@ 5 2 0\n")      # id < 26 must be written as a letter
+
+
+def _tick_pin(lv_text_or_level, refs, variant, nticks, seed, tdiffs, key_every=7):
+    """host/pwn_camera.c's tick against the reference's own block (main.c:188-379, extracted at build time into
+    oracle/_ref/libref_tick*.so): same keys, same tdiff, cam and gravity compared bit for bit after every tick.
+    Returns the number of ticks that differed (after a difference both sides continue from the reference's state)."""
+    import tempfile
+    ref = refs(variant)
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "level.txt")
+        if isinstance(lv_text_or_level, (bytes, str)):
+            txt = lv_text_or_level if isinstance(lv_text_or_level, bytes) else lv_text_or_level.encode("latin-1")
+            open(p, "wb").write(txt)
+            lv = api.level_parse(txt)
+        else:
+            lv = lv_text_or_level
+            lv.save_txt(p)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)          # level_load prints its portal table
+        try:
+            ref.level_load(p)
+        finally:
+            os.dup2(saved, 1)
+            os.close(devnull)
+            os.close(saved)
+    rng = np.random.default_rng(seed)
+    pl = api.Player(lv)
+    cam, grav = pl.cam.copy(), pl.gravity.copy()
+    keys = np.zeros(6, np.int32)
+    bad = crossed = 0
+    for t in range(nticks):
+        if t % key_every == 0:
+            keys = (rng.random(6) < 0.45).astype(np.int32)
+        td = tdiffs[t % len(tdiffs)]
+        before = cam[[12, 14]].copy()
+        pl.tick(keys, td)
+        ref.player_tick(cam, grav, np.array([keys[0], keys[1], 0, 0, keys[2], keys[3], keys[4], keys[5]], np.int32), td)
+        crossed += int(np.abs(cam[[12, 14]] - before).max() > 1.5)
+        if not (np.array_equal(cam.view(np.uint32), pl.cam.view(np.uint32)) and np.array_equal(grav.view(np.uint32), pl.gravity.view(np.uint32))):
+            bad += 1
+            pl.state[:16] = cam
+            pl.state[16:] = grav
+    return bad, crossed
+
+
+def test_player_tick_pinned_to_the_reference_block(refs, default_level):
+    """the product's player tick == main.c:188-379 compiled from the reference (strict flags) bit for
+    bit -- the 600-tick bench script, 20 000 random-key ticks on the default level (wall slides, raised floors,
+    all its portals), and 1000 random key sequences on the fuzz levels (every cell class next to every other,
+    third-occurrence and unpaired portal letters, open grid edges).  Against the shipped -ffast-math build of the
+    same block the tick may differ where gcc's fast-math code generation does (counted, as for the trace)."""
+    from oracle import refbind
+    import fuzz_levels
+    if not refbind.available("libref_tick_strict.so"):
+        pytest.skip("libref_tick_strict.so not built")
+    # the bench script itself: pwn_flythrough replayed through the reference's block
+    ref = refs("libref_tick_strict.so")
+    poses = api.flythrough(default_level, 600)
+    bad, crossed = _tick_pin(default_level, refs, "libref_tick_strict.so", 0, 0, [1.0 / 60.0])
+    cam = api.cam_spawn(default_level)
+    grav = np.zeros(4, np.float32)
+    for f in range(600):
+        assert np.array_equal(cam.view(np.uint32), poses["cam"][f].view(np.uint32)), f
+        t = f % 240
+        fwd, tl, tr, ml = (1, 0, 0, 0) if t < 90 else (1, 1, 0, 0) if t < 150 else (0, 0, 1, 0) if t < 200 else (1, 0, 0, 1)
+        ref.player_tick(cam, grav, np.array([tl, tr, 0, 0, fwd, 0, ml, 0], np.int32), np.float32(1.0) / np.float32(60.0))
+    bad, crossed = _tick_pin(default_level, refs, "libref_tick_strict.so", 20000, 1, [1.0 / 60.0, 0.013, 0.031, 0.1])
+    assert bad == 0 and crossed > 20, (bad, crossed)
+    total_cross = 0
+    for seed in range(100):
+        txt = fuzz_levels.random_level_text(seed, open_edges=(seed % 4 == 3))
+        for k in range(10):
+            bad, crossed = _tick_pin(txt, refs, "libref_tick_strict.so", 120, 1000 * seed + k, [1.0 / 60.0, 0.05, 0.2], key_every=5)
+            assert bad == 0, (seed, k, bad)
+            total_cross += crossed
+    assert total_cross > 50
+    if refbind.available("libref_tick.so"):
+        bad, _ = _tick_pin(default_level, refs, "libref_tick.so", 20000, 1, [1.0 / 60.0, 0.013, 0.031, 0.1])
+        assert bad <= 40, bad          # shipped flags: fast-math code generation, a few ticks in 20 000 (6 here)
+
+
+# game.lua:1-31 as data: the table the script builds.  When /root/reference is there the test parses it from the
+# script itself and checks this copy against it.
+_GAME_LUA_OPOS = [
+    (0.0, 0.0, 0.0, 0.3, 0.8, 0.8, 0.8, 0.6), (0.0, 0.3, 0.0, 0.1, 0.4, 0.4, 0.4, 0.2),
+    (0.3, 0.0, 0.0, 0.1, 0.7, 0.7, 1.0, 0.4), (0.0, 0.0, 0.3, 0.1, 0.7, 1.0, 0.7, 0.4),
+    (-0.3, 0.0, 0.0, 0.1, 1.0, 0.7, 0.7, 0.4), (0.0, 0.0, -0.3, 0.1, 0.5, 1.0, 1.0, 0.4),
+    (0.3, 0.0, 0.1, 0.03, 0.4, 0.4, 0.4, 0.2), (0.1, 0.0, 0.3, 0.03, 0.4, 0.4, 0.4, 0.2),
+    (-0.3, 0.0, 0.1, 0.03, 0.4, 0.4, 0.4, 0.2), (0.1, 0.0, -0.3, 0.03, 0.4, 0.4, 0.4, 0.2),
+    (0.3, 0.0, -0.1, 0.03, 0.4, 0.4, 0.4, 0.2), (-0.1, 0.0, 0.3, 0.03, 0.4, 0.4, 0.4, 0.2),
+    (-0.3, 0.0, -0.1, 0.03, 0.4, 0.4, 0.4, 0.2), (-0.1, 0.0, -0.3, 0.03, 0.4, 0.4, 0.4, 0.2)]
+
+
+class _LuaGame:
+    """A second, independent evaluation of game.lua in Python floats (= Lua 5.1 numbers = C doubles; math.fmod,
+    math.sin, math.cos, math.floor are the same libm calls Lua's math library makes): the globals and on_tick of
+    game.lua:22-87 statement by statement.  obj_set narrows to float when it stores into the part (script.h:22-32)."""
+
+    def __init__(self, level_get, opos):
+        import math
+        self.m = math
+        self.level_get = level_get
+        self.opos = [list(r) for r in opos]
+        self.obx, self.oby, self.obz = 9.5, 0.3, 5.5
+        self.obvx, self.obvz = 1, 0
+        self.obj = [None] * len(self.opos)
+        for i, o in enumerate(self.opos):
+            self.obj_set(i, o[3], o[7], self.obx + o[0], self.oby + o[1], self.obz + o[2], o[4], o[5], o[6])
+
+    def obj_set(self, i, r, refl, x, y, z, cb, cg, cr):
+        self.obj[i] = np.array([r, refl, x, y, z, 1.0, cb, cg, cr], np.float32)
+
+    def on_tick(self, sec_current, sec_delta):
+        m, opos = self.m, self.opos
+        if m.fmod(sec_current, 0.5) < 0.15:
+            opos[1][4], opos[1][5], opos[1][6] = 0.3, 0.3, 1.3
+        else:
+            opos[1][4], opos[1][5], opos[1][6] = 0.3, 0.3, 0.3
+        for i, o in enumerate(opos):
+            rx, ry, rz = o[0], o[1], o[2]
+            rs = m.sin(sec_current * m.pi * 2 / 2)
+            rc = m.cos(sec_current * m.pi * 2 / 2)
+            rx, rz = rc * rx + rs * rz, rc * rz - rs * rx
+            self.obj_set(i, o[3], o[7], self.obx + rx, self.oby + ry, self.obz + rz, o[4], o[5], o[6])
+        c1 = self.level_get(m.floor(self.obx), m.floor(self.obz))
+        spd = 2.0
+        nobx = self.obx + self.obvx * sec_delta * spd
+        nobz = self.obz + self.obvz * sec_delta * spd
+        c2 = self.level_get(m.floor(nobx + self.obvx * 0.5), m.floor(nobz + self.obvz * 0.5))
+        turns = 0
+        if c1 != c2:
+            if c2 == "." or ((c1 == "#" or c1 == "&") and c2 == '"'):
+                self.obvx, self.obvz = self.obvz, -self.obvx
+                nobx = self.obx + self.obvx * sec_delta * spd
+                nobz = self.obz + self.obvz * sec_delta * spd
+                c2 = self.level_get(m.floor(nobx + self.obvx * 0.5), m.floor(nobz + self.obvz * 0.5))
+                turns = 1
+                if c2 == "." or ((c1 == "#" or c1 == "&") and c2 == '"'):
+                    self.obvx, self.obvz = -self.obvx, -self.obvz
+                    nobx = self.obx + self.obvx * sec_delta * spd
+                    nobz = self.obz + self.obvz * sec_delta * spd
+                    c2 = self.level_get(m.floor(nobx + self.obvx * 0.5), m.floor(nobz + self.obvz * 0.5))
+                    turns = 2
+        self.obx, self.obz = nobx, nobz
+        return turns
+
+
+def _parse_game_lua(path):
+    """the opos table and the start values straight from the reference's script"""
+    import re
+    src = open(path).read()
+    body = src[src.index("opos = {"):src.index("obx, oby, obz")]
+    rows = re.findall(r"\{([^{}]+)\}", body)
+    return [tuple(float(v) for v in r.split(",") if v.strip()) for r in rows]
+
+
+def test_game_script_pinned_to_a_second_evaluation(default_level):
+    """host/pwn_game.c against an independent evaluation of game.lua:22-87 (there is no Lua interpreter
+    in this image): 10 000 ticks at 60 Hz and 3 000 at irregular steps, every sphere (r, refl, pos, col as floats)
+    bit for bit after every tick, the turn rule of game.lua:69-83 taken both once and twice; then the same on the
+    fuzz levels, where raised floors beside 2-high rooms make the second clause of the rule fire."""
+    import fuzz_levels
+    opos = _GAME_LUA_OPOS
+    lua = os.path.join(REFERENCE, "game.lua")
+    if os.path.isfile(lua):
+        assert _parse_game_lua(lua) == [tuple(r) for r in opos]
+
+    def run(lv, nticks, deltas):
+        def level_get(x, z):          # lf_level_get -> get_cell (script.h:53-63, util.h:151-158)
+            x, z = int(x), int(z)
+            if x < 0 or x >= 64:
+                x = 0
+            if z < 0 or z >= 64:
+                z = 0
+            c = int(lv.cells[z, x]) if (z < lv.h and x < lv.w) else ord(".")
+            return chr(c) if c < 256 else "?"
+        py = _LuaGame(level_get, opos)
+        g = api.Game(lv)
+        s0 = g.spheres()
+        for i in range(14):
+            assert np.array_equal(np.concatenate([[s0["r"][i], s0["refl"][i]], s0["pos"][i], s0["col"][i][:3]]).astype(np.float32).view(np.uint32),
+                                  py.obj[i].view(np.uint32)), i
+        sec = 0.0
+        turns = [0, 0, 0]
+        for t in range(nticks):
+            dt = deltas[t % len(deltas)]
+            sec += dt
+            turns[py.on_tick(sec, dt)] += 1
+            sp = g.tick(sec, dt)
+            got = np.concatenate([sp["r"][:, None], sp["refl"][:, None], sp["pos"], sp["col"][:, :3]], axis=1).astype(np.float32)
+            want = np.stack(py.obj)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (t, np.argwhere(got != want)[:3])
+        return turns
+
+    turns = run(default_level, 10000, [1.0 / 60.0])
+    assert turns[1] > 10, turns
+    t2 = run(default_level, 3000, [0.013, 0.05, 0.2, 1.0 / 30.0, 0.4])
+    both = [turns[k] + t2[k] for k in range(3)]
+    for seed in range(40):
+        lv = api.level_parse(fuzz_levels.random_level_text(seed + 200, dim=22))
+        # (the script starts at (9.5, 5.5): whatever cell that is in the fuzz level)
+        t3 = run(lv, 300, [1.0 / 60.0, 0.1, 0.3])
+        both = [both[k] + t3[k] for k in range(3)]
+    assert both[1] > 20 and both[2] > 0, both
