@@ -27,12 +27,35 @@ struct BlurParams
 	// pixel index) for k_blur_fix, which runs when the whole frame has been traced.
 	int ylimit;
 	uint32_t *defer_count, *defer_list;
+	uint32_t zero;         // always 0; opaque to the compiler (the -0 of the packed products)
 };
 
 // s -> A*s + C (mod 2^31) composed n times for n = 0, 2, 4, 6 (a pixel's offset inside its group)
 // and for n = 6 (from one sample of a pixel to its next)
 __constant__ uint32_t c_jumpA[8];
 __constant__ uint32_t c_jumpC[8];
+
+// ---- packed FP32 (FADD2 / FFMA2): the x and y offsets of a sample go through the same operations ----
+// (see trace_kernel.cuh for why a product that feeds an add is written fma(a, b, -0) with an opaque -0)
+#ifndef PWN_PACKED
+#define PWN_PACKED 1
+#endif
+typedef unsigned long long bf32x2;
+__device__ __forceinline__ bf32x2 bpk2(float lo, float hi) { bf32x2 u; asm("mov.b64 %0, {%1,%2};" : "=l"(u) : "f"(lo), "f"(hi)); return u; }
+__device__ __forceinline__ void bunpk2(bf32x2 u, float &lo, float &hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(u)); }
+__device__ __forceinline__ bf32x2 badd2(bf32x2 a, bf32x2 b) { bf32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ bf32x2 bsub2(bf32x2 a, bf32x2 b) { bf32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ bf32x2 bmul2x(bf32x2 a, bf32x2 b, bf32x2 nz) { bf32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(nz)); return d; }
+
+// one LCG draw reduced mod 3759, as a float (util.h:1-12 up to the division)
+__device__ __forceinline__ float blur_draw(uint32_t &seed)
+{
+	seed = (seed * 25739u + 4u) & 0x7FFFFFFFu;
+	return (float)(seed % 3759u);
+}
+
+// the clamped sample coordinates (sx, sy) of one sample: base + randfs*fstr*z per lane, randfs = r*fl(2/3759) - 1
+__device__ __forceinline__ void blur_sample_xy(uint32_t &seed, bf32x2 base, float fstr, float z, bf32x2 nz, int xmax, int ymax, int &sx, int &sy);
 
 __device__ __forceinline__ float blur_randfs(uint32_t &seed)
 {
@@ -50,6 +73,25 @@ __device__ __forceinline__ int cvtt_clamp(float v, int hi)
 {
 	const int i = (int)__float2uint_rz(v);
 	return min(max(i, 0), hi);
+}
+
+__device__ __forceinline__ void blur_sample_xy(uint32_t &seed, bf32x2 base, float fstr, float z, bf32x2 nz, int xmax, int ymax, int &sx, int &sy)
+{
+#if PWN_PACKED
+	const float r0 = blur_draw(seed), r1 = blur_draw(seed);
+	const float c = __uint_as_float(0x3A0B79B3u);
+	bf32x2 v = bsub2(bmul2x(bpk2(r0, r1), bpk2(c, c), nz), bpk2(1.0f, 1.0f));          // randfs, both lanes
+	v = bmul2x(bmul2x(v, bpk2(fstr, fstr), nz), bpk2(z, z), nz);                         // (randfs*fstr)*z
+	float fx, fy;
+	bunpk2(badd2(base, v), fx, fy);
+	sx = cvtt_clamp(fx, xmax);
+	sy = cvtt_clamp(fy, ymax);
+#else
+	float fx, fy;
+	bunpk2(base, fx, fy);
+	sx = cvtt_clamp(__fadd_rn(fx, __fmul_rn(__fmul_rn(blur_randfs(seed), fstr), z)), xmax);
+	sy = cvtt_clamp(__fadd_rn(fy, __fmul_rn(__fmul_rn(blur_randfs(seed), fstr), z)), ymax);
+#endif
 }
 
 // pavgb on four bytes at once: (a + b + 1) >> 1 per byte = (a | b) - (((a ^ b) >> 1) & 0x7f7f7f7f)
@@ -78,7 +120,9 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 	seed = c_jumpA[j]*seed + c_jumpC[j];
 
 	const float z = __fsub_rn(P.zbuf[pix], 1.0f);
-	const float fbx = (float)x, fby = (float)y;
+	const bf32x2 base = bpk2((float)x, (float)y);
+	const float negz = __uint_as_float(0x80000000u ^ (P.zero & (uint32_t)x));   // -0.0f ptxas cannot fold
+	const bf32x2 nz = bpk2(negz, negz);
 	// six draws separate this pixel's pair in sample i from its pair in sample i+1
 	const uint32_t a6 = c_jumpA[3], c6 = c_jumpC[3];
 	uint32_t s[4];
@@ -89,8 +133,8 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 		#pragma unroll
 		for(int i = 0; i < 4; i++)
 		{
-			const int sx = cvtt_clamp(__fadd_rn(fbx, __fmul_rn(__fmul_rn(blur_randfs(seed), P.fstr), z)), P.dimx - 1);
-			const int sy = cvtt_clamp(__fadd_rn(fby, __fmul_rn(__fmul_rn(blur_randfs(seed), P.fstr), z)), P.dimy - 1);
+			int sx, sy;
+			blur_sample_xy(seed, base, P.fstr, z, nz, P.dimx - 1, P.dimy - 1, sx, sy);
 			at[i] = (uint32_t)sy*(uint32_t)P.rwidth + (uint32_t)sx;
 			ymax = max(ymax, sy);
 			seed = a6*seed + c6;
@@ -110,8 +154,8 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 	#pragma unroll
 	for(int i = 0; i < 4; i++)
 	{
-		const int sx = cvtt_clamp(__fadd_rn(fbx, __fmul_rn(__fmul_rn(blur_randfs(seed), P.fstr), z)), P.dimx - 1);
-		const int sy = cvtt_clamp(__fadd_rn(fby, __fmul_rn(__fmul_rn(blur_randfs(seed), P.fstr), z)), P.dimy - 1);
+		int sx, sy;
+		blur_sample_xy(seed, base, P.fstr, z, nz, P.dimx - 1, P.dimy - 1, sx, sy);
 		s[i] = __ldg(&P.src[(uint32_t)sy*(uint32_t)P.rwidth + (uint32_t)sx]);
 		seed = a6*seed + c6;
 	}

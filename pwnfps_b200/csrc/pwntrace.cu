@@ -626,7 +626,7 @@ static BlurParams blur_params(pwn_ctx *ctx, const uint32_t *src, const float *z,
 	B.dimx = dimx; B.dimy = dimy; B.rwidth = ctx->rwidth; B.y0 = 0; B.y1 = dimy;
 	B.nshards = 1; B.shard = 0;
 	B.fstr = 0.002f * (float)dimy;   // screen.h:86
-	B.ylimit = dimy; B.defer_count = nullptr; B.defer_list = nullptr;
+	B.ylimit = dimy; B.defer_count = nullptr; B.defer_list = nullptr; B.zero = 0u;
 	return B;
 }
 

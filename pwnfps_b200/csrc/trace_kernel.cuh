@@ -219,6 +219,27 @@ __device__ __forceinline__ const uint32_t *opaque_ptr(const uint32_t *p, uint32_
 	return (const uint32_t *)(uintptr_t)(((unsigned long long)hi << 32) | lo);
 }
 
+// ---- packed FP32 (Blackwell FADD2 / FMUL2 / FFMA2: two lanes per issue slot) ------------------------------
+// The x and z quantities of a ray are stepped by the same operations, so they travel as pairs.  Two rules keep the
+// results those of the reference's separate roundings:
+//   * ptxas contracts a packed multiply that feeds a packed add into ONE FFMA2 (a single rounding), even for
+//     mul.rn/add.rn and under --fmad=false.  A product that feeds an add is therefore written as fma(a, b, -0)
+//     with the pair {-0, -0} coming from a kernel parameter ptxas cannot see through: a*b + (-0) is the correctly
+//     rounded product for every a*b (including +-0), and an FFMA2 is never contracted again.
+//   * a packed multiply whose result feeds scalar adds is left alone (measured on the SASS: FMUL2 + FADD + FADD).
+// Scalars ride along as broadcast operands (R.F32): no copies.
+#ifndef PWN_PACKED
+#define PWN_PACKED 1
+#endif
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 u; asm("mov.b64 %0, {%1,%2};" : "=l"(u) : "f"(lo), "f"(hi)); return u; }
+__device__ __forceinline__ void unpk2(f32x2 u, float &lo, float &hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(u)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// a*b, correctly rounded, in a form ptxas cannot fuse with a following add (nz = {-0, -0}, opaque)
+__device__ __forceinline__ f32x2 mul2x(f32x2 a, f32x2 b, f32x2 nz) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(nz)); return d; }
+
 // one bit of a map entry as a predicate.  Written in PTX so that the front end cannot rewrite the test
 // into shift-and-compare chains: ptxas turns and + setp into a single LOP3 with a predicate result.
 __device__ __forceinline__ bool bit_of(uint32_t v, uint32_t mask)
@@ -314,6 +335,10 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 	// the cell map's address in a register pair (without spheres there is room for it): read as a kernel
 	// parameter it is re-read from the constant bank at every cell step
 	const uint32_t *cmap = SPH ? L.cellmap : opaque_ptr(L.cellmap, P.zero);
+	// -0.0f that ptxas cannot fold (see mul2x), in a register of the thread's own (mixed with the thread index: left
+	// uniform it is re-read from the constant bank at every use)
+	const float negz = __uint_as_float(0x80000000u ^ (SPH ? P.zero : (P.zero & threadIdx.x)));   // (the sphere builds have no register to spare)
+	const f32x2 nz2 = pk2(negz, negz);
 
 	// ---- pixel of this thread: CTA = 32 x K1_ROWS pixels, warp = 8x4 (or 32x1) ----------------------
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -376,11 +401,23 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 		// ================= trace.h:203-248: segment setup =================
 		if(IDS) ops += W_SEGMENT;
 		float rx, ry, rz;
+#if PWN_PACKED
+		{
+			const f32x2 irxz = pk2(irx, irz);
+			float sx, sz;
+			unpk2(mul2x(irxz, irxz, nz2), sx, sz);
+			const float d = __fadd_rn(__fadd_rn(sx, sz), __fmul_rn(iry, iry));
+			const float s = rsqrt_emul(L, d);
+			unpk2(mul2x(irxz, pk2(s, s), nz2), rx, rz);
+			ry = __fmul_rn(iry, s);
+		}
+#else
 		{
 			const float d = __fadd_rn(__fadd_rn(__fmul_rn(irx, irx), __fmul_rn(irz, irz)), __fmul_rn(iry, iry));
 			const float s = rsqrt_emul(L, d);
 			rx = __fmul_rn(irx, s); ry = __fmul_rn(iry, s); rz = __fmul_rn(irz, s);
 		}
+#endif
 		int cx = __float2int_rz(fx), cz = __float2int_rz(fz);   // real cell coordinates (IDS builds keep them current)
 		const float EPS = 0.0000000000001f;
 		// The reference tests the signs twice: gx/gy/gz from the un-normalised ray (trace.h:225-227) and "ray >= 0"
@@ -394,8 +431,15 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 		const bool up = !yneg;                                  // gy > 0
 		uint32_t upmask = up ? 2u : 0u;
 		asm volatile("" : "+r"(upmask));   // a value of its own: ptxas would otherwise rebuild it from the ray at every step
+#if PWN_PACKED
+		float w0x, w0z, omx, omz;
+		unpk2(sub2(pk2(fx, fz), pk2((float)cx, (float)cz)), w0x, w0z);
+		unpk2(sub2(pk2(1.0f, 1.0f), pk2(w0x, w0z)), omx, omz);
+		float wx = xneg ? w0x : omx, wy = yneg ? fy : __fsub_rn(1.0f, fy), wz = zneg ? w0z : omz;
+#else
 		const float w0x = __fsub_rn(fx, (float)cx), w0z = __fsub_rn(fz, (float)cz);
 		float wx = xneg ? w0x : __fsub_rn(1.0f, w0x), wy = yneg ? fy : __fsub_rn(1.0f, fy), wz = zneg ? w0z : __fsub_rn(1.0f, w0z);
+#endif
 		// linear index into the padded map.  While a coordinate is outside the grid the lookup
 		// folds to index 0 on that axis (util.h:151-158): such rays (oobm != 0) take the slow path
 		// of every step, which tracks the real (cx, cz) and recomputes the index from them
@@ -419,7 +463,12 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 		float iax = rcp_emul(L, rx), iaz = rcp_emul(L, rz);   // iavel = rcpps(abs(ray)), trace.h:229-231
 		const float iay = rcp_emul(L, ry);
 		float px = fx, py = fy, pz = fz;
+#if PWN_PACKED
+		unpk2(mul2x(pk2(wx, wz), pk2(iax, iaz), nz2), wx, wz);
+		wy = __fmul_rn(wy, iay);
+#else
 		wx = __fmul_rn(wx, iax); wy = __fmul_rn(wy, iay); wz = __fmul_rn(wz, iaz);
+#endif
 
 		int stepz = gz*WP;   // index step of a z move; an x move steps by gx
 		// the faces the ray crosses: FXP/FXN = 0/2 and FZP/FZN = 1/3 for a sign of +1/-1, as arithmetic (the FMA
@@ -444,13 +493,25 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 #define hdist ((SPH && hsurf == SF_SPHERE) ? aux.dist : cdist)
 
 // the "sphere nearer than where we got to" exits (trace.h:313-319 and friends)
+// How a lane leaves the walk.  A `break` out of the divergent middle of the loop costs a BREAK (the lane takes itself
+// off the loop's convergence barrier) beside the branch; with PWN_EXIT_AT_TAIL the lane instead runs the step counter
+// down and jumps to the loop's tail, where the one exit test of the loop lets it go: one instruction fewer on the
+// room step.  Whether the walk ended on a surface or ran out of steps is read from hsurf, never from the counter.
+#ifndef PWN_EXIT_AT_TAIL
+#define PWN_EXIT_AT_TAIL 0
+#endif
+#if PWN_EXIT_AT_TAIL
+#define PWN_LEAVE { maxsteps = 1; continue; }
+#else
+#define PWN_LEAVE break;
+#endif
 #define PWN_SPHERE_MARK hsurf = SF_SPHERE; ldir = -1;
 #define PWN_SPHERE_EXIT(FOGC, FOGBEG) \
 		if(SPH && cdist > aux.dist) { \
 			PWN_SPHERE_MARK \
 			if((FOGC) && aux.dist > (FOGBEG)) fog = __fadd_rn(fog, __fsub_rn(aux.dist, (FOGBEG))); \
-			break; }
-#define PWN_WALL_EXIT(SURF) { hsurf = (SURF); break; }
+			PWN_LEAVE }
+#define PWN_WALL_EXIT(SURF) { hsurf = (SURF); PWN_LEAVE }
 // The step just taken (along x if XSTEP) put the ray on the border of the padded map, or the ray
 // already was outside the grid: bring the real cell coordinates up to date and look the cell up
 // the way get_cell does (util.h:151-158).  Builds with IDS keep cx/cz current themselves.
@@ -539,10 +600,21 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 				const float mxz = fminf(wx, wz);
 				const bool yfirst = wy < mxz;
 				const float t = fminf(wy, mxz);
+#if PWN_PACKED
+				float ax, az;
+				{
+					const f32x2 tt = pk2(t, t);
+					unpk2(add2(mul2x(tt, pk2(rx, rz), nz2), pk2(px, pz)), px, pz);     // pos.xz += t*ray.xz
+					unpk2(sub2(pk2(wx, wz), tt), ax, az);
+				}
+				cdist = __fadd_rn(cdist, t);
+				py = __fadd_rn(__fmul_rn(t, ry), py);
+#else
 				cdist = __fadd_rn(cdist, t);
 				px = __fadd_rn(__fmul_rn(t, rx), px);
 				py = __fadd_rn(__fmul_rn(t, ry), py);
 				pz = __fadd_rn(__fmul_rn(t, rz), pz);
+#endif
 
 				PWN_SPHERE_EXIT(fogc, fogbeg)
 				if(fogc) fog = __fadd_rn(fog, __fsub_rn(cdist, fogbeg));
@@ -553,7 +625,9 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 				}
 				// X/Z cell advance (trace.h:331-340): all lanes minus t, the stepped lane reloads
 				{
+#if !PWN_PACKED
 					const float ax = __fsub_rn(wx, t), az = __fsub_rn(wz, t);
+#endif
 					wy = __fsub_rn(wy, t);
 					wx = xfirst ? iax : ax;
 					wz = xfirst ? az : iaz;
@@ -728,6 +802,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 #undef PWN_SPHERE_EXIT
 #undef PWN_SPHERE_MARK
 #undef PWN_WALL_EXIT
+#undef PWN_LEAVE
 #undef PWN_OOB_FIX
 #undef PWN_OOB_CHECK
 #undef PWN_OOB_RELOOK_
