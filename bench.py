@@ -23,9 +23,10 @@ configuration north_star's target is quoted on), blur pass on as the reference s
              roofline fraction
 
 N > 1 (torchrun, one process per GPU): STRONG scaling of the same step.  Every frame of the batch
-is sharded over the N GPUs by 32-row bands and assembled, blurred, in GPU 0's frame inside the timed
-events (pwn_trace_shard_blur: the exchange of the pre-blur rows and the gather to GPU 0 are peer
-stores issued by the trace and blur kernels themselves, with device-side barriers).  The
+is sharded over the N GPUs in contiguous blocks of 32-row bands and assembled, blurred, in GPU 0's frame
+inside the timed events (pwn_trace_shard_blur, PWN_SHARD_BLOCKS: the halo rows go to the neighbouring GPU
+and the blurred rows to GPU 0 as peer stores of the trace and blur kernels themselves, the blur running
+under the trace, gated by per-band counters on the device).  The
 pose-sharded batch (no exchange at all) and the unblurred fused band gather are reported beside it.
 """
 import argparse
@@ -54,7 +55,7 @@ def headline_config(world, blur=True):
     return {"workload": "synthetic 10k-sector maze (128x128 cells, 1000 portal pairs, seed 1), 7680x4320, 64-pose batched frame set "
                         "(seed 9)%s (BASELINE configs[4])" % (", blur on" if blur else ", blur off"),
             "resolution": list(SIZE), "frames_per_step": NPOSES,
-            "sharding": "none" if world == 1 else "every frame by 32-row bands over %d GPUs, assembled on GPU 0" % world,
+            "sharding": "none" if world == 1 else "every frame in %d contiguous blocks of 32-row bands over %d GPUs, assembled on GPU 0" % (world, world),
             "l2": "every 8K frame (132.7 MB sbuf + 132.7 MB zbuf + 132.7 MB pre-blur) is larger than the 126 MB L2 and is written "
                   "once; a 256 MiB flush runs between steps, outside the per-step events"}
 
@@ -412,6 +413,7 @@ def run_ours(args, rank, world, local_rank):
         # the frames a single GPU produces, by checksum: what every sharded frame is compared with
         want = tr.trace_poses(poses[:4], w, h, flags, want_sums=True)
         tr.shard_config(world, rank)
+        tr.shard_layout(blocks=True)          # contiguous band blocks: halo exchange instead of an all-gather
         rig.barrier()
         if blur:
             bases = shard.open_all_peers(tr, rank, world, dist)
@@ -529,6 +531,7 @@ def run_ours(args, rank, world, local_rank):
                 raise SystemExit("bench.py: a device-side barrier of the sharded frames timed out")
         else:
             shard.close_peer_frame(tr, bases)
+        tr.shard_layout(blocks=False)
         tr.shard_config(1, 0)
         beside = shard.bench_band_gather(tr, rank, world, local_rank, rig.stream)
         tr.shard_config(1, 0)

@@ -185,6 +185,16 @@ int pwn_frame_clear(pwn_ctx *ctx);
  * 32-row bands b with b % nshards == shard (screen.h:63-64 bands).  Default 1/0.
  */
 int pwn_shard_config(pwn_ctx *ctx, int nshards, int shard);
+/*
+ * How the bands are dealt: PWN_SHARD_INTERLEAVED (default; band b goes to shard b % nshards: even load whatever the
+ * view) or PWN_SHARD_BLOCKS (shard s owns the contiguous bands [s*nbands/nshards, (s+1)*nbands/nshards)).  Blocks are
+ * what makes a sharded frame WITH the blur pass cheap: the blur reaches only 0.002*dimy*(z-1) rows (screen.h:86,100-102),
+ * so a shard needs a few halo bands of each neighbour instead of the whole pre-blur frame.  halo_bands: bands exchanged
+ * with each neighbour, 0 = ceil(0.015*dimy/32); samples that reach further are fetched from the owning shard afterwards,
+ * the frame is exact for any value.
+ */
+enum { PWN_SHARD_INTERLEAVED = 0, PWN_SHARD_BLOCKS = 1 };
+int pwn_shard_layout(pwn_ctx *ctx, int layout, int halo_bands);
 
 /* ---- the hot path ------------------------------------------------------------------ */
 /*
@@ -281,7 +291,13 @@ int pwn_frame_ipc_import(pwn_ctx *ctx, const void *handle64, uint64_t *base_dev)
 int pwn_frame_ipc_close(pwn_ctx *ctx, uint64_t base_dev);
 
 /*
- * A sharded frame WITH the blur pass.  screen.h:69-123 gathers from anywhere in the pre-blur
+ * A sharded frame WITH the blur pass, block layout (pwn_shard_layout PWN_SHARD_BLOCKS; what bench.py times at N > 1):
+ * one K1 launch traces the shard's bands, halo bands first, storing those into the neighbour's pre-blur buffer too and
+ * counting finished lanes per band; on a second stream the blur pass follows two bands at a time, each launch gated on the
+ * device by the counters of the bands it reads, and stores straight into shard 0's frame -- the gather to GPU 0 runs under
+ * the trace.  Samples beyond the exchanged rows are finished from the owning shard's rows after a device barrier.
+ *
+ * Interleaved layout: screen.h:69-123 gathers from anywhere in the pre-blur
  * frame, so every shard needs all of it: with pwn_frame_peers set, pwn_trace_shard_blur
  *   1. traces the own bands (pwn_shard_config) and stores every pixel into the pre-blur buffer
  *      of EVERY shard -- the all-gather is part of the trace kernel, whole 128-byte row
@@ -294,6 +310,8 @@ int pwn_frame_ipc_close(pwn_ctx *ctx, uint64_t base_dev);
  * base_dev[s] = device address of shard s's frame allocation in THIS process (pwn_frame_ipc_import
  * of the handle shard s exported; the own entry is ignored).  All shards must configure the same
  * frame size and call pwn_trace_shard_blur the same number of times.  nshards == 0 clears.
+ * The call also restarts the frame count the device barriers and band counters work with: every shard calls it,
+ * with no sharded frame in flight, and no shard starts a frame before all have returned from it (a host barrier).
  * A shard that never arrives ends the wait after 4 s: the next pwn_sync / pwn_read_frame / pwn_read_bands of
  * the waiting shard then fails with PWN_E_PEER (once per incident; the frame holds stale bands), and
  * pwn_frame_peers_status reports 1 until pwn_frame_peers is called again.  A shard whose own trace cannot be
@@ -303,6 +321,9 @@ int pwn_frame_ipc_close(pwn_ctx *ctx, uint64_t base_dev);
 int pwn_frame_peers(pwn_ctx *ctx, int nshards, const uint64_t *base_dev);
 int pwn_trace_shard_blur(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags);
 int pwn_frame_peers_status(pwn_ctx *ctx, int *timed_out);
+/* test hook: the first nwords words behind the frame planes (barrier flags [0,16), error word 16, band counters from 64),
+ * read on a stream of their own while kernels may be running; returns the number of words read */
+int pwn_debug_flags(pwn_ctx *ctx, uint32_t *out, int nwords);
 /*
  * Copy the bands this shard owns (pwn_shard_config) from its sbuf to the same rows of a HOST frame
  * of rwidth*rheight words -- typically one frame in shared memory that every shard's process has

@@ -63,7 +63,7 @@ ABI_SYMBOLS = [
     "pwn_screen_upscale", "pwn_surface_device_ptr", "pwn_last_upscale_ms", "pwn_trace_config",
     "pwn_frame_peers", "pwn_trace_shard_blur", "pwn_frame_peers_status",
     "pwn_host_register", "pwn_host_unregister", "pwn_debug_pack", "pwn_write_frame", "pwn_read_bands",
-    "pwn_math_status", "pwn_screen_chunks",
+    "pwn_math_status", "pwn_screen_chunks", "pwn_shard_layout", "pwn_debug_flags",
 ]
 
 
@@ -128,6 +128,8 @@ def lib():
     L.pwn_frame_peers_status.argtypes = [vp, C.POINTER(i)]
     L.pwn_math_status.argtypes = [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     L.pwn_screen_chunks.argtypes = [vp, i]
+    L.pwn_shard_layout.argtypes = [vp, i, i]
+    L.pwn_debug_flags.argtypes = [vp, vp, i]
     _lib = L
     return L
 
@@ -539,6 +541,10 @@ class Tracer:
     def shard_config(self, nshards, shard):
         _check(self.L.pwn_shard_config(self.h, nshards, shard))
 
+    def shard_layout(self, blocks=False, halo_bands=0):
+        """PWN_SHARD_BLOCKS (contiguous band blocks, halo exchange for the blur) or the default interleaved bands"""
+        _check(self.L.pwn_shard_layout(self.h, 1 if blocks else 0, halo_bands))
+
     # -- hot path ----------------------------------------------------------------
     def trace_cam(self, cam, dimx, dimy, sec_current=0.0, flags=0):
         cam = np.ascontiguousarray(cam, dtype=np.float32).reshape(16)
@@ -687,6 +693,13 @@ class Tracer:
         """copy this shard's bands into the same rows of a (rheight, rwidth) uint32 host frame (numpy array or address)"""
         ptr = host_frame.ctypes.data if isinstance(host_frame, np.ndarray) else host_frame
         _check(self.L.pwn_read_bands(self.h, dimx, dimy, ptr))
+
+    def debug_flags(self, nwords=128):
+        out = np.zeros(nwords, np.uint32)
+        n = self.L.pwn_debug_flags(self.h, out.ctypes.data, nwords)
+        if n < 0:
+            _check(n)
+        return out[:n]
 
     def peers_timed_out(self):
         v = C.c_int()

@@ -25,8 +25,12 @@ struct BlurParams
 	// pwn_trace_screen blurs a frame in row chunks while later chunks are still being traced: rows [0, ylimit) of src
 	// are final.  A pixel with a sample below them is not written but queued (defer_list[atomicAdd(defer_count)] =
 	// pixel index) for k_blur_fix, which runs when the whole frame has been traced.
-	int ylimit;
+	int ylo, ylimit;       // rows [ylo, ylimit) of src are final
 	uint32_t *defer_count, *defer_list;
+	// k_blur_fix on a frame sharded in contiguous blocks: row y of the pre-blur frame is read from the shard that traced it
+	const uint32_t *src_sh[8];
+	int band_start[9];     // shard s owns the bands [band_start[s], band_start[s+1])
+	int nsh;               // 0: src holds every row
 	uint32_t zero;         // always 0; opaque to the compiler (the -0 of the packed products)
 };
 
@@ -101,7 +105,7 @@ __device__ __forceinline__ uint32_t pavgb4(uint32_t a, uint32_t b)
 }
 
 // one output pixel of the blur pass (screen.h:91-117)
-template <bool DEFER>
+template <bool DEFER, bool PEER = false>
 __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 {
 	const uint32_t pix = (uint32_t)y*(uint32_t)P.rwidth + (uint32_t)x;   // (a frame has fewer than 2^31 pixels: pwn_frame_config)
@@ -109,7 +113,7 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 	if((x & ~3) >= P.dimx - 3)
 	{
 		// the last dimx%4 pixels are not blurred (screen.h:88-91)
-		P.dst[pix] = P.src[pix];
+		P.dst[pix] = (DEFER || PEER) ? __ldcg(&P.src[pix]) : P.src[pix];
 		return;
 	}
 	// the row's stream (seed = cy*cy + 415135, screen.h:82) advanced to draw 32*g + 2*j
@@ -119,7 +123,7 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 	// masks before it takes the remainder)
 	seed = c_jumpA[j]*seed + c_jumpC[j];
 
-	const float z = __fsub_rn(P.zbuf[pix], 1.0f);
+	const float z = __fsub_rn(DEFER || PEER ? __ldcg(&P.zbuf[pix]) : P.zbuf[pix], 1.0f);
 	const bf32x2 base = bpk2((float)x, (float)y);
 	const float negz = __uint_as_float(0x80000000u ^ (P.zero & (uint32_t)x));   // -0.0f ptxas cannot fold
 	const bf32x2 nz = bpk2(negz, negz);
@@ -129,7 +133,7 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 	if(DEFER)
 	{
 		uint32_t at[4];
-		int ymax = 0;
+		int ymax = 0, ymin = 0x7FFFFFFF;
 		#pragma unroll
 		for(int i = 0; i < 4; i++)
 		{
@@ -137,17 +141,37 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 			blur_sample_xy(seed, base, P.fstr, z, nz, P.dimx - 1, P.dimy - 1, sx, sy);
 			at[i] = (uint32_t)sy*(uint32_t)P.rwidth + (uint32_t)sx;
 			ymax = max(ymax, sy);
+			ymin = min(ymin, sy);
 			seed = a6*seed + c6;
 		}
-		if(ymax >= P.ylimit)   // a sample in a row that is still being traced: k_blur_fix finishes this pixel
+		if(ymax >= P.ylimit || ymin < P.ylo)   // a sample in a row that is not there (yet): k_blur_fix finishes this pixel
 		{
 			P.defer_list[atomicAdd(P.defer_count, 1u)] = pix;
 			return;
 		}
-		// (plain loads: later rows of src are written by a trace that runs beside this kernel, and the
-		// non-coherent path may only be used for data nobody writes during the launch)
+		// (through L2: the rows are written by a trace that runs beside this kernel, here or on the neighbouring GPU;
+		// the non-coherent path and L1 may only serve data nobody writes during the launch)
 		#pragma unroll
-		for(int i = 0; i < 4; i++) s[i] = P.src[at[i]];
+		for(int i = 0; i < 4; i++) s[i] = __ldcg(&P.src[at[i]]);
+	}
+	else if(PEER)
+	{
+		#pragma unroll
+		for(int i = 0; i < 4; i++)
+		{
+			int sx, sy;
+			blur_sample_xy(seed, base, P.fstr, z, nz, P.dimx - 1, P.dimy - 1, sx, sy);
+			const uint32_t *src = P.src;
+			if(P.nsh > 0)
+			{
+				const int sb = sy >> 5;
+				int o = 0;
+				while(o + 1 < P.nsh && sb >= P.band_start[o + 1]) o++;
+				src = P.src_sh[o];
+			}
+			s[i] = __ldcg(&src[(uint32_t)sy*(uint32_t)P.rwidth + (uint32_t)sx]);
+			seed = a6*seed + c6;
+		}
 	}
 	else
 	{
@@ -182,7 +206,36 @@ __global__ void __launch_bounds__(256) k_blur_fix(const __grid_constant__ BlurPa
 	{
 		const uint32_t pix = P.defer_list[i];
 		const uint32_t y = pix / (uint32_t)P.rwidth;
-		blur_pixel<false>(P, (int)(pix - y*(uint32_t)P.rwidth), (int)y);
+		blur_pixel<false, true>(P, (int)(pix - y*(uint32_t)P.rwidth), (int)y);
+	}
+}
+
+// stream-ordered wait for band counters (contiguous-block sharding): lane t polls band b0 + t until it holds
+// `target` lanes or more; a band that never fills ends the wait after timeout_ns with the error word set
+struct WaitParams
+{
+	const uint32_t *done;
+	int b0, b1;
+	uint32_t target;
+	unsigned long long timeout_ns;
+	uint32_t *err;
+};
+
+__global__ void k_wait_bands(const WaitParams W)
+{
+	unsigned long long t0, t1;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+	for(int b = W.b0 + (int)threadIdx.x; b < W.b1; b += (int)blockDim.x)
+	{
+		for(;;)
+		{
+			uint32_t v;
+			asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(W.done + b) : "memory");
+			if((int32_t)(v - W.target) >= 0) break;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+			if(t1 - t0 > W.timeout_ns) { *W.err = 1u; break; }
+			__nanosleep(100);
+		}
 	}
 }
 

@@ -56,8 +56,9 @@ struct FrameSet
 	void *base = nullptr;      // one allocation: sbuf | tsbuf | zbuf  (so one IPC handle covers the frame)
 	uint32_t *sbuf = nullptr, *tsbuf = nullptr;
 	float *zbuf = nullptr;
-	uint32_t *flags = nullptr; // 64 words after the planes: inter-GPU barrier flags (k_peer_barrier)
-	size_t off_sbuf = 0, off_tsbuf = 0, off_zbuf = 0, off_flags = 0, bytes = 0;
+	uint32_t *flags = nullptr; // 64 words after the planes: inter-GPU barrier flags (k_peer_barrier); then one counter per band
+	uint32_t *band_done = nullptr;   // (contiguous-block sharding: lanes that have finished the band, summed over the frames so far)
+	size_t off_sbuf = 0, off_tsbuf = 0, off_zbuf = 0, off_flags = 0, off_band_done = 0, bytes = 0;
 };
 
 struct pwn_ctx
@@ -68,6 +69,8 @@ struct pwn_ctx
 	cudaEvent_t ev_done[3] = {nullptr, nullptr, nullptr}, ev_copied[3] = {nullptr, nullptr, nullptr};
 	cudaEvent_t ev_chunk[16] = {};   // pwn_trace_screen: "chunk c traced" (0-7) and "chunk c blurred" (8-15)
 	uint32_t *h_defer = nullptr;     // pinned: how many pixels the chunked blur had to leave to k_blur_fix
+	cudaStream_t dbg_stream = nullptr;   // pwn_debug_flags
+	uint32_t *h_dbg = nullptr;
 
 	// level
 	uint32_t *d_cellmap = nullptr;
@@ -108,6 +111,10 @@ struct pwn_ctx
 	bool timed_k3 = false;
 
 	int nshards = 1, shard = 0;
+	int layout = PWN_SHARD_INTERLEAVED;
+	int halo_bands = 0;        // contiguous blocks: bands exchanged with each neighbour, 0 = from the frame height
+	uint32_t blk_frames = 0;   // sharded frames traced in the block layout since pwn_frame_peers (the band counters' epoch)
+	cudaEvent_t ev_blk_k2 = nullptr, ev_blk_done = nullptr;
 	int reflect = 2;           // REFLECT as shipped (defs.h:8)
 	int screen_chunks = 0;     // pwn_trace_screen: row chunks per frame, 0 = automatic
 	// sharded frame with the blur pass: the other shards' frame allocations (pwn_frame_peers)
@@ -133,6 +140,31 @@ static int set_device(pwn_ctx *ctx)
 #define CTX_ENTER(ctx) do { if((ctx) == nullptr) return fail(PWN_E_ARG, "null context"); \
 	int rc_ = set_device(ctx); if(rc_ != PWN_OK) return rc_; } while(0)
 
+// Under CUDA's lazy module loading (the default since 12.2) a kernel's code reaches the device at its first launch,
+// and that load waits for the device to go idle.  A sharded frame parks kernels on the device that spin until other work
+// arrives (k_peer_barrier, k_wait_bands): a first launch behind one of them stalls until its time-out.  Every kernel of the
+// library is therefore loaded when the first context is created (cudaFuncGetAttributes loads the function).
+template <typename F> static cudaError_t preload(F *fn)
+{
+	cudaFuncAttributes a;
+	return cudaFuncGetAttributes(&a, (const void *)fn);
+}
+
+static int preload_kernels()
+{
+#define PWN_PRELOAD(K) do { cudaError_t e_ = preload(K); if(e_ != cudaSuccess) \
+	return fail(PWN_E_CUDA, "loading %s: %s", #K, cudaGetErrorString(e_)); } while(0)
+#define PWN_PRELOAD_TRACE(S, L) PWN_PRELOAD((k_trace<S, false, L, false>)); PWN_PRELOAD((k_trace<S, false, L, true>)); PWN_PRELOAD((k_trace<S, true, L, false>))
+	PWN_PRELOAD_TRACE(false, false); PWN_PRELOAD_TRACE(false, true); PWN_PRELOAD_TRACE(true, false); PWN_PRELOAD_TRACE(true, true);
+	PWN_PRELOAD(k_blur<false>); PWN_PRELOAD(k_blur<true>); PWN_PRELOAD(k_blur_fix); PWN_PRELOAD(k_wait_bands); PWN_PRELOAD(k_peer_barrier);
+	PWN_PRELOAD(k_checksum); PWN_PRELOAD(k_fp32_peak); PWN_PRELOAD(k_pack_eval); PWN_PRELOAD(k_libm_eval<false>); PWN_PRELOAD(k_libm_eval<true>);
+	PWN_PRELOAD(k_upscale_packed<0>); PWN_PRELOAD(k_upscale_packed<1>); PWN_PRELOAD(k_upscale_packed<2>); PWN_PRELOAD(k_upscale_packed<4>);
+	PWN_PRELOAD(k_upscale_any);
+#undef PWN_PRELOAD_TRACE
+#undef PWN_PRELOAD
+	return PWN_OK;
+}
+
 extern "C" int pwn_create(pwn_ctx **out, int device)
 {
 	if(out == nullptr) return fail(PWN_E_ARG, "pwn_create: null out");
@@ -151,6 +183,7 @@ extern "C" int pwn_create(pwn_ctx **out, int device)
 	struct Guard { pwn_ctx *c; ~Guard() { if(c) pwn_destroy(c); } } guard{ctx};   // a failed step below undoes the ones before it
 	ctx->device = device;
 	CU(cudaSetDevice(device));
+	{ int rc = preload_kernels(); if(rc != PWN_OK) return rc; }
 	CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
 	CU(cudaEventCreate(&ctx->ev_k1a));
@@ -164,6 +197,8 @@ extern "C" int pwn_create(pwn_ctx **out, int device)
 		CU(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
 	}
 	for(int i = 0; i < 16; i++) CU(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&ctx->ev_blk_k2, cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&ctx->ev_blk_done, cudaEventDisableTiming));
 	CU(cudaHostAlloc((void **)&ctx->h_defer, 64, cudaHostAllocDefault));
 	ctx->h_defer[0] = 0;
 
@@ -206,7 +241,11 @@ extern "C" int pwn_destroy(pwn_ctx *ctx)
 		ctx->ev_copied[0], ctx->ev_copied[1], ctx->ev_copied[2]};
 	for(cudaEvent_t e : evs) if(e) cudaEventDestroy(e);
 	for(cudaEvent_t e : ctx->ev_chunk) if(e) cudaEventDestroy(e);
+	if(ctx->ev_blk_k2) cudaEventDestroy(ctx->ev_blk_k2);
+	if(ctx->ev_blk_done) cudaEventDestroy(ctx->ev_blk_done);
 	if(ctx->h_defer) cudaFreeHost(ctx->h_defer);
+	if(ctx->h_dbg) cudaFreeHost(ctx->h_dbg);
+	if(ctx->dbg_stream) cudaStreamDestroy(ctx->dbg_stream);
 	if(ctx->stream) cudaStreamDestroy(ctx->stream);
 	if(ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
 	cudaGetLastError();
@@ -568,10 +607,12 @@ extern "C" int pwn_frame_config(pwn_ctx *ctx, int rwidth, int rheight, int want_
 		for(int i = 0; i < 3; i++)
 		{
 			FrameSet &f = ctx->fs[i];
-			f.bytes = 3*plane + 256;
+			const size_t nbands = ((size_t)rheight + 31)/32;
+			f.bytes = 3*plane + 256 + align_up(4*(nbands + 1), 256);
 			CU(cudaMalloc(&f.base, f.bytes));
-			f.off_sbuf = 0; f.off_tsbuf = plane; f.off_zbuf = 2*plane; f.off_flags = 3*plane;
+			f.off_sbuf = 0; f.off_tsbuf = plane; f.off_zbuf = 2*plane; f.off_flags = 3*plane; f.off_band_done = 3*plane + 256;
 			f.flags = (uint32_t *)((char *)f.base + f.off_flags);
+			f.band_done = (uint32_t *)((char *)f.base + f.off_band_done);
 			f.sbuf = (uint32_t *)((char *)f.base + f.off_sbuf);
 			f.tsbuf = (uint32_t *)((char *)f.base + f.off_tsbuf);
 			f.zbuf = (float *)((char *)f.base + f.off_zbuf);
@@ -610,6 +651,15 @@ extern "C" int pwn_frame_clear(pwn_ctx *ctx)
 	return PWN_OK;
 }
 
+extern "C" int pwn_shard_layout(pwn_ctx *ctx, int layout, int halo_bands)
+{
+	if(ctx == nullptr) return fail(PWN_E_ARG, "null context");
+	if(layout != PWN_SHARD_INTERLEAVED && layout != PWN_SHARD_BLOCKS) return fail(PWN_E_ARG, "pwn_shard_layout: layout %d", layout);
+	if(halo_bands < 0 || halo_bands > 4096) return fail(PWN_E_ARG, "pwn_shard_layout: %d halo bands", halo_bands);
+	ctx->layout = layout; ctx->halo_bands = halo_bands;
+	return PWN_OK;
+}
+
 extern "C" int pwn_shard_config(pwn_ctx *ctx, int nshards, int shard)
 {
 	if(ctx == nullptr) return fail(PWN_E_ARG, "null context");
@@ -617,6 +667,34 @@ extern "C" int pwn_shard_config(pwn_ctx *ctx, int nshards, int shard)
 	ctx->nshards = nshards; ctx->shard = shard;
 	return PWN_OK;
 }
+
+// ---- contiguous-block sharding (PWN_SHARD_BLOCKS): who owns which bands, and which of them are halo -------------
+static int blk_start(int nbands, int nshards, int s) { return (int)((long long)s*nbands/nshards); }
+
+static int blk_halo(const pwn_ctx *ctx, int dimy)
+{
+	if(ctx->halo_bands > 0) return ctx->halo_bands;
+	// the blur reaches 0.002*dimy*(z-1) rows (screen.h:86,100-102): bands enough for surfaces up to ~8.5 units away;
+	// farther ones are finished by k_blur_fix from the owning shard's rows
+	int h = (int)((0.015*dimy + 31.0)/32.0);
+	return h < 1 ? 1 : h;
+}
+
+// shard s: bands [b0, b0 + nb); its first ht bands are read by the shard above, its last hb by the shard below
+static void blk_shape(const pwn_ctx *ctx, int dimy, int s, int &b0, int &nb, int &ht, int &hb)
+{
+	const int nbands = (dimy + 31)/32, h = blk_halo(ctx, dimy);
+	b0 = blk_start(nbands, ctx->nshards, s);
+	nb = blk_start(nbands, ctx->nshards, s + 1) - b0;
+	ht = (s > 0) ? (h < nb ? h : nb) : 0;
+	hb = (s + 1 < ctx->nshards) ? (h < nb - ht ? h : nb - ht) : 0;
+}
+
+struct BlkTrace   // what a K1 launch of pwn_trace_shard_blur adds in the block layout
+{
+	uint32_t *halo_up = nullptr, *halo_dn = nullptr, *done_local = nullptr, *done_up = nullptr, *done_dn = nullptr;
+	int ht = 0, hb = 0;
+};
 
 // ---- the hot path ----------------------------------------------------------------------------------
 static BlurParams blur_params(pwn_ctx *ctx, const uint32_t *src, const float *z, uint32_t *dst, int dimx, int dimy)
@@ -626,15 +704,18 @@ static BlurParams blur_params(pwn_ctx *ctx, const uint32_t *src, const float *z,
 	B.dimx = dimx; B.dimy = dimy; B.rwidth = ctx->rwidth; B.y0 = 0; B.y1 = dimy;
 	B.nshards = 1; B.shard = 0;
 	B.fstr = 0.002f * (float)dimy;   // screen.h:86
-	B.ylimit = dimy; B.defer_count = nullptr; B.defer_list = nullptr; B.zero = 0u;
+	B.ylo = 0; B.ylimit = dimy; B.defer_count = nullptr; B.defer_list = nullptr; B.zero = 0u;
+	B.nsh = 0;
+	for(int t = 0; t < 8; t++) B.src_sh[t] = nullptr;
+	for(int t = 0; t < 9; t++) B.band_start[t] = 0;
 	return B;
 }
 
-static int launch_blur(pwn_ctx *ctx, const BlurParams &B, int nrows = -1)
+static int launch_blur(pwn_ctx *ctx, const BlurParams &B, int nrows = -1, cudaStream_t st = nullptr)
 {
 	dim3 grid((B.dimx + 255)/256, nrows < 0 ? B.dimy : nrows), block(256);
-	if(B.defer_count != nullptr && B.ylimit < B.dimy) k_blur<true><<<grid, block, 0, ctx->stream>>>(B);
-	else k_blur<false><<<grid, block, 0, ctx->stream>>>(B);
+	if(B.defer_count != nullptr && (B.ylimit < B.dimy || B.ylo > 0)) k_blur<true><<<grid, block, 0, st ? st : ctx->stream>>>(B);
+	else k_blur<false><<<grid, block, 0, st ? st : ctx->stream>>>(B);
 	CU(cudaGetLastError());
 	ctx->launches++;
 	return PWN_OK;
@@ -663,7 +744,7 @@ static void launch_k1(const TraceParams &P, dim3 grid, cudaStream_t st, bool ids
 // then, for a single blurred frame, K2
 static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], const float rayb[4], const float rdx[4], const float rdy[4],
 	int dimx, int dimy, float sec, unsigned flags, bool timing, const FrameSet *prev = nullptr, bool defer_blur = false,
-	int band0 = 0, int nbands_launch = -1)
+	int band0 = 0, int nbands_launch = -1, const BlkTrace *blk = nullptr)
 {
 	if(!ctx->have_level) return fail(PWN_E_STATE, "trace before pwn_level_upload");
 	if(!ctx->have_tables) return fail(PWN_E_STATE, "trace before pwn_math_tables");
@@ -677,7 +758,7 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 	if(ctx->nsph > 0 && from[3] != ctx->sph_w)
 		return fail(PWN_E_UNSUPPORTED, "camera w (%g) differs from sphere w (%g)", from[3], ctx->sph_w);
 	if((flags & PWN_F_IDS) && ctx->d_ids == nullptr) return fail(PWN_E_STATE, "PWN_F_IDS without pwn_frame_config(want_ids)");
-	if((flags & PWN_F_BLUR) && ctx->nshards > 1 && !ctx->allgather_now)
+	if((flags & PWN_F_BLUR) && ctx->nshards > 1 && !ctx->allgather_now && blk == nullptr)
 		return fail(PWN_E_UNSUPPORTED, "blur needs the whole pre-blur frame: gather the bands, then pwn_blur_frame");
 
 	TraceParams P;
@@ -694,6 +775,18 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 	P.nshards = ctx->nshards; P.shard = ctx->shard;
 	const int nbands = (dimy + 31)/32;
 	P.nbands_local = nbands > ctx->shard ? (nbands - ctx->shard + ctx->nshards - 1)/ctx->nshards : 0;
+	if(ctx->layout == PWN_SHARD_BLOCKS && ctx->nshards > 1)
+	{
+		int b0, nb, ht, hb;
+		blk_shape(ctx, dimy, ctx->shard, b0, nb, ht, hb);
+		P.blk = 1; P.blk_b0 = b0; P.nbands_local = nb;
+		if(blk != nullptr)
+		{
+			P.blk_ht = blk->ht; P.blk_hb = blk->hb;
+			P.halo_up = blk->halo_up; P.halo_dn = blk->halo_dn;
+			P.done_local = blk->done_local; P.done_up = blk->done_up; P.done_dn = blk->done_dn;
+		}
+	}
 	const bool blur = (flags & PWN_F_BLUR) != 0;
 	uint32_t *sb = ctx->r_sbuf ? ctx->r_sbuf : f.sbuf, *tsb = ctx->r_tsbuf ? ctx->r_tsbuf : f.tsbuf;
 	P.sbuf = blur ? tsb : sb;
@@ -754,6 +847,20 @@ extern "C" int pwn_trace_frame(pwn_ctx *ctx, const float from[4], const float ra
 	return launch_trace(ctx, ctx->fs[0], from, rayb, rdx, rdy, dimx, dimy, sec_current, flags, true);
 }
 
+// (the band counters of the block layout count frames since this call on EVERY shard: call it on all of them, with
+// no sharded frame in flight)
+static int reset_band_counters(pwn_ctx *ctx)
+{
+	ctx->blk_frames = 0;
+	ctx->epoch = 0;          // the barrier flags count sharded frames since this call, like the band counters
+	if(ctx->rwidth == 0) return PWN_OK;
+	const FrameSet &f = ctx->fs[0];
+	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaStreamSynchronize(ctx->copy_stream));
+	CU(cudaMemset(f.flags, 0, f.bytes - f.off_flags));
+	return PWN_OK;
+}
+
 // ---- sharded frame WITH the blur pass: all-gather fused into K1, device-side barriers, sharded K2 -----
 extern "C" int pwn_frame_peers(pwn_ctx *ctx, int nshards, const uint64_t *base_dev)
 {
@@ -762,6 +869,7 @@ extern "C" int pwn_frame_peers(pwn_ctx *ctx, int nshards, const uint64_t *base_d
 	ctx->npeer_shards = 0;
 	ctx->barrier_pending = false;
 	ctx->peer_timeouts = 0;
+	{ int rc0 = set_device(ctx); if(rc0 != PWN_OK) return rc0; rc0 = reset_band_counters(ctx); if(rc0 != PWN_OK) return rc0; }
 	if(nshards == 0) return PWN_OK;
 	if(nshards < 2 || nshards > 8 || base_dev == nullptr) return fail(PWN_E_ARG, "pwn_frame_peers: %d shards (2..8)", nshards);
 	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "pwn_frame_peers before pwn_frame_config");
@@ -789,13 +897,109 @@ static int launch_barrier(pwn_ctx *ctx, int slot)
 	return PWN_OK;
 }
 
+// A sharded frame WITH the blur pass in the contiguous-block layout.  One K1 launch traces the shard's bands, halo bands
+// first, storing those into the neighbour's pre-blur buffer as well and counting finished lanes per band; on the second
+// stream the blur pass follows band group by band group, each gated by a one-warp kernel that waits for the counters of
+// the bands it reads, and stores straight into shard 0's frame -- so the gather to GPU 0 runs under the trace.  Samples
+// that reach beyond the exchanged rows are queued and finished by k_blur_fix from the owning shard's rows once every
+// shard's trace is complete (barrier A); barrier B closes the frame.
+static int trace_shard_blur_blocks(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags)
+{
+	float rayb[4], rdx[4], rdy[4];
+	pwn_ray_setup(cam, dimx, dimy, rayb, rdx, rdy);
+	const FrameSet &f = ctx->fs[0];
+	const int nbands = (dimy + 31)/32, S = ctx->nshards, r = ctx->shard;
+	int b0, nb, ht, hb;
+	blk_shape(ctx, dimy, r, b0, nb, ht, hb);
+	// what reaches this shard from its neighbours: the last hb bands of the shard above, the first ht of the one below
+	int ub0 = 0, unb = 0, uht = 0, uhb = 0, db0 = 0, dnb = 0, dht = 0, dhb = 0;
+	if(r > 0) blk_shape(ctx, dimy, r - 1, ub0, unb, uht, uhb);
+	if(r + 1 < S) blk_shape(ctx, dimy, r + 1, db0, dnb, dht, dhb);
+	const int vlo = b0 - uhb, vhi = b0 + nb + dht;          // bands whose rows this shard will hold
+	ctx->epoch++;
+	ctx->blk_frames++;
+	ctx->barrier_pending = true;
+	const uint32_t lanes_per_band = 32u*32u*(uint32_t)((dimx + 31)/32);
+	const uint32_t target = ctx->blk_frames*lanes_per_band;
+	uint32_t *defer_count = f.flags + 32;
+
+	cudaStream_t bstream = ctx->copy_stream;
+	const unsigned long long tmo = 4000000000ull;
+	// the blur stream must not run ahead of the previous frame's end
+	CU(cudaStreamWaitEvent(bstream, ctx->ev_blk_done, 0));
+	CU(cudaMemsetAsync(defer_count, 0, 4, bstream));      // (the queue is filled on this stream and drained after ev_blk_k2)
+	CU(cudaEventRecord(ctx->ev_k1a, ctx->stream));
+	BlkTrace bt;
+	bt.ht = ht; bt.hb = hb;
+	bt.done_local = f.band_done;
+	if(r > 0) { bt.halo_up = (uint32_t *)(ctx->peer_base[r - 1] + f.off_tsbuf); bt.done_up = (uint32_t *)(ctx->peer_base[r - 1] + f.off_band_done); }
+	if(r + 1 < S) { bt.halo_dn = (uint32_t *)(ctx->peer_base[r + 1] + f.off_tsbuf); bt.done_dn = (uint32_t *)(ctx->peer_base[r + 1] + f.off_band_done); }
+	const int rc_trace = launch_trace(ctx, f, cam + 12, rayb, rdx, rdy, dimx, dimy, sec_current, (flags | PWN_F_BLUR) & ~PWN_F_IDS, false, nullptr, true, 0, -1, &bt);
+	char trace_err[sizeof(g_err)];
+	if(rc_trace != PWN_OK) memcpy(trace_err, g_err, sizeof(g_err));
+	CU(cudaEventRecord(ctx->ev_k1b, ctx->stream));
+	ctx->timed = true;
+	int rc = launch_barrier(ctx, 0);          // A: every shard's trace is complete (k_blur_fix reads their rows)
+	if(rc != PWN_OK) return rc;
+
+	// the blur pass, on the second stream, in groups of bands
+	uint32_t *dst = (flags & PWN_F_LOCAL_BANDS) ? f.sbuf : (uint32_t *)(ctx->peer_base[0] + f.off_sbuf);
+	if(nb > 0 && rc_trace == PWN_OK)
+	{
+		const int h = blk_halo(ctx, dimy);
+		const int group = 2;          // bands per blur launch
+		for(int g0 = b0; g0 < b0 + nb; g0 += group)
+		{
+			const int g1 = (g0 + group < b0 + nb) ? g0 + group : b0 + nb;
+			int w0 = g0 - h, w1 = g1 + h;          // bands this group may read without queueing
+			if(w0 < vlo) w0 = vlo;
+			if(w1 > vhi) w1 = vhi;
+			if(w0 < 0) w0 = 0;
+			if(w1 > nbands) w1 = nbands;
+			WaitParams W;
+			W.done = f.band_done; W.b0 = w0; W.b1 = w1; W.target = target; W.timeout_ns = tmo; W.err = f.flags + 16;
+			k_wait_bands<<<1, 32, 0, bstream>>>(W);
+			CU(cudaGetLastError());
+			BlurParams B = blur_params(ctx, f.tsbuf, f.zbuf, dst, dimx, dimy);
+			B.y0 = g0*32; B.y1 = (g1*32 < dimy) ? g1*32 : dimy;
+			B.ylo = w0*32; B.ylimit = (w1*32 < dimy) ? w1*32 : dimy;
+			B.defer_count = defer_count; B.defer_list = ctx->fs[1].sbuf;
+			if(B.ylo == 0 && B.ylimit >= dimy) B.ylimit = dimy + 1;      // (the whole frame is here: still the coherent loads of the queueing build)
+			k_blur<true><<<dim3((dimx + 255)/256, B.y1 - B.y0), 256, 0, bstream>>>(B);
+			CU(cudaGetLastError());
+			ctx->launches += 2;
+		}
+	}
+	CU(cudaEventRecord(ctx->ev_blk_k2, bstream));
+	CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_blk_k2, 0));
+	if(nb > 0 && rc_trace == PWN_OK)
+	{
+		BlurParams B = blur_params(ctx, f.tsbuf, f.zbuf, dst, dimx, dimy);
+		B.defer_count = defer_count; B.defer_list = ctx->fs[1].sbuf;
+		B.nsh = S;
+		for(int t = 0; t < S; t++) B.src_sh[t] = (const uint32_t *)(ctx->peer_base[t] + f.off_tsbuf);
+		for(int t = 0; t <= S; t++) B.band_start[t] = blk_start(nbands, S, t);
+		k_blur_fix<<<296, 256, 0, ctx->stream>>>(B);
+		CU(cudaGetLastError());
+		ctx->launches++;
+	}
+	rc = launch_barrier(ctx, 1);              // B: the frame on shard 0 is complete; the pre-blur buffers may be rewritten
+	if(rc != PWN_OK) return rc;
+	CU(cudaEventRecord(ctx->ev_k2b, ctx->stream));
+	CU(cudaEventRecord(ctx->ev_blk_done, ctx->stream));
+	ctx->timed_blur = true;
+	if(rc_trace != PWN_OK) { memcpy(g_err, trace_err, sizeof(g_err)); return rc_trace; }
+	return PWN_OK;
+}
+
 extern "C" int pwn_trace_shard_blur(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags)
 {
 	CTX_ENTER(ctx);
 	if(cam == nullptr) return fail(PWN_E_ARG, "pwn_trace_shard_blur: null cam");
 	if(ctx->npeer_shards != ctx->nshards || ctx->nshards < 2) return fail(PWN_E_STATE, "pwn_trace_shard_blur before pwn_frame_peers");
 	if(ctx->r_sbuf || ctx->r_zbuf || ctx->r_tsbuf) return fail(PWN_E_STATE, "pwn_trace_shard_blur with a redirected frame");
-	if(dimx <= 0 || dimy <= 0) return fail(PWN_E_ARG, "pwn_trace_shard_blur: bad size");
+	if(dimx <= 0 || dimy <= 0 || dimx > ctx->rwidth || dimy > ctx->rheight) return fail(PWN_E_ARG, "pwn_trace_shard_blur: bad size");
+	if(ctx->layout == PWN_SHARD_BLOCKS) return trace_shard_blur_blocks(ctx, cam, dimx, dimy, sec_current, flags);
 	float rayb[4], rdx[4], rdy[4];
 	pwn_ray_setup(cam, dimx, dimy, rayb, rdx, rdy);
 	const FrameSet &f = ctx->fs[0];
@@ -860,6 +1064,16 @@ extern "C" int pwn_read_bands(pwn_ctx *ctx, int dimx, int dimy, uint32_t *sbuf_h
 	if(dimx <= 0 || dimy <= 0 || dimx > ctx->rwidth || dimy > ctx->rheight) return fail(PWN_E_ARG, "pwn_read_bands: bad size");
 	const FrameSet &f = ctx->fs[0];
 	const int nbands = (dimy + 31)/32;
+	if(ctx->layout == PWN_SHARD_BLOCKS && ctx->nshards > 1)
+	{
+		int b0, nb, ht, hb;
+		blk_shape(ctx, dimy, ctx->shard, b0, nb, ht, hb);
+		const int y0 = b0*32, y1 = ((b0 + nb)*32 < dimy) ? (b0 + nb)*32 : dimy;
+		if(y1 > y0)
+			CU(cudaMemcpyAsync(sbuf_host_frame + (size_t)y0*ctx->rwidth, f.sbuf + (size_t)y0*ctx->rwidth, (size_t)(y1 - y0)*ctx->rwidth*4,
+				cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	else
 	for(int b = ctx->shard; b < nbands; b += ctx->nshards)
 	{
 		const int y0 = b*32, rows = (dimy - y0 < 32) ? dimy - y0 : 32;
@@ -868,6 +1082,27 @@ extern "C" int pwn_read_bands(pwn_ctx *ctx, int dimx, int dimy, uint32_t *sbuf_h
 	}
 	CU(cudaStreamSynchronize(ctx->stream));
 	return check_peer_barriers(ctx);
+}
+
+// test hook: the barrier flags, the error word and the band counters of frame set 0, read while kernels may be running
+extern "C" int pwn_debug_flags(pwn_ctx *ctx, uint32_t *out, int nwords)
+{
+	CTX_ENTER(ctx);
+	if(out == nullptr || nwords <= 0) return fail(PWN_E_ARG, "pwn_debug_flags: bad arguments");
+	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "no frame configured");
+	const FrameSet &f = ctx->fs[0];
+	const size_t have = (f.bytes - f.off_flags)/4;
+	if((size_t)nwords > have) nwords = (int)have;
+	if(nwords > 1024) nwords = 1024;
+	if(ctx->dbg_stream == nullptr)
+	{
+		CU(cudaStreamCreateWithFlags(&ctx->dbg_stream, cudaStreamNonBlocking));
+		CU(cudaHostAlloc((void **)&ctx->h_dbg, 4096, cudaHostAllocDefault));
+	}
+	CU(cudaMemcpyAsync(ctx->h_dbg, f.flags, (size_t)nwords*4, cudaMemcpyDeviceToHost, ctx->dbg_stream));
+	CU(cudaStreamSynchronize(ctx->dbg_stream));
+	memcpy(out, ctx->h_dbg, (size_t)nwords*4);
+	return nwords;
 }
 
 extern "C" int pwn_frame_peers_status(pwn_ctx *ctx, int *timed_out)

@@ -119,8 +119,30 @@ struct TraceParams
 	int npeers;                // stored there too -- the all-gather the sharded blur pass needs, fused into the trace
 	int rowtile;               // 1: a warp covers 32x1 pixels (128-byte row stores, for frames reached over NVLink) instead of 8x4
 	uint32_t zero;             // always 0; opaque to the compiler (see xmov)
+	// Contiguous-block sharding (pwn_shard_layout PWN_SHARD_BLOCKS): this shard owns the bands [blk_b0, blk_b0 + nbands_local).
+	// Its first blk_ht and last blk_hb bands are the halo the blur pass of the shard above / below reads: they are traced
+	// FIRST and stored into that shard's pre-blur buffer as well.  Every group of lanes that finishes adds its lane count
+	// to the band's counter (here, and for a halo band on the neighbour too), after a fence: the blur pass of a band
+	// starts as soon as the counters of the bands it reads are full -- it runs under the trace of the later bands.
+	int blk, blk_b0, blk_ht, blk_hb;
+	uint32_t *halo_up, *halo_dn;          // pre-blur buffer of the shard above / below (null at the frame's edges)
+	uint32_t *done_local, *done_up, *done_dn;   // band counters, indexed by the band's number in the frame
 	BlurParams prev;           // BLURP builds: the blur pass of the PREVIOUS frame of a pose batch
 };
+
+// this group of lanes is done with band `band`: publish its stores, then count its lanes
+__device__ __forceinline__ void band_arrive(const TraceParams &P, int band, int which /* 0 none, 1 up, 2 down */, bool wrote)
+{
+	const unsigned m = __activemask();
+	if(wrote) { if(which) __threadfence_system(); else __threadfence(); }
+	if((threadIdx.x & 31) == (__ffs(m) - 1))
+	{
+		const unsigned n = __popc(m);
+		atomicAdd(P.done_local + band, n);
+		if(which == 1) atomicAdd_system(P.done_up + band, n);
+		if(which == 2) atomicAdd_system(P.done_dn + band, n);
+	}
+}
 
 // Algorithmic FP32 lane-ops per event (counted from the reference source: mul, add,
 // cmp, abs, cvt, rcp, rsqrt = 1 each, live lanes only).  Only the IDS instantiation counts.
@@ -346,8 +368,18 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 	const int ty = P.rowtile ? warp : (warp >> 2)*4 + (lane >> 3);
 	const int x = blockIdx.x*32 + tx;
 	const int lrow0 = (blockIdx.y + P.band0*(32/K1_ROWS))*K1_ROWS;
-	// local row -> global row through the band interleave (8 | 32: a CTA never straddles bands)
-	const int y0 = ((lrow0 >> 5)*P.nshards + P.shard)*32 + (lrow0 & 31);
+	// local row -> global row (8 | 32: a CTA never straddles bands): through the band interleave, or, for a contiguous
+	// block, in the order top halo, bottom halo, interior
+	int y0, halo = 0;
+	if(P.blk)
+	{
+		const int lb = lrow0 >> 5;
+		int b = lb - P.blk_hb;                                    // interior, after both halos
+		if(lb < P.blk_ht) { b = lb; halo = (P.halo_up != nullptr) ? 1 : 0; }
+		else if(lb < P.blk_ht + P.blk_hb) { b = P.nbands_local - P.blk_hb + (lb - P.blk_ht); halo = (P.halo_dn != nullptr) ? 2 : 0; }
+		y0 = (P.blk_b0 + b)*32 + (lrow0 & 31);
+	}
+	else y0 = ((lrow0 >> 5)*P.nshards + P.shard)*32 + (lrow0 & 31);
 	const int y = y0 + ty;
 
 	// ---- screen.h:12-13,18: rayl = ((rayb + y*rdy) + cx*rdx) + rdx + ... + rdx --------
@@ -368,7 +400,11 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 		}
 	}
 	__syncthreads();
-	if(x >= P.dimx || y >= P.dimy) return;
+	if(x >= P.dimx || y >= P.dimy)
+	{
+		if(P.done_local != nullptr) band_arrive(P, y0 >> 5, halo, false);   // (the counters count every lane of the grid)
+		return;
+	}
 	const uint32_t pix = (uint32_t)y*(uint32_t)P.rwidth + (uint32_t)x;   // (pwn_frame_config keeps rwidth*rheight below 2^31)
 	float irx = s_ray[0][ty][tx], iry = s_ray[1][ty][tx], irz = s_ray[2][ty][tx];
 
@@ -990,6 +1026,12 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 	const uint32_t word = pack_word(ob, og, orr, oa);
 	P.sbuf[pix] = word;
 	for(int p = 0; p < P.npeers; p++) P.peer[p][pix] = word;
+	if(P.done_local != nullptr)
+	{
+		if(halo == 1) P.halo_up[pix] = word;
+		if(halo == 2) P.halo_dn[pix] = word;
+		band_arrive(P, y0 >> 5, halo, true);
+	}
 
 	// ---- pose batches: this thread also blurs its pixel of the previous frame (screen.h:69-123),
 	// whose trace ran in the previous launch.  The launches are chained with programmatic dependent

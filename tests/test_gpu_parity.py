@@ -874,3 +874,113 @@ def test_trace_screen_chunked_pipeline(tracer, oracle):
         tracer.screen_chunks(0)
     with pytest.raises(api.PwnError):
         tracer.screen_chunks(9)
+
+
+@pytest.mark.parametrize("nsh,halo", [(3, 0), (2, 1), (4, 2), (8, 1)])
+def test_sharded_blur_block_layout_in_one_process(tracer, oracle, nsh, halo):
+    """(see block_layout_case)  Every shard parks kernels on the device that spin until its neighbours' work arrives; in
+    ONE process that only works while every stream has a hardware queue of its own (8 by default, two streams per
+    shard): the 4- and 8-shard cases run in a child process with CUDA_DEVICE_MAX_CONNECTIONS=32.  With one process per
+    GPU, as bench.py runs it, a shard waits for other GPUs only."""
+    if nsh <= 3:
+        block_layout_case(tracer, oracle, nsh, halo)
+        return
+    import subprocess
+    import sys
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from oracle import orcbind\nfrom pwnfps_b200 import api\nimport test_gpu_parity as T\n"
+            "t = api.Tracer(0)\nT.block_layout_case(t, orcbind.Oracle(), %d, %d)\nt.close()\nprint('block layout ok')\n"
+            % (os.path.dirname(GOLDEN.rstrip('/')), os.path.dirname(os.path.dirname(GOLDEN.rstrip('/'))), nsh, halo))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "block layout ok" in out.stdout, (out.stdout[-2000:], out.stderr[-3000:])
+
+
+def block_layout_case(tracer, oracle, nsh, halo):
+    """PWN_SHARD_BLOCKS: a frame sharded in contiguous band blocks WITH the blur pass -- halo bands traced first and
+    stored into the neighbour's pre-blur buffer, per-band lane counters, blur launches gated on the device by the
+    counters and running under the trace, far samples finished from the owning shard's rows.  `nsh` contexts on one
+    GPU stand in for `nsh` GPUs.  Result = the one-context blurred frame = the oracle's, bit for bit, frame after
+    frame; also with a halo too small for the scene (every far sample then goes through k_blur_fix) and with ragged
+    frame sizes."""
+    lv = levels.mirror_hall()                  # far surfaces: blur samples reach beyond any small halo
+    ts = [tracer] + [api.Tracer(0) for _ in range(nsh - 1)]
+    try:
+        cam0 = api.cam_spawn(lv)
+        for (rw, rh, w, h) in [(640, 360, 640, 360), (416, 300, 402, 290)]:
+            cams = [api.mat4_roty(cam0, a) for a in (1.5707964, 0.4, 4.1)]
+            oracle_set_level(oracle, lv)
+            want = []
+            for k, cam in enumerate(cams):
+                so, zo, _ = oracle.trace_frame(cam, 0.3 * k, w, h, rwidth=rw)
+                want.append(oracle.blur(so, zo, w, h, rwidth=rw))
+            for t in ts:
+                t.level_upload(lv)
+                t.level_prepare_render(lv)
+                t.frame_config(rw, rh)
+                t.frame_clear()
+            bases = [t.device_ptrs()[0] for t in ts]       # sbuf is at offset 0 of the frame allocation
+            for r, t in enumerate(ts):
+                t.shard_config(nsh, r)
+                t.shard_layout(blocks=True, halo_bands=halo)
+                t.frame_peers(bases)
+            for k, cam in enumerate(cams):
+                for t in ts:
+                    t.trace_shard_blur(cam, w, h, 0.3 * k)
+                for t in ts:
+                    t.sync()
+                assert not any(t.peers_timed_out() for t in ts)
+                got = ts[0].read_frame(want_z=False)[0]
+                assert (got[:h, :w] == want[k][:, :w]).all(), (nsh, halo, w, h, k, int((got[:h, :w] != want[k][:, :w]).sum()))
+            # the host-assembled variant: blurred blocks stay on their shard, every shard copies its own rows
+            host = np.zeros((rh, rw), np.uint32)
+            api.host_register(host)
+            try:
+                for t in ts:
+                    t.trace_shard_blur(cams[1], w, h, 0.3, api.PWN_F_LOCAL_BANDS)
+                for t in ts:
+                    t.read_bands(w, h, host)
+                assert (host[:h, :w] == want[1][:, :w]).all()
+            finally:
+                api.host_unregister(host)
+            for t in ts:
+                t.frame_peers(None)
+    finally:
+        for t in ts:
+            t.frame_peers(None)
+            t.shard_layout(blocks=False)
+            t.shard_config(1, 0)
+        for t in ts[1:]:
+            t.close()
+
+
+def test_block_layout_plain_trace_stitches(tracer, default_level):
+    """PWN_SHARD_BLOCKS without the blur: the blocks of all shards make up the one-shard frame"""
+    tracer.level_upload(default_level)
+    tracer.level_prepare_render()
+    cam = api.mat4_roty(api.cam_spawn(default_level), 2.0)
+    w, h = 640, 361
+    tracer.frame_config(w, h)
+    tracer.shard_config(1, 0)
+    tracer.frame_clear()
+    tracer.trace_cam(cam, w, h, 0.0, 0)
+    full, zfull, _ = tracer.read_frame()
+    try:
+        for n in (2, 3, 8, 16):
+            acc = np.zeros_like(full)
+            zacc = np.zeros_like(zfull)
+            nb = (h + 31) // 32
+            for r in range(n):
+                tracer.shard_config(n, r)
+                tracer.shard_layout(blocks=True)
+                tracer.frame_clear()
+                tracer.trace_cam(cam, w, h, 0.0, 0)
+                s, z, _ = tracer.read_frame()
+                y0, y1 = min(h, (r * nb // n) * 32), min(h, ((r + 1) * nb // n) * 32)
+                assert (s[:y0] == 0).all() and (s[y1:] == 0).all()
+                acc[y0:y1] = s[y0:y1]
+                zacc[y0:y1] = z[y0:y1]
+            assert (acc == full).all() and (zacc.view(np.uint32) == zfull.view(np.uint32)).all()
+    finally:
+        tracer.shard_layout(blocks=False)
+        tracer.shard_config(1, 0)
