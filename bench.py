@@ -445,6 +445,7 @@ def run_ours(args, rank, world, local_rank):
         def step_device():
             for p in poses:
                 one_frame(p)
+            tr.join()          # (two frames are in flight on two streams: the step's closing event comes after both)
 
     # ---- value: frames stay in HBM -----------------------------------------------------
     for _ in range(warm):

@@ -195,6 +195,14 @@ int pwn_shard_config(pwn_ctx *ctx, int nshards, int shard);
  */
 enum { PWN_SHARD_INTERLEAVED = 0, PWN_SHARD_BLOCKS = 1 };
 int pwn_shard_layout(pwn_ctx *ctx, int layout, int halo_bands);
+/*
+ * Block layout: explicit boundaries.  band_start[s] is the first band of shard s, band_start[nshards] the number of
+ * bands of the frame ((dimy + 31)/32; boundaries given for another height are ignored).  Rows differ in cost (the
+ * floor below the horizon carries the wavy-normal bounce, trace.h:39-56): a harness times the blocks and moves the
+ * boundaries until the shards finish together (pwnfps_b200/shard.py: balance_blocks).  Every shard must be given the
+ * same boundaries.  NULL restores the even split.
+ */
+int pwn_shard_blocks(pwn_ctx *ctx, int nshards, const int32_t *band_start);
 
 /* ---- the hot path ------------------------------------------------------------------ */
 /*
@@ -226,8 +234,14 @@ int pwn_trace_cam(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float s
 /* the ray basis alone (screen.h:43-57): exposed so a host can check it against its own build */
 void pwn_ray_setup(const float cam[16], int dimx, int dimy, float rayb[4], float rdx[4], float rdy[4]);
 
-/* wait for the context's stream */
+/* wait for the context's streams */
 int pwn_sync(pwn_ctx *ctx);
+/*
+ * Sharded frames of the block layout keep two frames in flight on two streams.  pwn_join makes everything the library
+ * has queued so far a predecessor of whatever comes next on pwn_stream (an event recorded there afterwards marks the
+ * completion of every frame submitted before it); no host wait.
+ */
+int pwn_join(pwn_ctx *ctx);
 
 /* device -> host; any pointer may be NULL.  Full frames: rwidth*rheight elements (ids: x3). Synchronous. */
 int pwn_read_frame(pwn_ctx *ctx, uint32_t *sbuf, float *zbuf, pwn_ids *ids);
@@ -296,6 +310,8 @@ int pwn_frame_ipc_close(pwn_ctx *ctx, uint64_t base_dev);
  * counting finished lanes per band; on a second stream the blur pass follows two bands at a time, each launch gated on the
  * device by the counters of the bands it reads, and stores straight into shard 0's frame -- the gather to GPU 0 runs under
  * the trace.  Samples beyond the exchanged rows are finished from the owning shard's rows after a device barrier.
+ * Frames alternate between two groups of planes: the call for frame n+1 may be made at once, its trace runs while frame
+ * n is still being blurred and gathered (pwn_sync / pwn_read_frame / pwn_join wait for or order after both).
  *
  * Interleaved layout: screen.h:69-123 gathers from anywhere in the pre-blur
  * frame, so every shard needs all of it: with pwn_frame_peers set, pwn_trace_shard_blur

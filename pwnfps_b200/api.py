@@ -63,7 +63,7 @@ ABI_SYMBOLS = [
     "pwn_screen_upscale", "pwn_surface_device_ptr", "pwn_last_upscale_ms", "pwn_trace_config",
     "pwn_frame_peers", "pwn_trace_shard_blur", "pwn_frame_peers_status",
     "pwn_host_register", "pwn_host_unregister", "pwn_debug_pack", "pwn_write_frame", "pwn_read_bands",
-    "pwn_math_status", "pwn_screen_chunks", "pwn_shard_layout", "pwn_debug_flags",
+    "pwn_math_status", "pwn_screen_chunks", "pwn_shard_layout", "pwn_debug_flags", "pwn_shard_blocks", "pwn_join",
 ]
 
 
@@ -130,6 +130,8 @@ def lib():
     L.pwn_screen_chunks.argtypes = [vp, i]
     L.pwn_shard_layout.argtypes = [vp, i, i]
     L.pwn_debug_flags.argtypes = [vp, vp, i]
+    L.pwn_shard_blocks.argtypes = [vp, i, vp]
+    L.pwn_join.argtypes = [vp]
     _lib = L
     return L
 
@@ -561,6 +563,10 @@ class Tracer:
     def sync(self):
         _check(self.L.pwn_sync(self.h))
 
+    def join(self):
+        """order everything queued so far (also on the library's second stream) before what follows on stream_ptr()"""
+        _check(self.L.pwn_join(self.h))
+
     def debug_pack(self, bgra):
         """the device's col_ftoint (util.h:48-59) on (n,4) float32 BGRA rows -> (n,) uint32"""
         v = np.ascontiguousarray(bgra, dtype=np.float32).reshape(-1, 4)
@@ -621,6 +627,14 @@ class Tracer:
                                        PWN_F_BLUR if blur else 0, sbuf.ctypes.data,
                                        zbuf.ctypes.data if zbuf is not None else None))
         return sbuf
+
+    def shard_blocks(self, band_start=None):
+        """block layout: first band of every shard + the frame's band count (nshards + 1 ints); None = even split"""
+        if band_start is None:
+            _check(self.L.pwn_shard_blocks(self.h, 0, None))
+            return
+        b = np.ascontiguousarray(band_start, dtype=np.int32)
+        _check(self.L.pwn_shard_blocks(self.h, len(b) - 1, b.ctypes.data))
 
     def screen_chunks(self, nchunks=0):
         """row chunks per frame of trace_screen_centred (0 = automatic)"""

@@ -113,7 +113,7 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 	if((x & ~3) >= P.dimx - 3)
 	{
 		// the last dimx%4 pixels are not blurred (screen.h:88-91)
-		P.dst[pix] = (DEFER || PEER) ? __ldcg(&P.src[pix]) : P.src[pix];
+		P.dst[pix] = P.src[pix];
 		return;
 	}
 	// the row's stream (seed = cy*cy + 415135, screen.h:82) advanced to draw 32*g + 2*j
@@ -123,7 +123,7 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 	// masks before it takes the remainder)
 	seed = c_jumpA[j]*seed + c_jumpC[j];
 
-	const float z = __fsub_rn(DEFER || PEER ? __ldcg(&P.zbuf[pix]) : P.zbuf[pix], 1.0f);
+	const float z = __fsub_rn(P.zbuf[pix], 1.0f);
 	const bf32x2 base = bpk2((float)x, (float)y);
 	const float negz = __uint_as_float(0x80000000u ^ (P.zero & (uint32_t)x));   // -0.0f ptxas cannot fold
 	const bf32x2 nz = bpk2(negz, negz);
@@ -149,10 +149,11 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 			P.defer_list[atomicAdd(P.defer_count, 1u)] = pix;
 			return;
 		}
-		// (through L2: the rows are written by a trace that runs beside this kernel, here or on the neighbouring GPU;
-		// the non-coherent path and L1 may only serve data nobody writes during the launch)
+		// (plain loads, not the non-coherent path: other rows of src are being written by a trace that runs beside this
+		// kernel.  The rows read here were released by their writers before the stream-ordered wait that precedes this
+		// launch acquired their counters, so they happen-before every load of this kernel.)
 		#pragma unroll
-		for(int i = 0; i < 4; i++) s[i] = __ldcg(&P.src[at[i]]);
+		for(int i = 0; i < 4; i++) s[i] = P.src[at[i]];
 	}
 	else if(PEER)
 	{
@@ -169,7 +170,7 @@ __device__ __forceinline__ void blur_pixel(const BlurParams &P, int x, int y)
 				while(o + 1 < P.nsh && sb >= P.band_start[o + 1]) o++;
 				src = P.src_sh[o];
 			}
-			s[i] = __ldcg(&src[(uint32_t)sy*(uint32_t)P.rwidth + (uint32_t)sx]);
+			s[i] = src[(uint32_t)sy*(uint32_t)P.rwidth + (uint32_t)sx];
 			seed = a6*seed + c6;
 		}
 	}

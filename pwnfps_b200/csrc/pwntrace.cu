@@ -59,6 +59,9 @@ struct FrameSet
 	uint32_t *flags = nullptr; // 64 words after the planes: inter-GPU barrier flags (k_peer_barrier); then one counter per band
 	uint32_t *band_done = nullptr;   // (contiguous-block sharding: lanes that have finished the band, summed over the frames so far)
 	size_t off_sbuf = 0, off_tsbuf = 0, off_zbuf = 0, off_flags = 0, off_band_done = 0, bytes = 0;
+	// frame set 0 only: a second group sbuf | tsbuf | zbuf | band counters at off_alt (same offsets inside the group), so that
+	// two sharded frames can be in flight (block layout: the trace of frame n+1 runs under the blur and gather of frame n)
+	size_t off_alt = 0, group_bytes = 0;
 };
 
 struct pwn_ctx
@@ -113,8 +116,10 @@ struct pwn_ctx
 	int nshards = 1, shard = 0;
 	int layout = PWN_SHARD_INTERLEAVED;
 	int halo_bands = 0;        // contiguous blocks: bands exchanged with each neighbour, 0 = from the frame height
+	std::vector<int> blk_bounds;   // contiguous blocks: first band of every shard + the band count (pwn_shard_blocks), or empty
 	uint32_t blk_frames = 0;   // sharded frames traced in the block layout since pwn_frame_peers (the band counters' epoch)
-	cudaEvent_t ev_blk_k2 = nullptr, ev_blk_done = nullptr;
+	cudaEvent_t ev_blk_k1[2] = {nullptr, nullptr}, ev_blk_done[2] = {nullptr, nullptr};
+	int blk_par = 0;           // which group of frame set 0 holds the latest sharded frame of the block layout
 	int reflect = 2;           // REFLECT as shipped (defs.h:8)
 	int screen_chunks = 0;     // pwn_trace_screen: row chunks per frame, 0 = automatic
 	// sharded frame with the blur pass: the other shards' frame allocations (pwn_frame_peers)
@@ -185,7 +190,13 @@ extern "C" int pwn_create(pwn_ctx **out, int device)
 	CU(cudaSetDevice(device));
 	{ int rc = preload_kernels(); if(rc != PWN_OK) return rc; }
 	CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-	CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+	{
+		// the second stream carries copies and, for sharded frames, the blur launches that run under the trace: with the
+		// higher priority their few CTAs are placed ahead of the trace's pending ones whenever an SM has room
+		int lo = 0, hi = 0;
+		CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		CU(cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, hi));
+	}
 	CU(cudaEventCreate(&ctx->ev_k1a));
 	CU(cudaEventCreate(&ctx->ev_k1b));
 	CU(cudaEventCreate(&ctx->ev_k2b));
@@ -197,8 +208,11 @@ extern "C" int pwn_create(pwn_ctx **out, int device)
 		CU(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
 	}
 	for(int i = 0; i < 16; i++) CU(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
-	CU(cudaEventCreateWithFlags(&ctx->ev_blk_k2, cudaEventDisableTiming));
-	CU(cudaEventCreateWithFlags(&ctx->ev_blk_done, cudaEventDisableTiming));
+	for(int i = 0; i < 2; i++)
+	{
+		CU(cudaEventCreateWithFlags(&ctx->ev_blk_k1[i], cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&ctx->ev_blk_done[i], cudaEventDisableTiming));
+	}
 	CU(cudaHostAlloc((void **)&ctx->h_defer, 64, cudaHostAllocDefault));
 	ctx->h_defer[0] = 0;
 
@@ -241,8 +255,7 @@ extern "C" int pwn_destroy(pwn_ctx *ctx)
 		ctx->ev_copied[0], ctx->ev_copied[1], ctx->ev_copied[2]};
 	for(cudaEvent_t e : evs) if(e) cudaEventDestroy(e);
 	for(cudaEvent_t e : ctx->ev_chunk) if(e) cudaEventDestroy(e);
-	if(ctx->ev_blk_k2) cudaEventDestroy(ctx->ev_blk_k2);
-	if(ctx->ev_blk_done) cudaEventDestroy(ctx->ev_blk_done);
+	for(int i = 0; i < 2; i++) { if(ctx->ev_blk_k1[i]) cudaEventDestroy(ctx->ev_blk_k1[i]); if(ctx->ev_blk_done[i]) cudaEventDestroy(ctx->ev_blk_done[i]); }
 	if(ctx->h_defer) cudaFreeHost(ctx->h_defer);
 	if(ctx->h_dbg) cudaFreeHost(ctx->h_dbg);
 	if(ctx->dbg_stream) cudaStreamDestroy(ctx->dbg_stream);
@@ -608,7 +621,9 @@ extern "C" int pwn_frame_config(pwn_ctx *ctx, int rwidth, int rheight, int want_
 		{
 			FrameSet &f = ctx->fs[i];
 			const size_t nbands = ((size_t)rheight + 31)/32;
-			f.bytes = 3*plane + 256 + align_up(4*(nbands + 1), 256);
+			f.group_bytes = 3*plane + 256 + align_up(4*(nbands + 1), 256);
+			f.bytes = f.group_bytes*(i == 0 ? 2 : 1);
+			f.off_alt = (i == 0) ? f.group_bytes : 0;
 			CU(cudaMalloc(&f.base, f.bytes));
 			f.off_sbuf = 0; f.off_tsbuf = plane; f.off_zbuf = 2*plane; f.off_flags = 3*plane; f.off_band_done = 3*plane + 256;
 			f.flags = (uint32_t *)((char *)f.base + f.off_flags);
@@ -647,6 +662,7 @@ extern "C" int pwn_frame_clear(pwn_ctx *ctx)
 	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "pwn_frame_clear before pwn_frame_config");
 	// the planes only: the barrier flags behind them carry the epoch of the last sharded frame
 	for(int i = 0; i < 3; i++) CU(cudaMemsetAsync(ctx->fs[i].base, 0, ctx->fs[i].off_flags, ctx->stream));
+	CU(cudaMemsetAsync((char *)ctx->fs[0].base + ctx->fs[0].off_alt, 0, ctx->fs[0].off_flags, ctx->stream));
 	if(ctx->d_ids) CU(cudaMemsetAsync(ctx->d_ids, 0xFF, (size_t)ctx->rwidth*ctx->rheight*3*sizeof(pwn_ids), ctx->stream));
 	return PWN_OK;
 }
@@ -660,6 +676,18 @@ extern "C" int pwn_shard_layout(pwn_ctx *ctx, int layout, int halo_bands)
 	return PWN_OK;
 }
 
+extern "C" int pwn_shard_blocks(pwn_ctx *ctx, int nshards, const int32_t *band_start)
+{
+	if(ctx == nullptr) return fail(PWN_E_ARG, "null context");
+	if(band_start == nullptr || nshards == 0) { ctx->blk_bounds.clear(); return PWN_OK; }
+	if(nshards < 1 || nshards > 8) return fail(PWN_E_ARG, "pwn_shard_blocks: %d shards", nshards);
+	if(band_start[0] != 0) return fail(PWN_E_ARG, "pwn_shard_blocks: the first block starts at band %d", band_start[0]);
+	for(int t = 0; t < nshards; t++)
+		if(band_start[t + 1] < band_start[t]) return fail(PWN_E_ARG, "pwn_shard_blocks: boundaries must not decrease");
+	ctx->blk_bounds.assign(band_start, band_start + nshards + 1);
+	return PWN_OK;
+}
+
 extern "C" int pwn_shard_config(pwn_ctx *ctx, int nshards, int shard)
 {
 	if(ctx == nullptr) return fail(PWN_E_ARG, "null context");
@@ -669,7 +697,12 @@ extern "C" int pwn_shard_config(pwn_ctx *ctx, int nshards, int shard)
 }
 
 // ---- contiguous-block sharding (PWN_SHARD_BLOCKS): who owns which bands, and which of them are halo -------------
-static int blk_start(int nbands, int nshards, int s) { return (int)((long long)s*nbands/nshards); }
+static int blk_start(const pwn_ctx *ctx, int nbands, int s)
+{
+	// explicit boundaries (pwn_shard_blocks), valid for the frame height they were given for; else an even split
+	if((int)ctx->blk_bounds.size() == ctx->nshards + 1 && ctx->blk_bounds[ctx->nshards] == nbands) return ctx->blk_bounds[s];
+	return (int)((long long)s*nbands/ctx->nshards);
+}
 
 static int blk_halo(const pwn_ctx *ctx, int dimy)
 {
@@ -684,8 +717,8 @@ static int blk_halo(const pwn_ctx *ctx, int dimy)
 static void blk_shape(const pwn_ctx *ctx, int dimy, int s, int &b0, int &nb, int &ht, int &hb)
 {
 	const int nbands = (dimy + 31)/32, h = blk_halo(ctx, dimy);
-	b0 = blk_start(nbands, ctx->nshards, s);
-	nb = blk_start(nbands, ctx->nshards, s + 1) - b0;
+	b0 = blk_start(ctx, nbands, s);
+	nb = blk_start(ctx, nbands, s + 1) - b0;
 	ht = (s > 0) ? (h < nb ? h : nb) : 0;
 	hb = (s + 1 < ctx->nshards) ? (h < nb - ht ? h : nb - ht) : 0;
 }
@@ -803,7 +836,7 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 	P.reflect = ctx->reflect;
 	// a redirected frame lives on another GPU: whole 128-byte row segments per warp store cross NVLink
 	// at about twice the rate of the four 32-byte pieces an 8x4 warp tile would send
-	P.rowtile = (ctx->r_sbuf != nullptr) ? 1 : 0;
+	P.rowtile = (ctx->r_sbuf != nullptr || (blk != nullptr && (blk->halo_up != nullptr || blk->halo_dn != nullptr))) ? 1 : 0;
 	if(ctx->allgather_now)
 	{
 		P.sbuf = f.tsbuf; P.zbuf = f.zbuf;
@@ -857,7 +890,9 @@ static int reset_band_counters(pwn_ctx *ctx)
 	const FrameSet &f = ctx->fs[0];
 	CU(cudaStreamSynchronize(ctx->stream));
 	CU(cudaStreamSynchronize(ctx->copy_stream));
-	CU(cudaMemset(f.flags, 0, f.bytes - f.off_flags));
+	CU(cudaMemset(f.flags, 0, f.group_bytes - f.off_flags));
+	CU(cudaMemset((char *)f.base + f.off_alt + f.off_flags, 0, f.group_bytes - f.off_flags));
+	ctx->blk_par = 0;
 	return PWN_OK;
 }
 
@@ -883,7 +918,7 @@ extern "C" int pwn_frame_peers(pwn_ctx *ctx, int nshards, const uint64_t *base_d
 	return PWN_OK;
 }
 
-static int launch_barrier(pwn_ctx *ctx, int slot)
+static int launch_barrier(pwn_ctx *ctx, int slot, cudaStream_t st = nullptr)
 {
 	BarrierParams B;
 	memset(&B, 0, sizeof(B));
@@ -891,23 +926,25 @@ static int launch_barrier(pwn_ctx *ctx, int slot)
 	B.local = ctx->fs[0].flags;
 	B.nshards = ctx->nshards; B.shard = ctx->shard; B.slot = slot; B.epoch = ctx->epoch;
 	B.timeout_ns = 4000000000ull;
-	k_peer_barrier<<<1, 32, 0, ctx->stream>>>(B);
+	k_peer_barrier<<<1, 32, 0, st ? st : ctx->stream>>>(B);
 	CU(cudaGetLastError());
 	ctx->launches++;
 	return PWN_OK;
 }
 
-// A sharded frame WITH the blur pass in the contiguous-block layout.  One K1 launch traces the shard's bands, halo bands
-// first, storing those into the neighbour's pre-blur buffer as well and counting finished lanes per band; on the second
-// stream the blur pass follows band group by band group, each gated by a one-warp kernel that waits for the counters of
-// the bands it reads, and stores straight into shard 0's frame -- so the gather to GPU 0 runs under the trace.  Samples
-// that reach beyond the exchanged rows are queued and finished by k_blur_fix from the owning shard's rows once every
-// shard's trace is complete (barrier A); barrier B closes the frame.
+// A sharded frame WITH the blur pass in the contiguous-block layout.  Stream 1: one K1 launch per frame traces the shard's
+// bands, halo bands first, storing those into the neighbour's pre-blur buffer as well and counting finished lanes per band.
+// Stream 2: the blur pass follows band group by band group, each launch gated by a one-warp kernel that waits for the
+// counters of the bands it reads, and stores straight into shard 0's frame; then barrier A (every shard's trace of this
+// frame is complete), k_blur_fix (samples that reached beyond the exchanged rows, read from the owning shard), barrier B
+// (the frame on shard 0 is complete).  Frames alternate between two groups of planes, so stream 1 goes on with the trace of
+// frame n+1 while stream 2 still blurs and gathers frame n: per frame the GPU does the trace and the blur, and GPU 0's
+// NVLink ingest (the frame's 4 bytes per pixel) runs under both.  K1 of frame n+2 waits for barrier B of frame n.
 static int trace_shard_blur_blocks(pwn_ctx *ctx, const float cam[16], int dimx, int dimy, float sec_current, unsigned flags)
 {
 	float rayb[4], rdx[4], rdy[4];
 	pwn_ray_setup(cam, dimx, dimy, rayb, rdx, rdy);
-	const FrameSet &f = ctx->fs[0];
+	const FrameSet &f0 = ctx->fs[0];
 	const int nbands = (dimy + 31)/32, S = ctx->nshards, r = ctx->shard;
 	int b0, nb, ht, hb;
 	blk_shape(ctx, dimy, r, b0, nb, ht, hb);
@@ -919,35 +956,43 @@ static int trace_shard_blur_blocks(pwn_ctx *ctx, const float cam[16], int dimx, 
 	ctx->epoch++;
 	ctx->blk_frames++;
 	ctx->barrier_pending = true;
+	const int par = (int)((ctx->blk_frames - 1) & 1u);
+	const size_t alt = par ? f0.off_alt : 0;      // this frame's group of planes (the same offset on every shard)
+	ctx->blk_par = par;
+	FrameSet f = f0;                               // a view of that group
+	f.sbuf = (uint32_t *)((char *)f0.base + alt + f0.off_sbuf);
+	f.tsbuf = (uint32_t *)((char *)f0.base + alt + f0.off_tsbuf);
+	f.zbuf = (float *)((char *)f0.base + alt + f0.off_zbuf);
+	f.band_done = (uint32_t *)((char *)f0.base + alt + f0.off_band_done);
 	const uint32_t lanes_per_band = 32u*32u*(uint32_t)((dimx + 31)/32);
-	const uint32_t target = ctx->blk_frames*lanes_per_band;
-	uint32_t *defer_count = f.flags + 32;
-
-	cudaStream_t bstream = ctx->copy_stream;
+	const uint32_t target = ((ctx->blk_frames + 1)/2)*lanes_per_band;      // frames that have used this group, this one included
+	uint32_t *defer_count = f0.flags + 32;
+	cudaStream_t s1 = ctx->stream, s2 = ctx->copy_stream;
 	const unsigned long long tmo = 4000000000ull;
-	// the blur stream must not run ahead of the previous frame's end
-	CU(cudaStreamWaitEvent(bstream, ctx->ev_blk_done, 0));
-	CU(cudaMemsetAsync(defer_count, 0, 4, bstream));      // (the queue is filled on this stream and drained after ev_blk_k2)
-	CU(cudaEventRecord(ctx->ev_k1a, ctx->stream));
+
+	// ---- stream 1: the trace ----
+	CU(cudaStreamWaitEvent(s1, ctx->ev_blk_done[par], 0));     // the frame before last used these planes: its barrier B
+	CU(cudaEventRecord(ctx->ev_k1a, s1));
 	BlkTrace bt;
 	bt.ht = ht; bt.hb = hb;
 	bt.done_local = f.band_done;
-	if(r > 0) { bt.halo_up = (uint32_t *)(ctx->peer_base[r - 1] + f.off_tsbuf); bt.done_up = (uint32_t *)(ctx->peer_base[r - 1] + f.off_band_done); }
-	if(r + 1 < S) { bt.halo_dn = (uint32_t *)(ctx->peer_base[r + 1] + f.off_tsbuf); bt.done_dn = (uint32_t *)(ctx->peer_base[r + 1] + f.off_band_done); }
+	if(r > 0) { bt.halo_up = (uint32_t *)(ctx->peer_base[r - 1] + alt + f0.off_tsbuf); bt.done_up = (uint32_t *)(ctx->peer_base[r - 1] + alt + f0.off_band_done); }
+	if(r + 1 < S) { bt.halo_dn = (uint32_t *)(ctx->peer_base[r + 1] + alt + f0.off_tsbuf); bt.done_dn = (uint32_t *)(ctx->peer_base[r + 1] + alt + f0.off_band_done); }
 	const int rc_trace = launch_trace(ctx, f, cam + 12, rayb, rdx, rdy, dimx, dimy, sec_current, (flags | PWN_F_BLUR) & ~PWN_F_IDS, false, nullptr, true, 0, -1, &bt);
 	char trace_err[sizeof(g_err)];
 	if(rc_trace != PWN_OK) memcpy(trace_err, g_err, sizeof(g_err));
-	CU(cudaEventRecord(ctx->ev_k1b, ctx->stream));
+	CU(cudaEventRecord(ctx->ev_k1b, s1));
+	CU(cudaEventRecord(ctx->ev_blk_k1[par], s1));
 	ctx->timed = true;
-	int rc = launch_barrier(ctx, 0);          // A: every shard's trace is complete (k_blur_fix reads their rows)
-	if(rc != PWN_OK) return rc;
 
-	// the blur pass, on the second stream, in groups of bands
-	uint32_t *dst = (flags & PWN_F_LOCAL_BANDS) ? f.sbuf : (uint32_t *)(ctx->peer_base[0] + f.off_sbuf);
+	// ---- stream 2: the blur pass in groups of bands, the barriers, the fix ----
+	uint32_t *dst = (flags & PWN_F_LOCAL_BANDS) ? f.sbuf : (uint32_t *)(ctx->peer_base[0] + alt + f0.off_sbuf);
+	CU(cudaMemsetAsync(defer_count, 0, 4, s2));      // (the queue is filled and drained on this stream, frame after frame)
 	if(nb > 0 && rc_trace == PWN_OK)
 	{
 		const int h = blk_halo(ctx, dimy);
-		const int group = 2;          // bands per blur launch
+		int group = (nb + 7)/8;       // bands per blur launch: about eight launches per frame
+		if(group < 2) group = 2;
 		for(int g0 = b0; g0 < b0 + nb; g0 += group)
 		{
 			const int g1 = (g0 + group < b0 + nb) ? g0 + group : b0 + nb;
@@ -957,38 +1002,51 @@ static int trace_shard_blur_blocks(pwn_ctx *ctx, const float cam[16], int dimx, 
 			if(w0 < 0) w0 = 0;
 			if(w1 > nbands) w1 = nbands;
 			WaitParams W;
-			W.done = f.band_done; W.b0 = w0; W.b1 = w1; W.target = target; W.timeout_ns = tmo; W.err = f.flags + 16;
-			k_wait_bands<<<1, 32, 0, bstream>>>(W);
+			W.done = f.band_done; W.b0 = w0; W.b1 = w1; W.target = target; W.timeout_ns = tmo; W.err = f0.flags + 16;
+			k_wait_bands<<<1, 32, 0, s2>>>(W);
 			CU(cudaGetLastError());
 			BlurParams B = blur_params(ctx, f.tsbuf, f.zbuf, dst, dimx, dimy);
 			B.y0 = g0*32; B.y1 = (g1*32 < dimy) ? g1*32 : dimy;
 			B.ylo = w0*32; B.ylimit = (w1*32 < dimy) ? w1*32 : dimy;
 			B.defer_count = defer_count; B.defer_list = ctx->fs[1].sbuf;
-			if(B.ylo == 0 && B.ylimit >= dimy) B.ylimit = dimy + 1;      // (the whole frame is here: still the coherent loads of the queueing build)
-			k_blur<true><<<dim3((dimx + 255)/256, B.y1 - B.y0), 256, 0, bstream>>>(B);
+			if(B.ylo == 0 && B.ylimit >= dimy) B.ylimit = dimy + 1;      // (the whole frame is here: still the queueing build, which reads with plain loads)
+			k_blur<true><<<dim3((dimx + 255)/256, B.y1 - B.y0), 256, 0, s2>>>(B);
 			CU(cudaGetLastError());
 			ctx->launches += 2;
 		}
 	}
-	CU(cudaEventRecord(ctx->ev_blk_k2, bstream));
-	CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_blk_k2, 0));
+	CU(cudaStreamWaitEvent(s2, ctx->ev_blk_k1[par], 0));      // the own trace of this frame is complete
+	int rc = launch_barrier(ctx, 0, s2);          // A: every shard's trace and blur launches of this frame are complete
+	if(rc != PWN_OK) return rc;
 	if(nb > 0 && rc_trace == PWN_OK)
 	{
 		BlurParams B = blur_params(ctx, f.tsbuf, f.zbuf, dst, dimx, dimy);
 		B.defer_count = defer_count; B.defer_list = ctx->fs[1].sbuf;
 		B.nsh = S;
-		for(int t = 0; t < S; t++) B.src_sh[t] = (const uint32_t *)(ctx->peer_base[t] + f.off_tsbuf);
-		for(int t = 0; t <= S; t++) B.band_start[t] = blk_start(nbands, S, t);
-		k_blur_fix<<<296, 256, 0, ctx->stream>>>(B);
+		for(int t = 0; t < S; t++) B.src_sh[t] = (const uint32_t *)(ctx->peer_base[t] + alt + f0.off_tsbuf);
+		for(int t = 0; t <= S; t++) B.band_start[t] = blk_start(ctx, nbands, t);
+		k_blur_fix<<<296, 256, 0, s2>>>(B);
 		CU(cudaGetLastError());
 		ctx->launches++;
 	}
-	rc = launch_barrier(ctx, 1);              // B: the frame on shard 0 is complete; the pre-blur buffers may be rewritten
+	rc = launch_barrier(ctx, 1, s2);              // B: the frame on shard 0 is complete; these planes may be rewritten
 	if(rc != PWN_OK) return rc;
-	CU(cudaEventRecord(ctx->ev_k2b, ctx->stream));
-	CU(cudaEventRecord(ctx->ev_blk_done, ctx->stream));
+	CU(cudaEventRecord(ctx->ev_k2b, s2));
+	CU(cudaEventRecord(ctx->ev_blk_done[par], s2));
 	ctx->timed_blur = true;
 	if(rc_trace != PWN_OK) { memcpy(g_err, trace_err, sizeof(g_err)); return rc_trace; }
+	return PWN_OK;
+}
+
+// Work the library has put on its second stream (the blur pass and the barriers of sharded frames in the block layout)
+// becomes part of the first: what the caller records or launches on pwn_stream afterwards comes after it.
+extern "C" int pwn_join(pwn_ctx *ctx)
+{
+	CTX_ENTER(ctx);
+	ScopedEvent e;
+	CU(cudaEventCreateWithFlags(&e.e, cudaEventDisableTiming));
+	CU(cudaEventRecord(e.e, ctx->copy_stream));
+	CU(cudaStreamWaitEvent(ctx->stream, e.e, 0));
 	return PWN_OK;
 }
 
@@ -1069,8 +1127,10 @@ extern "C" int pwn_read_bands(pwn_ctx *ctx, int dimx, int dimy, uint32_t *sbuf_h
 		int b0, nb, ht, hb;
 		blk_shape(ctx, dimy, ctx->shard, b0, nb, ht, hb);
 		const int y0 = b0*32, y1 = ((b0 + nb)*32 < dimy) ? (b0 + nb)*32 : dimy;
+		const size_t alt = (ctx->blk_par && ctx->blk_frames > 0) ? f.off_alt : 0;
+		CU(cudaStreamSynchronize(ctx->copy_stream));
 		if(y1 > y0)
-			CU(cudaMemcpyAsync(sbuf_host_frame + (size_t)y0*ctx->rwidth, f.sbuf + (size_t)y0*ctx->rwidth, (size_t)(y1 - y0)*ctx->rwidth*4,
+			CU(cudaMemcpyAsync(sbuf_host_frame + (size_t)y0*ctx->rwidth, (char *)(f.sbuf + (size_t)y0*ctx->rwidth) + alt, (size_t)(y1 - y0)*ctx->rwidth*4,
 				cudaMemcpyDeviceToHost, ctx->stream));
 	}
 	else
@@ -1091,7 +1151,7 @@ extern "C" int pwn_debug_flags(pwn_ctx *ctx, uint32_t *out, int nwords)
 	if(out == nullptr || nwords <= 0) return fail(PWN_E_ARG, "pwn_debug_flags: bad arguments");
 	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "no frame configured");
 	const FrameSet &f = ctx->fs[0];
-	const size_t have = (f.bytes - f.off_flags)/4;
+	const size_t have = (f.group_bytes - f.off_flags)/4;
 	if((size_t)nwords > have) nwords = (int)have;
 	if(nwords > 1024) nwords = 1024;
 	if(ctx->dbg_stream == nullptr)
@@ -1163,8 +1223,11 @@ extern "C" int pwn_read_frame(pwn_ctx *ctx, uint32_t *sbuf, float *zbuf, pwn_ids
 	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "pwn_read_frame before pwn_frame_config");
 	const size_t n = (size_t)ctx->rwidth*ctx->rheight;
 	const FrameSet &f = ctx->fs[0];
-	if(sbuf) CU(cudaMemcpyAsync(sbuf, f.sbuf, n*4, cudaMemcpyDeviceToHost, ctx->stream));
-	if(zbuf) CU(cudaMemcpyAsync(zbuf, f.zbuf, n*4, cudaMemcpyDeviceToHost, ctx->stream));
+	// (after sharded frames of the block layout the latest frame is in the group of planes it was traced into)
+	const size_t alt = (ctx->blk_par && ctx->blk_frames > 0) ? f.off_alt : 0;
+	CU(cudaStreamSynchronize(ctx->copy_stream));
+	if(sbuf) CU(cudaMemcpyAsync(sbuf, (char *)f.sbuf + alt, n*4, cudaMemcpyDeviceToHost, ctx->stream));
+	if(zbuf) CU(cudaMemcpyAsync(zbuf, (char *)f.zbuf + alt, n*4, cudaMemcpyDeviceToHost, ctx->stream));
 	if(ids)
 	{
 		if(ctx->d_ids == nullptr) return fail(PWN_E_STATE, "no ids buffer configured");
@@ -1556,6 +1619,7 @@ extern "C" int pwn_last_kernel_ms(pwn_ctx *ctx, float *k1_ms, float *k2_ms)
 {
 	CTX_ENTER(ctx);
 	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaStreamSynchronize(ctx->copy_stream));
 	if(k1_ms) { *k1_ms = 0.0f; if(ctx->timed) CU(cudaEventElapsedTime(k1_ms, ctx->ev_k1a, ctx->ev_k1b)); }
 	if(k2_ms) { *k2_ms = 0.0f; if(ctx->timed && ctx->timed_blur) CU(cudaEventElapsedTime(k2_ms, ctx->ev_k1b, ctx->ev_k2b)); }
 	return PWN_OK;

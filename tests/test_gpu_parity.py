@@ -932,6 +932,16 @@ def block_layout_case(tracer, oracle, nsh, halo):
                 assert not any(t.peers_timed_out() for t in ts)
                 got = ts[0].read_frame(want_z=False)[0]
                 assert (got[:h, :w] == want[k][:, :w]).all(), (nsh, halo, w, h, k, int((got[:h, :w] != want[k][:, :w]).sum()))
+            # frames back to back, no host sync in between: two are in flight on each shard (alternating plane groups)
+            for rep in range(2):
+                for k, cam in enumerate(cams):
+                    for t in ts:
+                        t.trace_shard_blur(cam, w, h, 0.3 * k)
+            for t in ts:
+                t.sync()
+            assert not any(t.peers_timed_out() for t in ts)
+            got = ts[0].read_frame(want_z=False)[0]
+            assert (got[:h, :w] == want[-1][:, :w]).all(), (nsh, halo, w, h, "pipelined")
             # the host-assembled variant: blurred blocks stay on their shard, every shard copies its own rows
             host = np.zeros((rh, rw), np.uint32)
             api.host_register(host)
