@@ -147,7 +147,7 @@ static int set_device(pwn_ctx *ctx)
 
 // Under CUDA's lazy module loading (the default since 12.2) a kernel's code reaches the device at its first launch,
 // and that load waits for the device to go idle.  A sharded frame parks kernels on the device that spin until other work
-// arrives (k_peer_barrier, k_wait_bands): a first launch behind one of them stalls until its time-out.  Every kernel of the
+// arrives (k_peer_barrier, k_blur_gated): a first launch behind one of them stalls until its time-out.  Every kernel of the
 // library is therefore loaded when the first context is created (cudaFuncGetAttributes loads the function).
 template <typename F> static cudaError_t preload(F *fn)
 {
@@ -161,7 +161,7 @@ static int preload_kernels()
 	return fail(PWN_E_CUDA, "loading %s: %s", #K, cudaGetErrorString(e_)); } while(0)
 #define PWN_PRELOAD_TRACE(S, L) PWN_PRELOAD((k_trace<S, false, L, false>)); PWN_PRELOAD((k_trace<S, false, L, true>)); PWN_PRELOAD((k_trace<S, true, L, false>))
 	PWN_PRELOAD_TRACE(false, false); PWN_PRELOAD_TRACE(false, true); PWN_PRELOAD_TRACE(true, false); PWN_PRELOAD_TRACE(true, true);
-	PWN_PRELOAD(k_blur<false>); PWN_PRELOAD(k_blur<true>); PWN_PRELOAD(k_blur_fix); PWN_PRELOAD(k_wait_bands); PWN_PRELOAD(k_peer_barrier);
+	PWN_PRELOAD(k_blur<false>); PWN_PRELOAD(k_blur<true>); PWN_PRELOAD(k_blur_gated); PWN_PRELOAD(k_blur_fix); PWN_PRELOAD(k_peer_barrier);
 	PWN_PRELOAD(k_checksum); PWN_PRELOAD(k_fp32_peak); PWN_PRELOAD(k_pack_eval); PWN_PRELOAD(k_libm_eval<false>); PWN_PRELOAD(k_libm_eval<true>);
 	PWN_PRELOAD(k_upscale_packed<0>); PWN_PRELOAD(k_upscale_packed<1>); PWN_PRELOAD(k_upscale_packed<2>); PWN_PRELOAD(k_upscale_packed<4>);
 	PWN_PRELOAD(k_upscale_any);
@@ -727,6 +727,7 @@ struct BlkTrace   // what a K1 launch of pwn_trace_shard_blur adds in the block 
 {
 	uint32_t *halo_up = nullptr, *halo_dn = nullptr, *done_local = nullptr, *done_up = nullptr, *done_dn = nullptr;
 	int ht = 0, hb = 0;
+	uint32_t lanes = 0, target = 0;
 };
 
 // ---- the hot path ----------------------------------------------------------------------------------
@@ -818,6 +819,7 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 			P.blk_ht = blk->ht; P.blk_hb = blk->hb;
 			P.halo_up = blk->halo_up; P.halo_dn = blk->halo_dn;
 			P.done_local = blk->done_local; P.done_up = blk->done_up; P.done_dn = blk->done_dn;
+			P.blk_lanes = blk->lanes; P.blk_target = blk->target;
 		}
 	}
 	const bool blur = (flags & PWN_F_BLUR) != 0;
@@ -976,6 +978,7 @@ static int trace_shard_blur_blocks(pwn_ctx *ctx, const float cam[16], int dimx, 
 	BlkTrace bt;
 	bt.ht = ht; bt.hb = hb;
 	bt.done_local = f.band_done;
+	bt.lanes = lanes_per_band; bt.target = target;
 	if(r > 0) { bt.halo_up = (uint32_t *)(ctx->peer_base[r - 1] + alt + f0.off_tsbuf); bt.done_up = (uint32_t *)(ctx->peer_base[r - 1] + alt + f0.off_band_done); }
 	if(r + 1 < S) { bt.halo_dn = (uint32_t *)(ctx->peer_base[r + 1] + alt + f0.off_tsbuf); bt.done_dn = (uint32_t *)(ctx->peer_base[r + 1] + alt + f0.off_band_done); }
 	const int rc_trace = launch_trace(ctx, f, cam + 12, rayb, rdx, rdy, dimx, dimy, sec_current, (flags | PWN_F_BLUR) & ~PWN_F_IDS, false, nullptr, true, 0, -1, &bt);
@@ -990,30 +993,19 @@ static int trace_shard_blur_blocks(pwn_ctx *ctx, const float cam[16], int dimx, 
 	CU(cudaMemsetAsync(defer_count, 0, 4, s2));      // (the queue is filled and drained on this stream, frame after frame)
 	if(nb > 0 && rc_trace == PWN_OK)
 	{
-		const int h = blk_halo(ctx, dimy);
-		int group = (nb + 7)/8;       // bands per blur launch: about eight launches per frame
-		if(group < 2) group = 2;
-		for(int g0 = b0; g0 < b0 + nb; g0 += group)
-		{
-			const int g1 = (g0 + group < b0 + nb) ? g0 + group : b0 + nb;
-			int w0 = g0 - h, w1 = g1 + h;          // bands this group may read without queueing
-			if(w0 < vlo) w0 = vlo;
-			if(w1 > vhi) w1 = vhi;
-			if(w0 < 0) w0 = 0;
-			if(w1 > nbands) w1 = nbands;
-			WaitParams W;
-			W.done = f.band_done; W.b0 = w0; W.b1 = w1; W.target = target; W.timeout_ns = tmo; W.err = f0.flags + 16;
-			k_wait_bands<<<1, 32, 0, s2>>>(W);
-			CU(cudaGetLastError());
-			BlurParams B = blur_params(ctx, f.tsbuf, f.zbuf, dst, dimx, dimy);
-			B.y0 = g0*32; B.y1 = (g1*32 < dimy) ? g1*32 : dimy;
-			B.ylo = w0*32; B.ylimit = (w1*32 < dimy) ? w1*32 : dimy;
-			B.defer_count = defer_count; B.defer_list = ctx->fs[1].sbuf;
-			if(B.ylo == 0 && B.ylimit >= dimy) B.ylimit = dimy + 1;      // (the whole frame is here: still the queueing build, which reads with plain loads)
-			k_blur<true><<<dim3((dimx + 255)/256, B.y1 - B.y0), 256, 0, s2>>>(B);
-			CU(cudaGetLastError());
-			ctx->launches += 2;
-		}
+		// one launch: its CTAs wait, tile by tile, for the band counters (see k_blur_gated)
+		BlurParams B = blur_params(ctx, f.tsbuf, f.zbuf, dst, dimx, dimy);
+		B.y0 = b0*32; B.y1 = ((b0 + nb)*32 < dimy) ? (b0 + nb)*32 : dimy;
+		B.defer_count = defer_count; B.defer_list = ctx->fs[1].sbuf;
+		GateParams G;
+		G.done = f.band_done; G.target = target; G.h = blk_halo(ctx, dimy); G.vlo = vlo; G.vhi = vhi; G.nbands = nbands;
+		G.timeout_ns = tmo; G.err = f0.flags + 16;
+		static int nctas = -1;
+		if(nctas < 0) { const char *e = getenv("PWN_BLK_BLUR_CTAS"); nctas = e ? atoi(e) : 296; if(nctas < 1) nctas = 296; }
+		const int ntiles = ((dimx + 255)/256)*(B.y1 - B.y0);
+		k_blur_gated<<<ntiles < nctas ? ntiles : nctas, 256, 0, s2>>>(B, G);
+		CU(cudaGetLastError());
+		ctx->launches++;
 	}
 	CU(cudaStreamWaitEvent(s2, ctx->ev_blk_k1[par], 0));      // the own trace of this frame is complete
 	int rc = launch_barrier(ctx, 0, s2);          // A: every shard's trace and blur launches of this frame are complete

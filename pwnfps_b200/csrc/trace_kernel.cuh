@@ -127,6 +127,7 @@ struct TraceParams
 	int blk, blk_b0, blk_ht, blk_hb;
 	uint32_t *halo_up, *halo_dn;          // pre-blur buffer of the shard above / below (null at the frame's edges)
 	uint32_t *done_local, *done_up, *done_dn;   // band counters, indexed by the band's number in the frame
+	uint32_t blk_lanes, blk_target;             // lanes per band (32 rows x the grid's width); a counter's value when this frame's band is complete
 	BlurParams prev;           // BLURP builds: the blur pass of the PREVIOUS frame of a pose batch
 };
 
@@ -137,15 +138,27 @@ __device__ __forceinline__ void band_arrive(const TraceParams &P, int band, int 
 	// warp -- it costs the walk its 98% L1 hit rate on the cell map (measured: K1 +28%).  The lanes meet at a warp
 	// barrier (which orders their stores before what the leader does next) and the leader's add is a RELEASE: the
 	// waiter's acquire load of the counter then sees every lane's pixels.
+	// A halo band is signalled to the neighbour ONCE, by the group that completes it here: a system-scope release per
+	// warp (MEMBAR.SYS: a round trip over NVLink with the warp's slot held) cost K1 +60% at 8 GPUs.  The completing group
+	// has acquired every other group's release through the local counter, so its one system-scope fence publishes the
+	// whole band's pixels on the neighbour before the neighbour's counter moves.
 	const unsigned m = __activemask();
 	__syncwarp(m);
 	(void)wrote;
 	if((threadIdx.x & 31) == (__ffs(m) - 1))
 	{
 		const unsigned n = __popc(m);
-		asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(P.done_local + band), "r"(n) : "memory");
-		if(which == 1) asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(P.done_up + band), "r"(n) : "memory");
-		if(which == 2) asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(P.done_dn + band), "r"(n) : "memory");
+		if(which == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(P.done_local + band), "r"(n) : "memory");
+		else
+		{
+			unsigned old;
+			asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(P.done_local + band), "r"(n) : "memory");
+			if(old + n == P.blk_target)
+			{
+				__threadfence_system();
+				asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"((which == 1 ? P.done_up : P.done_dn) + band), "r"(P.blk_lanes) : "memory");
+			}
+		}
 	}
 }
 

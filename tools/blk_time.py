@@ -40,7 +40,7 @@ b.record(stream)
 b.synchronize()
 one = a.elapsed_time(b) / len(poses)
 tr.shard_config(world, rank)
-for layout in ("interleaved", "blocks", "blocks balanced"):
+for layout in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("interleaved", "blocks", "blocks balanced")):
     tr.shard_layout(blocks=(layout != "interleaved"))
     if layout == "blocks balanced":
         print("boundaries", shard.balance_blocks(tr, rank, world, dist, poses[::4], w, h)) if rank == 0 else shard.balance_blocks(tr, rank, world, dist, poses[::4], w, h)
