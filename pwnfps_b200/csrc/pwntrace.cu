@@ -68,7 +68,6 @@ struct pwn_ctx
 {
 	int device = -1;
 	cudaStream_t stream = nullptr, copy_stream = nullptr;
-	cudaStream_t end_stream = nullptr;   // block layout: the closing barriers and k_blur_fix of frame n run beside the blur of frame n+1
 	cudaEvent_t ev_k1a = nullptr, ev_k1b = nullptr, ev_k2b = nullptr;
 	cudaEvent_t ev_done[3] = {nullptr, nullptr, nullptr}, ev_copied[3] = {nullptr, nullptr, nullptr};
 	cudaEvent_t ev_chunk[16] = {};   // pwn_trace_screen: "chunk c traced" (0-7) and "chunk c blurred" (8-15)
@@ -119,7 +118,7 @@ struct pwn_ctx
 	int halo_bands = 0;        // contiguous blocks: bands exchanged with each neighbour, 0 = from the frame height
 	std::vector<int> blk_bounds;   // contiguous blocks: first band of every shard + the band count (pwn_shard_blocks), or empty
 	uint32_t blk_frames = 0;   // sharded frames traced in the block layout since pwn_frame_peers (the band counters' epoch)
-	cudaEvent_t ev_blk_k1[2] = {nullptr, nullptr}, ev_blk_done[2] = {nullptr, nullptr}, ev_blk_blur[2] = {nullptr, nullptr};
+	cudaEvent_t ev_blk_k1[2] = {nullptr, nullptr}, ev_blk_done[2] = {nullptr, nullptr};
 	int blk_par = 0;           // which group of frame set 0 holds the latest sharded frame of the block layout
 	int reflect = 2;           // REFLECT as shipped (defs.h:8)
 	int screen_chunks = 0;     // pwn_trace_screen: row chunks per frame, 0 = automatic
@@ -213,9 +212,7 @@ extern "C" int pwn_create(pwn_ctx **out, int device)
 	{
 		CU(cudaEventCreateWithFlags(&ctx->ev_blk_k1[i], cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&ctx->ev_blk_done[i], cudaEventDisableTiming));
-		CU(cudaEventCreateWithFlags(&ctx->ev_blk_blur[i], cudaEventDisableTiming));
 	}
-	CU(cudaStreamCreateWithFlags(&ctx->end_stream, cudaStreamNonBlocking));
 	CU(cudaHostAlloc((void **)&ctx->h_defer, 64, cudaHostAllocDefault));
 	ctx->h_defer[0] = 0;
 
@@ -258,13 +255,7 @@ extern "C" int pwn_destroy(pwn_ctx *ctx)
 		ctx->ev_copied[0], ctx->ev_copied[1], ctx->ev_copied[2]};
 	for(cudaEvent_t e : evs) if(e) cudaEventDestroy(e);
 	for(cudaEvent_t e : ctx->ev_chunk) if(e) cudaEventDestroy(e);
-	for(int i = 0; i < 2; i++)
-	{
-		if(ctx->ev_blk_k1[i]) cudaEventDestroy(ctx->ev_blk_k1[i]);
-		if(ctx->ev_blk_done[i]) cudaEventDestroy(ctx->ev_blk_done[i]);
-		if(ctx->ev_blk_blur[i]) cudaEventDestroy(ctx->ev_blk_blur[i]);
-	}
-	if(ctx->end_stream) cudaStreamDestroy(ctx->end_stream);
+	for(int i = 0; i < 2; i++) { if(ctx->ev_blk_k1[i]) cudaEventDestroy(ctx->ev_blk_k1[i]); if(ctx->ev_blk_done[i]) cudaEventDestroy(ctx->ev_blk_done[i]); }
 	if(ctx->h_defer) cudaFreeHost(ctx->h_defer);
 	if(ctx->h_dbg) cudaFreeHost(ctx->h_dbg);
 	if(ctx->dbg_stream) cudaStreamDestroy(ctx->dbg_stream);
@@ -621,7 +612,7 @@ extern "C" int pwn_frame_config(pwn_ctx *ctx, int rwidth, int rheight, int want_
 	if((unsigned long long)rwidth*(unsigned long long)rheight >= (1ull << 31))
 		return fail(PWN_E_LIMIT, "pwn_frame_config: %dx%d has 2^31 pixels or more", rwidth, rheight);
 	CU(cudaStreamSynchronize(ctx->stream));
-	CU(cudaStreamSynchronize(ctx->copy_stream)); CU(cudaStreamSynchronize(ctx->end_stream));
+	CU(cudaStreamSynchronize(ctx->copy_stream));
 	if(rwidth != ctx->rwidth || rheight != ctx->rheight)
 	{
 		free_frames(ctx);
@@ -900,7 +891,7 @@ static int reset_band_counters(pwn_ctx *ctx)
 	if(ctx->rwidth == 0) return PWN_OK;
 	const FrameSet &f = ctx->fs[0];
 	CU(cudaStreamSynchronize(ctx->stream));
-	CU(cudaStreamSynchronize(ctx->copy_stream)); CU(cudaStreamSynchronize(ctx->end_stream));
+	CU(cudaStreamSynchronize(ctx->copy_stream));
 	CU(cudaMemset(f.flags, 0, f.group_bytes - f.off_flags));
 	CU(cudaMemset((char *)f.base + f.off_alt + f.off_flags, 0, f.group_bytes - f.off_flags));
 	ctx->blk_par = 0;
@@ -977,9 +968,8 @@ static int trace_shard_blur_blocks(pwn_ctx *ctx, const float cam[16], int dimx, 
 	f.band_done = (uint32_t *)((char *)f0.base + alt + f0.off_band_done);
 	const uint32_t lanes_per_band = 32u*32u*(uint32_t)((dimx + 31)/32);
 	const uint32_t target = ((ctx->blk_frames + 1)/2)*lanes_per_band;      // frames that have used this group, this one included
-	uint32_t *defer_count = f0.flags + 32 + par;          // one queue of unfinished pixels per plane group
-	uint32_t *defer_list = ctx->fs[1 + par].sbuf;
-	cudaStream_t s1 = ctx->stream, s2 = ctx->copy_stream, s3 = ctx->end_stream;
+	uint32_t *defer_count = f0.flags + 32;
+	cudaStream_t s1 = ctx->stream, s2 = ctx->copy_stream;
 	const unsigned long long tmo = 4000000000ull;
 
 	// ---- stream 1: the trace ----
@@ -998,16 +988,15 @@ static int trace_shard_blur_blocks(pwn_ctx *ctx, const float cam[16], int dimx, 
 	CU(cudaEventRecord(ctx->ev_blk_k1[par], s1));
 	ctx->timed = true;
 
-	// ---- stream 2: the blur pass; stream 3: the barriers and the fix ----
+	// ---- stream 2: the blur pass in groups of bands, the barriers, the fix ----
 	uint32_t *dst = (flags & PWN_F_LOCAL_BANDS) ? f.sbuf : (uint32_t *)(ctx->peer_base[0] + alt + f0.off_sbuf);
-	CU(cudaStreamWaitEvent(s2, ctx->ev_blk_done[par], 0));     // these planes, shard 0's copy of them and this queue are free again
-	CU(cudaMemsetAsync(defer_count, 0, 4, s2));
+	CU(cudaMemsetAsync(defer_count, 0, 4, s2));      // (the queue is filled and drained on this stream, frame after frame)
 	if(nb > 0 && rc_trace == PWN_OK)
 	{
 		// one launch: its CTAs wait, tile by tile, for the band counters (see k_blur_gated)
 		BlurParams B = blur_params(ctx, f.tsbuf, f.zbuf, dst, dimx, dimy);
 		B.y0 = b0*32; B.y1 = ((b0 + nb)*32 < dimy) ? (b0 + nb)*32 : dimy;
-		B.defer_count = defer_count; B.defer_list = defer_list;
+		B.defer_count = defer_count; B.defer_list = ctx->fs[1].sbuf;
 		GateParams G;
 		G.done = f.band_done; G.target = target; G.h = blk_halo(ctx, dimy); G.vlo = vlo; G.vhi = vhi; G.nbands = nbands;
 		G.timeout_ns = tmo; G.err = f0.flags + 16;
@@ -1018,26 +1007,24 @@ static int trace_shard_blur_blocks(pwn_ctx *ctx, const float cam[16], int dimx, 
 		CU(cudaGetLastError());
 		ctx->launches++;
 	}
-	CU(cudaEventRecord(ctx->ev_blk_blur[par], s2));
-	CU(cudaStreamWaitEvent(s3, ctx->ev_blk_blur[par], 0));
-	CU(cudaStreamWaitEvent(s3, ctx->ev_blk_k1[par], 0));      // the own trace of this frame is complete
-	int rc = launch_barrier(ctx, 0, s3);          // A: every shard's trace and blur launch of this frame are complete
+	CU(cudaStreamWaitEvent(s2, ctx->ev_blk_k1[par], 0));      // the own trace of this frame is complete
+	int rc = launch_barrier(ctx, 0, s2);          // A: every shard's trace and blur launches of this frame are complete
 	if(rc != PWN_OK) return rc;
 	if(nb > 0 && rc_trace == PWN_OK)
 	{
 		BlurParams B = blur_params(ctx, f.tsbuf, f.zbuf, dst, dimx, dimy);
-		B.defer_count = defer_count; B.defer_list = defer_list;
+		B.defer_count = defer_count; B.defer_list = ctx->fs[1].sbuf;
 		B.nsh = S;
 		for(int t = 0; t < S; t++) B.src_sh[t] = (const uint32_t *)(ctx->peer_base[t] + alt + f0.off_tsbuf);
 		for(int t = 0; t <= S; t++) B.band_start[t] = blk_start(ctx, nbands, t);
-		k_blur_fix<<<296, 256, 0, s3>>>(B);
+		k_blur_fix<<<296, 256, 0, s2>>>(B);
 		CU(cudaGetLastError());
 		ctx->launches++;
 	}
-	rc = launch_barrier(ctx, 1, s3);              // B: the frame on shard 0 is complete; these planes may be rewritten
+	rc = launch_barrier(ctx, 1, s2);              // B: the frame on shard 0 is complete; these planes may be rewritten
 	if(rc != PWN_OK) return rc;
-	CU(cudaEventRecord(ctx->ev_k2b, s3));
-	CU(cudaEventRecord(ctx->ev_blk_done[par], s3));
+	CU(cudaEventRecord(ctx->ev_k2b, s2));
+	CU(cudaEventRecord(ctx->ev_blk_done[par], s2));
 	ctx->timed_blur = true;
 	if(rc_trace != PWN_OK) { memcpy(g_err, trace_err, sizeof(g_err)); return rc_trace; }
 	return PWN_OK;
@@ -1048,13 +1035,10 @@ static int trace_shard_blur_blocks(pwn_ctx *ctx, const float cam[16], int dimx, 
 extern "C" int pwn_join(pwn_ctx *ctx)
 {
 	CTX_ENTER(ctx);
-	ScopedEvent e, e3;
+	ScopedEvent e;
 	CU(cudaEventCreateWithFlags(&e.e, cudaEventDisableTiming));
-	CU(cudaEventCreateWithFlags(&e3.e, cudaEventDisableTiming));
 	CU(cudaEventRecord(e.e, ctx->copy_stream));
-	CU(cudaEventRecord(e3.e, ctx->end_stream));
 	CU(cudaStreamWaitEvent(ctx->stream, e.e, 0));
-	CU(cudaStreamWaitEvent(ctx->stream, e3.e, 0));
 	return PWN_OK;
 }
 
@@ -1136,7 +1120,7 @@ extern "C" int pwn_read_bands(pwn_ctx *ctx, int dimx, int dimy, uint32_t *sbuf_h
 		blk_shape(ctx, dimy, ctx->shard, b0, nb, ht, hb);
 		const int y0 = b0*32, y1 = ((b0 + nb)*32 < dimy) ? (b0 + nb)*32 : dimy;
 		const size_t alt = (ctx->blk_par && ctx->blk_frames > 0) ? f.off_alt : 0;
-		CU(cudaStreamSynchronize(ctx->copy_stream)); CU(cudaStreamSynchronize(ctx->end_stream));
+		CU(cudaStreamSynchronize(ctx->copy_stream));
 		if(y1 > y0)
 			CU(cudaMemcpyAsync(sbuf_host_frame + (size_t)y0*ctx->rwidth, (char *)(f.sbuf + (size_t)y0*ctx->rwidth) + alt, (size_t)(y1 - y0)*ctx->rwidth*4,
 				cudaMemcpyDeviceToHost, ctx->stream));
@@ -1221,7 +1205,7 @@ extern "C" int pwn_sync(pwn_ctx *ctx)
 {
 	CTX_ENTER(ctx);
 	CU(cudaStreamSynchronize(ctx->stream));
-	CU(cudaStreamSynchronize(ctx->copy_stream)); CU(cudaStreamSynchronize(ctx->end_stream));
+	CU(cudaStreamSynchronize(ctx->copy_stream));
 	return check_peer_barriers(ctx);
 }
 
@@ -1233,7 +1217,7 @@ extern "C" int pwn_read_frame(pwn_ctx *ctx, uint32_t *sbuf, float *zbuf, pwn_ids
 	const FrameSet &f = ctx->fs[0];
 	// (after sharded frames of the block layout the latest frame is in the group of planes it was traced into)
 	const size_t alt = (ctx->blk_par && ctx->blk_frames > 0) ? f.off_alt : 0;
-	CU(cudaStreamSynchronize(ctx->copy_stream)); CU(cudaStreamSynchronize(ctx->end_stream));
+	CU(cudaStreamSynchronize(ctx->copy_stream));
 	if(sbuf) CU(cudaMemcpyAsync(sbuf, (char *)f.sbuf + alt, n*4, cudaMemcpyDeviceToHost, ctx->stream));
 	if(zbuf) CU(cudaMemcpyAsync(zbuf, (char *)f.zbuf + alt, n*4, cudaMemcpyDeviceToHost, ctx->stream));
 	if(ids)
@@ -1357,7 +1341,7 @@ extern "C" int pwn_trace_screen(pwn_ctx *ctx, const float cam[16], int dimx, int
 		ctx->timed_blur = true;
 	}
 	CU(cudaStreamSynchronize(ctx->stream));
-	CU(cudaStreamSynchronize(ctx->copy_stream)); CU(cudaStreamSynchronize(ctx->end_stream));
+	CU(cudaStreamSynchronize(ctx->copy_stream));
 	if(ctx->h_defer[0] != 0)
 	{
 		// (rare: a surface so far away that its blur samples reach beyond the next chunk) the chunks went out before
@@ -1511,7 +1495,7 @@ extern "C" int pwn_trace_poses(pwn_ctx *ctx, int n, const pwn_pose *poses, int d
 	if(sums != nullptr && n > 0)
 		CU(cudaMemcpyAsync(sums, ctx->d_sums, (size_t)n*sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
-	CU(cudaStreamSynchronize(ctx->copy_stream)); CU(cudaStreamSynchronize(ctx->end_stream));
+	CU(cudaStreamSynchronize(ctx->copy_stream));
 	return PWN_OK;
 }
 
@@ -1627,7 +1611,7 @@ extern "C" int pwn_last_kernel_ms(pwn_ctx *ctx, float *k1_ms, float *k2_ms)
 {
 	CTX_ENTER(ctx);
 	CU(cudaStreamSynchronize(ctx->stream));
-	CU(cudaStreamSynchronize(ctx->copy_stream)); CU(cudaStreamSynchronize(ctx->end_stream));
+	CU(cudaStreamSynchronize(ctx->copy_stream));
 	if(k1_ms) { *k1_ms = 0.0f; if(ctx->timed) CU(cudaEventElapsedTime(k1_ms, ctx->ev_k1a, ctx->ev_k1b)); }
 	if(k2_ms) { *k2_ms = 0.0f; if(ctx->timed && ctx->timed_blur) CU(cudaEventElapsedTime(k2_ms, ctx->ev_k1b, ctx->ev_k2b)); }
 	return PWN_OK;
