@@ -404,6 +404,7 @@ def run_ours(args, rank, world, local_rank):
     warm = max(args.warmup, 3)
 
     bases = None
+    bounds = None
     shard_check = None
     if world == 1:
         def step_device():
@@ -414,6 +415,9 @@ def run_ours(args, rank, world, local_rank):
         want = tr.trace_poses(poses[:4], w, h, flags, want_sums=True)
         tr.shard_config(world, rank)
         tr.shard_layout(blocks=True)          # contiguous band blocks: halo exchange instead of an all-gather
+        # rows below the horizon cost more (floor bounce): the block boundaries are moved until the shards' traces take
+        # the same time on a sample of the batch (outside the timed region; the boundaries are part of `config`)
+        bounds = shard.balance_blocks(tr, rank, world, dist, poses[::8], w, h)
         rig.barrier()
         if blur:
             bases = shard.open_all_peers(tr, rank, world, dist)
@@ -437,6 +441,8 @@ def run_ours(args, rank, world, local_rank):
             if rank == 0:
                 s0, _, _ = tr.read_frame(want_z=False)
                 got.append(int(api.checksum_ref(s0, w, h)))
+        if blur and tr.peers_timed_out():
+            raise SystemExit("bench.py: a device-side wait of the sharded frames timed out on rank %d" % rank)
         if rank == 0:
             shard_check = bool(got == [int(v) for v in want])
             if not shard_check:
@@ -532,6 +538,7 @@ def run_ours(args, rank, world, local_rank):
                 raise SystemExit("bench.py: a device-side barrier of the sharded frames timed out")
         else:
             shard.close_peer_frame(tr, bases)
+        tr.shard_blocks(None)
         tr.shard_layout(blocks=False)
         tr.shard_config(1, 0)
         beside = shard.bench_band_gather(tr, rank, world, local_rank, rig.stream)
@@ -627,6 +634,7 @@ def run_ours(args, rank, world, local_rank):
         }
         if shard_check is not None:
             line["sharded_frames_equal_one_gpu"] = shard_check
+            line["config"]["block_boundaries_bands"] = [int(b) for b in bounds]
         if others is not None:
             line["other_configs"] = others
         if beside is not None:

@@ -708,9 +708,9 @@ class Tracer:
         ptr = host_frame.ctypes.data if isinstance(host_frame, np.ndarray) else host_frame
         _check(self.L.pwn_read_bands(self.h, dimx, dimy, ptr))
 
-    def debug_flags(self, nwords=128):
+    def debug_flags(self, nwords=128, alt=False):
         out = np.zeros(nwords, np.uint32)
-        n = self.L.pwn_debug_flags(self.h, out.ctypes.data, nwords)
+        n = self.L.pwn_debug_flags(self.h, out.ctypes.data, -nwords if alt else nwords)
         if n < 0:
             _check(n)
         return out[:n]

@@ -119,6 +119,7 @@ struct pwn_ctx
 	std::vector<int> blk_bounds;   // contiguous blocks: first band of every shard + the band count (pwn_shard_blocks), or empty
 	uint32_t blk_frames = 0;   // sharded frames traced in the block layout since pwn_frame_peers (the band counters' epoch)
 	cudaEvent_t ev_blk_k1[2] = {nullptr, nullptr}, ev_blk_done[2] = {nullptr, nullptr};
+	cudaEvent_t ev_join = nullptr;
 	int blk_par = 0;           // which group of frame set 0 holds the latest sharded frame of the block layout
 	int reflect = 2;           // REFLECT as shipped (defs.h:8)
 	int screen_chunks = 0;     // pwn_trace_screen: row chunks per frame, 0 = automatic
@@ -149,10 +150,16 @@ static int set_device(pwn_ctx *ctx)
 // and that load waits for the device to go idle.  A sharded frame parks kernels on the device that spin until other work
 // arrives (k_peer_barrier, k_blur_gated): a first launch behind one of them stalls until its time-out.  Every kernel of the
 // library is therefore loaded when the first context is created (cudaFuncGetAttributes loads the function).
+// Every kernel also asks for the SAME shared-memory carve-out (the 100 KB step: K1's nine CTAs of 9.5 KB + 1 KB each).  An SM
+// changes its L1 / shared-memory split only when it is empty: left to the driver's per-kernel choice, a blur launch whose
+// waiting CTAs sit on every SM keeps the trace kernel they wait for from starting anywhere (measured: each frame that
+// started its blur launch before its trace launch ran into the 4 s time-out).
 template <typename F> static cudaError_t preload(F *fn)
 {
 	cudaFuncAttributes a;
-	return cudaFuncGetAttributes(&a, (const void *)fn);
+	cudaError_t e = cudaFuncGetAttributes(&a, (const void *)fn);
+	if(e != cudaSuccess) return e;
+	return cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, 43);
 }
 
 static int preload_kernels()
@@ -195,6 +202,7 @@ extern "C" int pwn_create(pwn_ctx **out, int device)
 		// higher priority their few CTAs are placed ahead of the trace's pending ones whenever an SM has room
 		int lo = 0, hi = 0;
 		CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		if(getenv("PWN_NO_STREAM_PRIORITY") != nullptr) hi = lo;
 		CU(cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, hi));
 	}
 	CU(cudaEventCreate(&ctx->ev_k1a));
@@ -256,6 +264,7 @@ extern "C" int pwn_destroy(pwn_ctx *ctx)
 	for(cudaEvent_t e : evs) if(e) cudaEventDestroy(e);
 	for(cudaEvent_t e : ctx->ev_chunk) if(e) cudaEventDestroy(e);
 	for(int i = 0; i < 2; i++) { if(ctx->ev_blk_k1[i]) cudaEventDestroy(ctx->ev_blk_k1[i]); if(ctx->ev_blk_done[i]) cudaEventDestroy(ctx->ev_blk_done[i]); }
+	if(ctx->ev_join) cudaEventDestroy(ctx->ev_join);
 	if(ctx->h_defer) cudaFreeHost(ctx->h_defer);
 	if(ctx->h_dbg) cudaFreeHost(ctx->h_dbg);
 	if(ctx->dbg_stream) cudaStreamDestroy(ctx->dbg_stream);
@@ -1000,8 +1009,17 @@ static int trace_shard_blur_blocks(pwn_ctx *ctx, const float cam[16], int dimx, 
 		GateParams G;
 		G.done = f.band_done; G.target = target; G.h = blk_halo(ctx, dimy); G.vlo = vlo; G.vhi = vhi; G.nbands = nbands;
 		G.timeout_ns = tmo; G.err = f0.flags + 16;
+		// fewer CTAs than SMs: whatever the launch order and the SMs' state, the trace kernel the waiting CTAs depend on
+		// always finds SMs without them
 		static int nctas = -1;
-		if(nctas < 0) { const char *e = getenv("PWN_BLK_BLUR_CTAS"); nctas = e ? atoi(e) : 296; if(nctas < 1) nctas = 296; }
+		if(nctas < 0)
+		{
+			const char *e = getenv("PWN_BLK_BLUR_CTAS");
+			cudaDeviceProp prop;
+			CU(cudaGetDeviceProperties(&prop, ctx->device));
+			nctas = e ? atoi(e) : prop.multiProcessorCount - 16;
+			if(nctas < 1) nctas = 1;
+		}
 		const int ntiles = ((dimx + 255)/256)*(B.y1 - B.y0);
 		k_blur_gated<<<ntiles < nctas ? ntiles : nctas, 256, 0, s2>>>(B, G);
 		CU(cudaGetLastError());
@@ -1035,10 +1053,9 @@ static int trace_shard_blur_blocks(pwn_ctx *ctx, const float cam[16], int dimx, 
 extern "C" int pwn_join(pwn_ctx *ctx)
 {
 	CTX_ENTER(ctx);
-	ScopedEvent e;
-	CU(cudaEventCreateWithFlags(&e.e, cudaEventDisableTiming));
-	CU(cudaEventRecord(e.e, ctx->copy_stream));
-	CU(cudaStreamWaitEvent(ctx->stream, e.e, 0));
+	if(ctx->ev_join == nullptr) CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+	CU(cudaEventRecord(ctx->ev_join, ctx->copy_stream));
+	CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
 	return PWN_OK;
 }
 
@@ -1140,9 +1157,11 @@ extern "C" int pwn_read_bands(pwn_ctx *ctx, int dimx, int dimy, uint32_t *sbuf_h
 extern "C" int pwn_debug_flags(pwn_ctx *ctx, uint32_t *out, int nwords)
 {
 	CTX_ENTER(ctx);
-	if(out == nullptr || nwords <= 0) return fail(PWN_E_ARG, "pwn_debug_flags: bad arguments");
+	if(out == nullptr || nwords == 0) return fail(PWN_E_ARG, "pwn_debug_flags: bad arguments");
 	if(ctx->rwidth == 0) return fail(PWN_E_STATE, "no frame configured");
 	const FrameSet &f = ctx->fs[0];
+	const bool alt = nwords < 0;          // (negative: the same words of the second group of planes)
+	if(alt) nwords = -nwords;
 	const size_t have = (f.group_bytes - f.off_flags)/4;
 	if((size_t)nwords > have) nwords = (int)have;
 	if(nwords > 1024) nwords = 1024;
@@ -1151,7 +1170,7 @@ extern "C" int pwn_debug_flags(pwn_ctx *ctx, uint32_t *out, int nwords)
 		CU(cudaStreamCreateWithFlags(&ctx->dbg_stream, cudaStreamNonBlocking));
 		CU(cudaHostAlloc((void **)&ctx->h_dbg, 4096, cudaHostAllocDefault));
 	}
-	CU(cudaMemcpyAsync(ctx->h_dbg, f.flags, (size_t)nwords*4, cudaMemcpyDeviceToHost, ctx->dbg_stream));
+	CU(cudaMemcpyAsync(ctx->h_dbg, (char *)f.flags + (alt ? f.off_alt : 0), (size_t)nwords*4, cudaMemcpyDeviceToHost, ctx->dbg_stream));
 	CU(cudaStreamSynchronize(ctx->dbg_stream));
 	memcpy(out, ctx->h_dbg, (size_t)nwords*4);
 	return nwords;

@@ -266,6 +266,8 @@ def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), fr
         # block layout (halo bands only, the blur under the trace): the second is what bench.py's headline times
         for layout in ("interleaved", "blocks"):
             tr.shard_layout(blocks=(layout == "blocks"))
+            if layout == "blocks":
+                out["block_boundaries_bands"] = [int(b) for b in balance_blocks(tr, rank, world, dist, poses[::4], w, h)]
             dist.barrier()
             bases = open_all_peers(tr, rank, world, dist)
             got = []
@@ -328,6 +330,7 @@ def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), fr
             out["host_frame_error"] = "%s: %s" % (type(e).__name__, e)
         dist.barrier()
         close_all_peers(tr, bases)
+        tr.shard_blocks(None)
         tr.shard_layout(blocks=False)
         if rank == 0:
             out["sharded_blur_timed_out"] = bool(timed_out)
