@@ -307,7 +307,7 @@ int pwn_frame_ipc_close(pwn_ctx *ctx, uint64_t base_dev);
 /*
  * A sharded frame WITH the blur pass, block layout (pwn_shard_layout PWN_SHARD_BLOCKS; what bench.py times at N > 1):
  * one K1 launch traces the shard's bands, halo bands first, storing those into the neighbour's pre-blur buffer too and
- * counting finished lanes per band; on a second stream the blur pass follows two bands at a time, each launch gated on the
+ * counting finished lanes per band; on a second stream the blur pass follows in a few groups of bands, each launch gated on the
  * device by the counters of the bands it reads, and stores straight into shard 0's frame -- the gather to GPU 0 runs under
  * the trace.  Samples beyond the exchanged rows are finished from the owning shard's rows after a device barrier.
  * Frames alternate between two groups of planes: the call for frame n+1 may be made at once, its trace runs while frame

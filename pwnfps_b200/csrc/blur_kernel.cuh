@@ -199,78 +199,6 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ BlurParams
 	blur_pixel<DEFER>(P, x, y);
 }
 
-// The blur pass of a shard's block of a frame that is still being traced (contiguous-block sharding).  A bounded number
-// of CTAs walks the block's tiles of 256 pixels top to bottom; before a tile, thread 0 waits until the per-band counters
-// say that the rows the tile may read -- its own band and `h` bands either side, as far as this shard ever receives them
-// -- are complete (an acquire load per band, then the CTA's barrier), so the launch sits beside the trace kernel and
-// follows it band by band.  Samples outside those rows are queued for k_blur_fix.  The CTA count is bounded because the
-// results go over NVLink into GPU 0, whose ingest all shards share: CTAs waiting on those stores must not fill the SMs.
-struct GateParams
-{
-	const uint32_t *done;     // band counters (this shard's array: its own bands and the neighbours' halo bands land here)
-	uint32_t target;          // a counter's value when this frame's band is complete
-	int h, vlo, vhi, nbands;  // halo width in bands; the bands [vlo, vhi) are the ones this shard will ever hold
-	unsigned long long timeout_ns;
-	uint32_t *err;
-};
-
-__global__ void __launch_bounds__(256) k_blur_gated(const __grid_constant__ BlurParams P0, const __grid_constant__ GateParams G)
-{
-	__shared__ int s_ok;
-	const int ntx = (P0.dimx + 255) >> 8, ntiles = ntx*(P0.y1 - P0.y0);
-	int ready_lo = 0x7FFFFFFF, ready_hi = -1;      // bands [ready_lo, ready_hi) are known to be complete (thread 0)
-	for(int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-	{
-		const int row = tile / ntx, y = P0.y0 + row, x = ((tile - row*ntx) << 8) + (int)threadIdx.x;
-		const int b = y >> 5;
-		int w0 = b - G.h, w1 = b + G.h + 1;
-		if(w0 < G.vlo) w0 = G.vlo;
-		if(w1 > G.vhi) w1 = G.vhi;
-		if(w0 < 0) w0 = 0;
-		if(w1 > G.nbands) w1 = G.nbands;
-		if(threadIdx.x == 0)
-		{
-			int ok = 1;
-			if(w0 < ready_lo || w1 > ready_hi)
-			{
-				unsigned long long t0, t1;
-				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-				for(int q = w0; q < w1 && ok; q++)
-				{
-					if(q >= ready_lo && q < ready_hi) continue;
-					for(;;)
-					{
-						uint32_t v;
-						asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(G.done + q) : "memory");
-						if((int32_t)(v - G.target) >= 0) break;
-						asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-						if(t1 - t0 > G.timeout_ns) { *G.err = 1u; ok = 0; break; }
-						__nanosleep(200);
-					}
-				}
-				if(ok)
-				{
-					if(ready_hi < 0 || w0 > ready_hi || w1 < ready_lo) { ready_lo = w0; ready_hi = w1; }      // (not adjacent: start over)
-					else { ready_lo = w0 < ready_lo ? w0 : ready_lo; ready_hi = w1 > ready_hi ? w1 : ready_hi; }
-				}
-			}
-			s_ok = ok;
-		}
-		__syncthreads();
-		const int ok = s_ok;
-		__syncthreads();
-		if(!ok) return;          // a band never arrived: the frame is incomplete, the error word says so
-		if(x < P0.dimx)
-		{
-			BlurParams P = P0;
-			P.ylo = w0*32;
-			P.ylimit = (w1*32 < P0.dimy) ? w1*32 : P0.dimy;
-			if(P.ylo == 0 && P.ylimit >= P0.dimy) P.ylimit = P0.dimy + 1;   // (everything is here: nothing to queue)
-			blur_pixel<true>(P, x, y);
-		}
-	}
-}
-
 // the pixels k_blur<true> queued, once the whole pre-blur frame is there
 __global__ void __launch_bounds__(256) k_blur_fix(const __grid_constant__ BlurParams P)
 {
@@ -280,6 +208,35 @@ __global__ void __launch_bounds__(256) k_blur_fix(const __grid_constant__ BlurPa
 		const uint32_t pix = P.defer_list[i];
 		const uint32_t y = pix / (uint32_t)P.rwidth;
 		blur_pixel<false, true>(P, (int)(pix - y*(uint32_t)P.rwidth), (int)y);
+	}
+}
+
+// stream-ordered wait for band counters (contiguous-block sharding): lane t polls band b0 + t until it holds
+// `target` lanes or more; a band that never fills ends the wait after timeout_ns with the error word set
+struct WaitParams
+{
+	const uint32_t *done;
+	int b0, b1;
+	uint32_t target;
+	unsigned long long timeout_ns;
+	uint32_t *err;
+};
+
+__global__ void k_wait_bands(const WaitParams W)
+{
+	unsigned long long t0, t1;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+	for(int b = W.b0 + (int)threadIdx.x; b < W.b1; b += (int)blockDim.x)
+	{
+		for(;;)
+		{
+			uint32_t v;
+			asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(W.done + b) : "memory");
+			if((int32_t)(v - W.target) >= 0) break;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+			if(t1 - t0 > W.timeout_ns) { *W.err = 1u; break; }
+			__nanosleep(100);
+		}
 	}
 }
 

@@ -148,7 +148,7 @@ static int set_device(pwn_ctx *ctx)
 
 // Under CUDA's lazy module loading (the default since 12.2) a kernel's code reaches the device at its first launch,
 // and that load waits for the device to go idle.  A sharded frame parks kernels on the device that spin until other work
-// arrives (k_peer_barrier, k_blur_gated): a first launch behind one of them stalls until its time-out.  Every kernel of the
+// arrives (k_peer_barrier, k_wait_bands): a first launch behind one of them stalls until its time-out.  Every kernel of the
 // library is therefore loaded when the first context is created (cudaFuncGetAttributes loads the function).
 // Every kernel also asks for the SAME shared-memory carve-out (the 100 KB step: K1's nine CTAs of 9.5 KB + 1 KB each).  An SM
 // changes its L1 / shared-memory split only when it is empty: left to the driver's per-kernel choice, a blur launch whose
@@ -168,7 +168,7 @@ static int preload_kernels()
 	return fail(PWN_E_CUDA, "loading %s: %s", #K, cudaGetErrorString(e_)); } while(0)
 #define PWN_PRELOAD_TRACE(S, L) PWN_PRELOAD((k_trace<S, false, L, false>)); PWN_PRELOAD((k_trace<S, false, L, true>)); PWN_PRELOAD((k_trace<S, true, L, false>))
 	PWN_PRELOAD_TRACE(false, false); PWN_PRELOAD_TRACE(false, true); PWN_PRELOAD_TRACE(true, false); PWN_PRELOAD_TRACE(true, true);
-	PWN_PRELOAD(k_blur<false>); PWN_PRELOAD(k_blur<true>); PWN_PRELOAD(k_blur_gated); PWN_PRELOAD(k_blur_fix); PWN_PRELOAD(k_peer_barrier);
+	PWN_PRELOAD(k_blur<false>); PWN_PRELOAD(k_blur<true>); PWN_PRELOAD(k_wait_bands); PWN_PRELOAD(k_blur_fix); PWN_PRELOAD(k_peer_barrier);
 	PWN_PRELOAD(k_checksum); PWN_PRELOAD(k_fp32_peak); PWN_PRELOAD(k_pack_eval); PWN_PRELOAD(k_libm_eval<false>); PWN_PRELOAD(k_libm_eval<true>);
 	PWN_PRELOAD(k_upscale_packed<0>); PWN_PRELOAD(k_upscale_packed<1>); PWN_PRELOAD(k_upscale_packed<2>); PWN_PRELOAD(k_upscale_packed<4>);
 	PWN_PRELOAD(k_upscale_any);
@@ -1002,28 +1002,36 @@ static int trace_shard_blur_blocks(pwn_ctx *ctx, const float cam[16], int dimx, 
 	CU(cudaMemsetAsync(defer_count, 0, 4, s2));      // (the queue is filled and drained on this stream, frame after frame)
 	if(nb > 0 && rc_trace == PWN_OK)
 	{
-		// one launch: its CTAs wait, tile by tile, for the band counters (see k_blur_gated)
-		BlurParams B = blur_params(ctx, f.tsbuf, f.zbuf, dst, dimx, dimy);
-		B.y0 = b0*32; B.y1 = ((b0 + nb)*32 < dimy) ? (b0 + nb)*32 : dimy;
-		B.defer_count = defer_count; B.defer_list = ctx->fs[1].sbuf;
-		GateParams G;
-		G.done = f.band_done; G.target = target; G.h = blk_halo(ctx, dimy); G.vlo = vlo; G.vhi = vhi; G.nbands = nbands;
-		G.timeout_ns = tmo; G.err = f0.flags + 16;
-		// fewer CTAs than SMs: whatever the launch order and the SMs' state, the trace kernel the waiting CTAs depend on
-		// always finds SMs without them
-		static int nctas = -1;
-		if(nctas < 0)
+		// The block's bands in a few groups; each group is one ordinary blur launch behind a one-warp kernel that waits for
+		// the counters of the bands the group reads.  (Nothing but those single warps ever waits on the device: a blur
+		// launch whose own CTAs did the waiting, parked on every SM, kept the trace kernel of a frame that had not started
+		// yet from starting at all.)
+		const int h = blk_halo(ctx, dimy);
+		static int ngroups = -1;
+		if(ngroups < 0) { const char *e = getenv("PWN_BLK_BLUR_GROUPS"); ngroups = e ? atoi(e) : 4; if(ngroups < 1) ngroups = 1; }
+		int group = (nb + ngroups - 1)/ngroups;
+		if(group < 1) group = 1;
+		for(int g0 = b0; g0 < b0 + nb; g0 += group)
 		{
-			const char *e = getenv("PWN_BLK_BLUR_CTAS");
-			cudaDeviceProp prop;
-			CU(cudaGetDeviceProperties(&prop, ctx->device));
-			nctas = e ? atoi(e) : prop.multiProcessorCount - 16;
-			if(nctas < 1) nctas = 1;
+			const int g1 = (g0 + group < b0 + nb) ? g0 + group : b0 + nb;
+			int w0 = g0 - h, w1 = g1 + h;          // bands this group may read without queueing
+			if(w0 < vlo) w0 = vlo;
+			if(w1 > vhi) w1 = vhi;
+			if(w0 < 0) w0 = 0;
+			if(w1 > nbands) w1 = nbands;
+			WaitParams W;
+			W.done = f.band_done; W.b0 = w0; W.b1 = w1; W.target = target; W.timeout_ns = tmo; W.err = f0.flags + 16;
+			k_wait_bands<<<1, 32, 0, s2>>>(W);
+			CU(cudaGetLastError());
+			BlurParams B = blur_params(ctx, f.tsbuf, f.zbuf, dst, dimx, dimy);
+			B.y0 = g0*32; B.y1 = (g1*32 < dimy) ? g1*32 : dimy;
+			B.ylo = w0*32; B.ylimit = (w1*32 < dimy) ? w1*32 : dimy;
+			B.defer_count = defer_count; B.defer_list = ctx->fs[1].sbuf;
+			if(B.ylo == 0 && B.ylimit >= dimy) B.ylimit = dimy + 1;      // (the whole frame is here: still the queueing build, which reads with plain loads)
+			k_blur<true><<<dim3((dimx + 255)/256, B.y1 - B.y0), 256, 0, s2>>>(B);
+			CU(cudaGetLastError());
+			ctx->launches += 2;
 		}
-		const int ntiles = ((dimx + 255)/256)*(B.y1 - B.y0);
-		k_blur_gated<<<ntiles < nctas ? ntiles : nctas, 256, 0, s2>>>(B, G);
-		CU(cudaGetLastError());
-		ctx->launches++;
 	}
 	CU(cudaStreamWaitEvent(s2, ctx->ev_blk_k1[par], 0));      // the own trace of this frame is complete
 	int rc = launch_barrier(ctx, 0, s2);          // A: every shard's trace and blur launches of this frame are complete

@@ -15,11 +15,6 @@ from pwnfps_b200 import api, levels
 
 pytestmark = pytest.mark.gpu
 
-# Several shards share ONE GPU in these tests: the blur launch of the block layout parks CTAs that wait for the other
-# shards' traces, and with the production count (296 per shard) four shards' worth would fill every SM and leave the traces
-# they wait for nowhere to run.  (One process per GPU, as bench.py runs it, has one such launch per GPU.)
-os.environ.setdefault("PWN_BLK_BLUR_CTAS", "24")
-
 IDF = ("cell", "ldir", "kind", "nstep", "nportal")
 
 # RGB tolerance stated by north_star: <= 1 LSB per channel on >= 99.9% of pixels
@@ -892,7 +887,7 @@ def test_sharded_blur_block_layout_in_one_process(tracer, oracle, nsh, halo):
         return
     import subprocess
     import sys
-    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", PWN_BLK_BLUR_CTAS="12")
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
             "from oracle import orcbind\nfrom pwnfps_b200 import api\nimport test_gpu_parity as T\n"
             "t = api.Tracer(0)\nT.block_layout_case(t, orcbind.Oracle(), %d, %d)\nt.close()\nprint('block layout ok')\n"
