@@ -48,6 +48,10 @@ NPOSES = 64
 SM_COUNT = 148
 FP32_LANES = 128
 METRIC = "primary_mrays_per_s"
+# algorithmic FP32 lane-ops of the blur pass per blurred pixel, counted from the source like the trace's (SURVEY 8d rules:
+# mul, add, cmp, cvt = 1 each): 4 samples x [z = dist - 1 (1) + 2 coordinates x (randfs: cvt, mul, sub (3); x fstr, x z (2);
+# int base -> float, add (2); float -> int (1))] = 4 x 17  (screen.h:95-102; the clamps and pavgb are integer work)
+W_BLUR = 68
 
 
 def headline_config(world, blur=True):
@@ -590,7 +594,11 @@ def run_ours(args, rank, world, local_rank):
             # step events: the same algorithmic trace work over the whole launch, the blur's own work not counted
             "timed_step": ({"kernel": "k_trace<..., BLURP> (K1 + the blur of the previous frame)", "ms_per_launch": step_ms_frame,
                             "achieved": r["ops_per_launch"] / (step_ms_frame * 1e-3) / 1e12,
-                            "frac": r["ops_per_launch"] / (step_ms_frame * 1e-3) / 1e12 / rig.peak_issue} if world == 1 else None),
+                            "frac": r["ops_per_launch"] / (step_ms_frame * 1e-3) / 1e12 / rig.peak_issue,
+                            # the same launch with the blur's own lane-ops counted too (the launch does both)
+                            "blur_ops_per_pixel": W_BLUR if blur else 0,
+                            "frac_with_blur_ops": (r["ops_per_launch"] + (W_BLUR if blur else 0) * w * h) / (step_ms_frame * 1e-3) / 1e12 / rig.peak_issue}
+                           if world == 1 else None),
             "hbm": {"bound": "hbm", "achieved": store_bytes / (r["k1_ms_per_launch"] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": store_bytes / (r["k1_ms_per_launch"] * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["source"],
                     "algorithmic_bytes_per_pixel": 8},

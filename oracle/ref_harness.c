@@ -313,6 +313,26 @@ double ref_trace_frame(const float *cam16, float sec, int w, int h, int nthreads
 	return t1 - t0;
 }
 
+/*
+ * The FP environment of the shipped executable.  The reference Makefile's -ffast-math makes gcc link crtfastmath.o into
+ * an EXECUTABLE, whose constructor sets MXCSR.FTZ and MXCSR.DAZ; gcc does not link it into a shared object, so these
+ * libraries, loaded into Python, run with denormals on.  ref_set_fpenv(1) sets FTZ|DAZ on the calling thread and on every
+ * OpenMP worker (what the game's threads inherit from main), ref_set_fpenv(0) clears them: tests/test_oracle_ref.py traces
+ * the same frames both ways.
+ */
+int ref_set_fpenv(int ftz_daz)
+{
+	const unsigned bits = 0x8040u;   /* FTZ (bit 15) | DAZ (bit 6) */
+	_mm_setcsr(ftz_daz ? (_mm_getcsr() | bits) : (_mm_getcsr() & ~bits));
+#ifdef _OPENMP
+#pragma omp parallel
+	{
+		_mm_setcsr(ftz_daz ? (_mm_getcsr() | bits) : (_mm_getcsr() & ~bits));
+	}
+#endif
+	return (int)(_mm_getcsr() & bits);
+}
+
 /* Repeat the same frame n times without copying out: the CPU-baseline timer. */
 double ref_time_frames(const float *cam16, float sec, int w, int h, int nthreads, int nframes)
 {

@@ -128,6 +128,10 @@ class Ref:
         if self.lib.ref_player_tick(cam16, gravity4, np.ascontiguousarray(keys8, dtype=np.int32), float(tdiff)) != 0:
             raise RuntimeError("ref_player_tick: no level loaded")
 
+    def set_fpenv(self, ftz_daz):
+        """MXCSR FTZ|DAZ on (what crtfastmath.o gives the shipped executable) or off, on this thread and the OpenMP workers"""
+        return self.lib.ref_set_fpenv(1 if ftz_daz else 0)
+
     def max_threads(self):
         return self.lib.ref_max_threads()
 

@@ -472,3 +472,68 @@ def test_loader_on_random_bytes_vs_reference(refs, tmp_path):
             inner &= (pm[:, k] == -1) | ((pm[:, k] >= 1) & (pm[:, k] <= 62))
         assert (pm[inner] == mine[inner]).all(), it
         assert ref.spawn() == (lv.sx, lv.sz), it
+
+
+def test_ftz_daz_environment_changes_nothing(refs, default_level, tmp_path):
+    """Which FP environment is parity pinned to?  The shipped executable runs with MXCSR FTZ|DAZ on (-ffast-math links
+    crtfastmath.o into an EXECUTABLE); the shared objects under oracle/_ref, loaded into Python, run with denormals on,
+    and the device is built -ftz=false to match them.  The two environments give the same frames: the reference's own
+    code (shipped flags, blur on) traced both ways -- default level, the fog-heavy fly-through poses, the mirror hall
+    incl. its exhausted walks, twelve fuzz levels with spheres, and a level that is all fog -- differs in 0 pixels of
+    sbuf and 0 words of zbuf.  (The smallest magnitudes on the path are the EPSILON clamp, 1e-13, and exp(-0.6*fog):
+    the latter is denormal only for an accumulated fog length in (145.6, 172.2) units, i.e. a walk of that length
+    through fog cells alone; the all-fog corridor with portals at both ends below is the level built to come close,
+    and the pixels that see farther than 100 units in it are counted in the printed line.)"""
+    import fuzz_levels
+    ref = refs("libref.so")
+    cases = []
+    p = str(tmp_path / "level.txt")
+    default_level.save_txt(p)
+    poses = api.flythrough(default_level, 600)
+    cases.append((p, [(poses["cam"][i], float(poses["sec_current"][i])) for i in range(0, 600, 60)], None))
+    hall = levels.mirror_hall()
+    ph = str(tmp_path / "hall.txt")
+    hall.save_txt(ph)
+    last = hall.portals[16]
+    cam = np.eye(4, dtype=np.float32)
+    cam[3, :3] = (last["x1"] - 2.5, 0.5, last["z1"] + 0.5)
+    cases.append((ph, [(api.mat4_roty(api.cam_spawn(hall), 1.5707964), 0.5), (api.mat4_roty(cam.reshape(16), 1.5707964), 0.0)], None))
+    for seed in range(12):
+        txt = fuzz_levels.random_level_text(seed, open_edges=(seed % 4 == 3))
+        pf = str(tmp_path / ("fuzz%d.txt" % seed))
+        open(pf, "wb").write(txt)
+        lv = api.level_parse(txt)
+        fuzz_levels.random_spheres(lv, seed, 10)
+        cases.append((pf, [(q["cam"], float(q["sec_current"])) for q in fuzz_levels.random_poses(lv, seed, 2)], lv.spheres))
+    # every open cell foggy ('$'), a long corridor with mirrors of portals at both ends: fog accumulates over hundreds of cells
+    rows = [b"." * 40] + [b"." + b"$" * 38 + b"." for _ in range(3)] + [b"." * 40]
+    rows[2] = b"A" + b"$" * 38 + b"A"
+    pfog = str(tmp_path / "fog.txt")
+    open(pfog, "wb").write(b"\n".join(rows) + b"\n")
+    camf = np.eye(4, dtype=np.float32)
+    camf[3, :3] = (20.5, 0.5, 2.5)
+    cases.append((pfog, [(api.mat4_roty(camf.reshape(16), 1.5707964), 0.0), (api.mat4_roty(camf.reshape(16), 1.4), 0.3)], None))
+    total = differing = 0
+    denormal_fog = 0
+    try:
+        for path, views, spheres in cases:
+            ref.level_load(path)
+            ref.objs_clear()
+            if spheres is not None:
+                for sp in spheres:
+                    ref.obj_sphere(sp["r"], sp["refl"], sp["pos"][0], sp["pos"][1], sp["pos"][2], sp["col"][0], sp["col"][1], sp["col"][2])
+            for cam, sec in views:
+                out = []
+                for env in (0, 1):
+                    assert bool(ref.set_fpenv(env)) == bool(env)
+                    s, z, _, _ = ref.trace_frame(cam, sec, 320, 180)
+                    out.append((s, z))
+                total += out[0][0].size
+                differing += int((out[0][0] != out[1][0]).sum()) + int((out[0][1].view(np.uint32) != out[1][1].view(np.uint32)).sum())
+                if path == pfog:
+                    denormal_fog += int((out[0][1] > 100.0).sum())
+    finally:
+        ref.set_fpenv(0)
+        ref.objs_clear()
+    print("FTZ|DAZ on vs off: %d of %d pixels differ (%d pixels of the all-fog level see farther than 100 units)" % (differing, total, denormal_fog))
+    assert differing == 0, (differing, total)
