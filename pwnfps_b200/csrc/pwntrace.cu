@@ -85,6 +85,9 @@ struct pwn_ctx
 
 	// math tables
 	uint32_t *d_rcp = nullptr, *d_rsqrt = nullptr;
+	std::vector<uint32_t> h_rcp, h_rsqrt;   // the tables as the device reads them: copied in front of every cell map (STD builds of K1)
+	bool std_tables = false;                // the usual widths (rcpps 11 bits, rsqrtps 10 + parity): 2048 entries each
+	uint32_t *d_cellmap_alloc = nullptr;    // d_cellmap's allocation: 16 KB of tables, then the map
 	int rcp_bits = 0, rsqrt_bits = 0;
 	bool have_tables = false;
 
@@ -166,13 +169,15 @@ static int preload_kernels()
 {
 #define PWN_PRELOAD(K) do { cudaError_t e_ = preload(K); if(e_ != cudaSuccess) \
 	return fail(PWN_E_CUDA, "loading %s: %s", #K, cudaGetErrorString(e_)); } while(0)
-#define PWN_PRELOAD_TRACE(S, L) PWN_PRELOAD((k_trace<S, false, L, false>)); PWN_PRELOAD((k_trace<S, false, L, true>)); PWN_PRELOAD((k_trace<S, true, L, false>))
+#define PWN_PRELOAD_TRACE_(S, L, T) PWN_PRELOAD((k_trace<S, false, L, false, T>)); PWN_PRELOAD((k_trace<S, false, L, true, T>)); PWN_PRELOAD((k_trace<S, true, L, false, T>))
+#define PWN_PRELOAD_TRACE(S, L) PWN_PRELOAD_TRACE_(S, L, false); PWN_PRELOAD_TRACE_(S, L, true)
 	PWN_PRELOAD_TRACE(false, false); PWN_PRELOAD_TRACE(false, true); PWN_PRELOAD_TRACE(true, false); PWN_PRELOAD_TRACE(true, true);
 	PWN_PRELOAD(k_blur<false>); PWN_PRELOAD(k_blur<true>); PWN_PRELOAD(k_wait_bands); PWN_PRELOAD(k_blur_fix); PWN_PRELOAD(k_peer_barrier);
 	PWN_PRELOAD(k_checksum); PWN_PRELOAD(k_fp32_peak); PWN_PRELOAD(k_pack_eval); PWN_PRELOAD(k_libm_eval<false>); PWN_PRELOAD(k_libm_eval<true>);
 	PWN_PRELOAD(k_upscale_packed<0>); PWN_PRELOAD(k_upscale_packed<1>); PWN_PRELOAD(k_upscale_packed<2>); PWN_PRELOAD(k_upscale_packed<4>);
 	PWN_PRELOAD(k_upscale_any);
 #undef PWN_PRELOAD_TRACE
+#undef PWN_PRELOAD_TRACE_
 #undef PWN_PRELOAD
 	return PWN_OK;
 }
@@ -254,7 +259,7 @@ extern "C" int pwn_destroy(pwn_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	free_frames(ctx);
-	cudaFree(ctx->d_cellmap); cudaFree(ctx->d_portals);
+	cudaFree(ctx->d_cellmap_alloc); cudaFree(ctx->d_portals);
 	cudaFree(ctx->d_rcp); cudaFree(ctx->d_rsqrt);
 	cudaFree(ctx->d_parts_blob); cudaFreeHost(ctx->h_parts_stage);
 	if(ctx->ev_parts) cudaEventDestroy(ctx->ev_parts);
@@ -298,8 +303,17 @@ extern "C" int pwn_math_tables(pwn_ctx *ctx, const uint32_t *rcp_tab, int rcp_bi
 		for(size_t i2 = 0; i2 < ns; i2++)
 			st2[i2] = rsqrt_tab[i2 ^ ((size_t)1 << rsqrt_bits)] - ((uint32_t)((i2 >> rsqrt_bits) & 1) << 23) + 0x20000000u;
 		CU(cudaMemcpy(ctx->d_rsqrt, st2.data(), ns*sizeof(uint32_t), cudaMemcpyHostToDevice));
+		ctx->h_rsqrt = st2;
 	}
+	ctx->h_rcp.assign(rcp_tab, rcp_tab + nr);
 	ctx->rcp_bits = rcp_bits; ctx->rsqrt_bits = rsqrt_bits;
+	ctx->std_tables = (rcp_bits == STD_RCP_BITS && rsqrt_bits == STD_RSQRT_BITS);
+	if(ctx->std_tables && ctx->d_cellmap_alloc != nullptr)      // a level is there already: its copy of the tables
+	{
+		CU(cudaMemcpy(ctx->d_cellmap_alloc, ctx->h_rcp.data(), STD_TAB_WORDS/2*4, cudaMemcpyHostToDevice));
+		CU(cudaMemcpy(ctx->d_cellmap_alloc + STD_TAB_WORDS/2, ctx->h_rsqrt.data(), STD_TAB_WORDS/2*4, cudaMemcpyHostToDevice));
+	}
+	ctx->nsph = 0;      // (the sphere builds' copy of the map carries the tables too: pwn_parts_upload rebuilds it)
 	ctx->have_tables = true;
 	return PWN_OK;
 }
@@ -494,10 +508,17 @@ extern "C" int pwn_level_upload(pwn_ctx *ctx, int w, int h, const int32_t *cells
 	if(recs.empty()) { PortalRec r; memset(&r, 0, sizeof(r)); recs.push_back(r); }
 
 	CU(cudaStreamSynchronize(ctx->stream));
-	cudaFree(ctx->d_cellmap); cudaFree(ctx->d_portals);
-	ctx->d_cellmap = nullptr; ctx->d_portals = nullptr;
+	cudaFree(ctx->d_cellmap_alloc); cudaFree(ctx->d_portals);
+	ctx->d_cellmap_alloc = ctx->d_cellmap = nullptr; ctx->d_portals = nullptr;
 	ctx->have_level = false;
-	CU(cudaMalloc(&ctx->d_cellmap, map.size()*sizeof(uint32_t)));
+	CU(cudaMalloc(&ctx->d_cellmap_alloc, (STD_TAB_WORDS + map.size())*sizeof(uint32_t)));
+	ctx->d_cellmap = ctx->d_cellmap_alloc + STD_TAB_WORDS;
+	CU(cudaMemset(ctx->d_cellmap_alloc, 0, STD_TAB_WORDS*sizeof(uint32_t)));
+	if(ctx->std_tables)
+	{
+		CU(cudaMemcpy(ctx->d_cellmap_alloc, ctx->h_rcp.data(), STD_TAB_WORDS/2*4, cudaMemcpyHostToDevice));
+		CU(cudaMemcpy(ctx->d_cellmap_alloc + STD_TAB_WORDS/2, ctx->h_rsqrt.data(), STD_TAB_WORDS/2*4, cudaMemcpyHostToDevice));
+	}
 	CU(cudaMalloc(&ctx->d_portals, recs.size()*sizeof(PortalRec)));
 	CU(cudaMemcpy(ctx->d_cellmap, map.data(), map.size()*sizeof(uint32_t), cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(ctx->d_portals, recs.data(), recs.size()*sizeof(PortalRec), cudaMemcpyHostToDevice));
@@ -564,7 +585,8 @@ extern "C" int pwn_parts_upload(pwn_ctx *ctx, int nsph, const pwn_sphere *sph)
 			const size_t b_pos = 0, b_col = b_pos + align16((size_t)nsph*sizeof(float4)), b_rr = b_col + align16((size_t)nsph*sizeof(float4));
 			const size_t b_off = b_rr + align16((size_t)nsph*sizeof(float2)), b_idx = b_off + align16((ncell + 1)*sizeof(uint32_t));
 			const size_t b_pk = b_idx + align16(idx.size()*sizeof(uint32_t));
-			const size_t b_map = b_pk + align16(ncell*sizeof(uint32_t));
+			const size_t b_tab = b_pk + align16(ncell*sizeof(uint32_t));      // 16 KB of tables in front of the map, as in d_cellmap_alloc
+			const size_t b_map = b_tab + STD_TAB_WORDS*sizeof(uint32_t);
 			const size_t total = b_map + align16(ncell*sizeof(uint32_t));
 			if(ctx->h_cellmap.size() != ncell) return fail(PWN_E_STATE, "pwn_parts_upload: no host copy of the cell map");
 			if(idx.size() >= (1u << 24)) return fail(PWN_E_LIMIT, "more than 2^24 sphere list entries");
@@ -593,6 +615,11 @@ extern "C" int pwn_parts_upload(pwn_ctx *ctx, int nsph, const pwn_sphere *sph)
 			// per cell: the packed list handle, and the map entry again with CM_SPH_BIT where the list is not empty --
 			// the walk then learns from the entry it has loaded anyway whether the cell's list is worth a look
 			uint32_t *pk = (uint32_t *)(hs + b_pk), *mp = (uint32_t *)(hs + b_map);
+			if(ctx->std_tables)
+			{
+				memcpy(hs + b_tab, ctx->h_rcp.data(), STD_TAB_WORDS/2*4);
+				memcpy(hs + b_tab + STD_TAB_WORDS/2*4, ctx->h_rsqrt.data(), STD_TAB_WORDS/2*4);
+			}
 			for(size_t c = 0; c < ncell; c++)
 			{
 				const uint32_t cnt = off[c + 1] - off[c];
@@ -764,10 +791,10 @@ static int launch_blur(pwn_ctx *ctx, const BlurParams &B, int nrows = -1, cudaSt
 	return PWN_OK;
 }
 
-template <bool SPH, bool LFMA>
+template <bool SPH, bool LFMA, bool STD>
 static void launch_k1(const TraceParams &P, dim3 grid, cudaStream_t st, bool ids, bool blurp)
 {
-	if(ids) k_trace<SPH, true, LFMA, false><<<grid, K1_THREADS, 0, st>>>(P);
+	if(ids) k_trace<SPH, true, LFMA, false, STD><<<grid, K1_THREADS, 0, st>>>(P);
 	else if(blurp)
 	{
 		// programmatic dependent launch: this grid may begin before the previous one has drained
@@ -778,9 +805,9 @@ static void launch_k1(const TraceParams &P, dim3 grid, cudaStream_t st, bool ids
 		at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 		at[0].val.programmaticStreamSerializationAllowed = 1;
 		cfg.attrs = at; cfg.numAttrs = 1;
-		cudaLaunchKernelEx(&cfg, k_trace<SPH, false, LFMA, true>, P);
+		cudaLaunchKernelEx(&cfg, k_trace<SPH, false, LFMA, true, STD>, P);
 	}
-	else k_trace<SPH, false, LFMA, false><<<grid, K1_THREADS, 0, st>>>(P);
+	else k_trace<SPH, false, LFMA, false, STD><<<grid, K1_THREADS, 0, st>>>(P);
 }
 
 // K1 for one frame into frame set f (+ the blur of `prev`'s frame riding along, pose batches),
@@ -868,8 +895,18 @@ static int launch_trace(pwn_ctx *ctx, const FrameSet &f, const float from[4], co
 		dim3 grid((dimx + 31)/32, nb_launch*(32/K1_ROWS));
 		if(timing) CU(cudaEventRecord(ctx->ev_k1a, ctx->stream));
 		const bool ids = P.ids != nullptr;
-		if(ctx->nsph > 0) { if(ctx->libm_fma) launch_k1<true, true>(P, grid, ctx->stream, ids, blurp); else launch_k1<true, false>(P, grid, ctx->stream, ids, blurp); }
-		else { if(ctx->libm_fma) launch_k1<false, true>(P, grid, ctx->stream, ids, blurp); else launch_k1<false, false>(P, grid, ctx->stream, ids, blurp); }
+		const int variant = (ctx->nsph > 0 ? 4 : 0) | (ctx->libm_fma ? 2 : 0) | (ctx->std_tables ? 1 : 0);
+		switch(variant)
+		{
+			case 0: launch_k1<false, false, false>(P, grid, ctx->stream, ids, blurp); break;
+			case 1: launch_k1<false, false, true>(P, grid, ctx->stream, ids, blurp); break;
+			case 2: launch_k1<false, true, false>(P, grid, ctx->stream, ids, blurp); break;
+			case 3: launch_k1<false, true, true>(P, grid, ctx->stream, ids, blurp); break;
+			case 4: launch_k1<true, false, false>(P, grid, ctx->stream, ids, blurp); break;
+			case 5: launch_k1<true, false, true>(P, grid, ctx->stream, ids, blurp); break;
+			case 6: launch_k1<true, true, false>(P, grid, ctx->stream, ids, blurp); break;
+			default: launch_k1<true, true, true>(P, grid, ctx->stream, ids, blurp); break;
+		}
 		CU(cudaGetLastError());
 		ctx->launches++;
 		if(timing) { CU(cudaEventRecord(ctx->ev_k1b, ctx->stream)); ctx->timed = true; }

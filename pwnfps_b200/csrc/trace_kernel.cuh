@@ -182,10 +182,17 @@ enum : uint32_t
 
 // ---- host-CPU primitives, emulated ---------------------------------------------------
 // rcpps(|x|), x normal: neither the table index nor the exponent field looks at the sign bit
-__device__ __forceinline__ float rcp_emul(const LevelDev &L, float x)
+// With the table widths of every x86 CPU seen so far (rcpps 11 bits, rsqrtps 10 + parity: 2048 entries each) the two
+// tables sit in the 16 KB in front of the cell map (STD builds): one base pointer serves map and tables, the shifts and the
+// mask are immediates, and nothing about the tables is read from the kernel parameters (five loads per segment less).
+constexpr int STD_RCP_BITS = 11, STD_RSQRT_BITS = 10;
+constexpr int STD_TAB_WORDS = 4096;      // rcp at cmap - 4096, rsqrt at cmap - 2048 (words)
+
+template <bool STD>
+__device__ __forceinline__ float rcp_emul(const LevelDev &L, const uint32_t *cmap, float x)
 {
 	uint32_t u = __float_as_uint(x);
-	uint32_t t = __ldg(&L.rcp_tab[(u & 0x7FFFFFu) >> L.rcp_shift]);
+	uint32_t t = STD ? __ldg(cmap - STD_TAB_WORDS + ((u & 0x7FFFFFu) >> (23 - STD_RCP_BITS))) : __ldg(&L.rcp_tab[(u & 0x7FFFFFu) >> L.rcp_shift]);
 	return __uint_as_float(t - (u & 0x7F800000u) + 0x3F800000u);
 }
 
@@ -193,10 +200,12 @@ __device__ __forceinline__ float rcp_emul(const LevelDev &L, float x)
 // result exponent is floor((E - 127)/2) = ((E + 1) >> 1) - 64, E the biased exponent.  pwn_math_tables stores the
 // table re-indexed by [E & 1 | top mantissa bits] -- the bit pattern as it is -- with (E & 1) << 23 and the
 // exponent bias already taken out of each entry, which leaves a shift, a mask and a subtract around the load.
-__device__ __forceinline__ float rsqrt_emul(const LevelDev &L, float x)
+template <bool STD>
+__device__ __forceinline__ float rsqrt_emul(const LevelDev &L, const uint32_t *cmap, float x)
 {
 	const uint32_t u = __float_as_uint(x);
-	const uint32_t t = __ldg(&L.rsqrt_tab[(u >> L.rsqrt_shift) & L.rsqrt_mask]);
+	const uint32_t t = STD ? __ldg(cmap - STD_TAB_WORDS/2 + ((u >> (23 - STD_RSQRT_BITS)) & ((2u << STD_RSQRT_BITS) - 1u)))
+	                       : __ldg(&L.rsqrt_tab[(u >> L.rsqrt_shift) & L.rsqrt_mask]);
 	return __uint_as_float(t - ((u >> 1) & 0x7F800000u));
 }
 
@@ -314,11 +323,12 @@ struct Aux
 };
 
 // v_normalise(hit - centre) (trace.h:283-284), shared by the test and by the rebuild at the hit
-__device__ __forceinline__ void sphere_normal(const LevelDev &L, float hx, float hy, float hz, const float4 &sp4, float &nx, float &ny, float &nz)
+template <bool STD>
+__device__ __forceinline__ void sphere_normal(const LevelDev &L, const uint32_t *cmap, float hx, float hy, float hz, const float4 &sp4, float &nx, float &ny, float &nz)
 {
 	nx = __fsub_rn(hx, sp4.x); ny = __fsub_rn(hy, sp4.y); nz = __fsub_rn(hz, sp4.z);
 	const float nd = __fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(nz, nz)), __fmul_rn(ny, ny));
-	const float ns = rsqrt_emul(L, nd);
+	const float ns = rsqrt_emul<STD>(L, cmap, nd);
 	nx = __fmul_rn(nx, ns); ny = __fmul_rn(ny, ns); nz = __fmul_rn(nz, ns);
 }
 
@@ -352,7 +362,7 @@ constexpr int K1_SEG_UNROLL = PWN_SEG_UNROLL;     // 1: one copy of the segment 
 constexpr int K1_WALK_UNROLL = PWN_WALK_UNROLL;   // 1: the walk stays rolled (measured: see DESIGN.md)
 constexpr int K1_MIN_CTAS_SPH = PWN_SPH_MIN_CTAS;   // with spheres the nearest-hit record adds 12 live registers
 
-template <bool SPH, bool IDS, bool LFMA, bool BLURP>
+template <bool SPH, bool IDS, bool LFMA, bool BLURP, bool STD>
 __global__ void __launch_bounds__(K1_THREADS, SPH ? K1_MIN_CTAS_SPH : K1_MIN_CTAS) k_trace(const __grid_constant__ TraceParams P)
 {
 	const LevelDev &L = P.lv;
@@ -461,14 +471,14 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 			float sx, sz;
 			unpk2(mul2x(irxz, irxz, nz2), sx, sz);
 			const float d = __fadd_rn(__fadd_rn(sx, sz), __fmul_rn(iry, iry));
-			const float s = rsqrt_emul(L, d);
+			const float s = rsqrt_emul<STD>(L, cmap, d);
 			unpk2(mul2x(irxz, pk2(s, s), nz2), rx, rz);
 			ry = __fmul_rn(iry, s);
 		}
 #else
 		{
 			const float d = __fadd_rn(__fadd_rn(__fmul_rn(irx, irx), __fmul_rn(irz, irz)), __fmul_rn(iry, iry));
-			const float s = rsqrt_emul(L, d);
+			const float s = rsqrt_emul<STD>(L, cmap, d);
 			rx = __fmul_rn(irx, s); ry = __fmul_rn(iry, s); rz = __fmul_rn(irz, s);
 		}
 #endif
@@ -514,8 +524,8 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 				ci = (((unsigned)cz >= (unsigned)H ? 0 : cz) + 1)*WP + ((unsigned)cx >= (unsigned)W ? 0 : cx) + 1;
 			}
 		}
-		float iax = rcp_emul(L, rx), iaz = rcp_emul(L, rz);   // iavel = rcpps(abs(ray)), trace.h:229-231
-		const float iay = rcp_emul(L, ry);
+		float iax = rcp_emul<STD>(L, cmap, rx), iaz = rcp_emul<STD>(L, cmap, rz);   // iavel = rcpps(abs(ray)), trace.h:229-231
+		const float iay = rcp_emul<STD>(L, cmap, ry);
 		float px = fx, py = fy, pz = fz;
 #if PWN_PACKED
 		unpk2(mul2x(pk2(wx, wz), pk2(iax, iaz), nz2), wx, wz);
@@ -625,7 +635,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 									aux.py = __fadd_rn(py, __fmul_rn(sd, ry));
 									aux.pz = __fadd_rn(pz, __fmul_rn(sd, rz));
 									float nx, ny, nz;
-									sphere_normal(L, aux.px, aux.py, aux.pz, sp4, nx, ny, nz);
+									sphere_normal<STD>(L, cmap, aux.px, aux.py, aux.pz, sp4, nx, ny, nz);
 									float diff = -__fadd_rn(__fadd_rn(__fmul_rn(rx, nx), __fmul_rn(rz, nz)), __fmul_rn(ry, ny));
 									if(diff < 0.0f) diff = 0.0f;
 									aux.diff = __fadd_rn(0.2f, __fmul_rn(__fsub_rn(1.0f, 0.2f), diff));
@@ -894,7 +904,12 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 			// ceilings, floors and walls side by side
 			const float4 sc = PWN_SURFACE(hsurf);
 			const float sb = sc.x, sg = sc.y, sr = sc.z;
+#if PWN_PACKED
+			unpk2(mul2x(pk2(icb, icg), pk2(sb, sg), nz2), cb, cg);
+			cr = __fmul_rn(icr, sr);
+#else
 			cb = __fmul_rn(icb, sb); cg = __fmul_rn(icg, sg); cr = __fmul_rn(icr, sr);
+#endif
 			if(SPH) ca = __fmul_rn(ica, 0.0f);   // (without spheres the alpha lane of a shaded colour is +0 exactly, see ALPHA0)
 			// diffuse = +-ray[axis(ldir)]: FXP FZP FXN FZN FYP FYN = 0..5
 			float diffuse = (ldir >= PWN_FYP) ? ry : ((ldir & 1) ? rz : rx);
@@ -902,7 +917,12 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 			diffuse = __uint_as_float(__float_as_uint(diffuse) ^ ((0x2Cu << (31 - ldir)) & 0x80000000u));
 			if(diffuse < 0.0f) diffuse = 0.0f;
 			diffuse = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, 0.1f), diffuse), 0.1f);
+#if PWN_PACKED
+			unpk2(mul2x(pk2(cb, cg), pk2(diffuse, diffuse), nz2), cb, cg);
+			cr = __fmul_rn(cr, diffuse);
+#else
 			cb = __fmul_rn(cb, diffuse); cg = __fmul_rn(cg, diffuse); cr = __fmul_rn(cr, diffuse);
+#endif
 			if(SPH) ca = __fmul_rn(ca, diffuse);
 			refl = (ldir == PWN_FYN ? 0.7f : 0.25f);
 		}
@@ -956,7 +976,7 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 				libm_sincosf<LFMA>(ang, &s, &c);
 				// v_normalise(sin, 38, cos, 0): (x^2 + z^2) + (y^2 + 0)
 				const float nd = __fadd_rn(__fadd_rn(__fmul_rn(s, s), __fmul_rn(c, c)), __fmul_rn(38.0f, 38.0f));
-				const float ns = rsqrt_emul(L, nd);
+				const float ns = rsqrt_emul<STD>(L, cmap, nd);
 				nx = __fmul_rn(s, ns); ny = __fmul_rn(38.0f, ns); nz = __fmul_rn(c, ns);
 			}
 			else
@@ -965,22 +985,52 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 				npx = __fsub_rn(npx, __fmul_rn(0.001f, nrx));
 				npy = __fsub_rn(npy, __fmul_rn(0.001f, nry));
 				npz = __fsub_rn(npz, __fmul_rn(0.001f, nrz));
-				sphere_normal(L, aux.px, aux.py, aux.pz, __ldg(&L.sph_pos[aux.si]), nx, ny, nz);   // aux_norm, rebuilt
+				sphere_normal<STD>(L, cmap, aux.px, aux.py, aux.pz, __ldg(&L.sph_pos[aux.si]), nx, ny, nz);   // aux_norm, rebuilt
 			}
 			// rmul = -2*(((0 + rx*nx) + ry*ny) + rz*nz); ray = normalise(rmul*norm + ray)
+#if PWN_PACKED
+			{
+				const f32x2 nxz = pk2(nx, nz);
+				float dx, dz, qx, qz;
+				unpk2(mul2x(pk2(nrx, nrz), nxz, nz2), dx, dz);
+				const float rmul = __fmul_rn(-2.0f, __fadd_rn(__fadd_rn(dx, __fmul_rn(nry, ny)), dz));
+				unpk2(add2(mul2x(pk2(rmul, rmul), nxz, nz2), pk2(nrx, nrz)), nrx, nrz);
+				nry = __fadd_rn(__fmul_rn(rmul, ny), nry);
+				const f32x2 rxz2 = pk2(nrx, nrz);
+				unpk2(mul2x(rxz2, rxz2, nz2), qx, qz);
+				const float d = __fadd_rn(__fadd_rn(qx, qz), __fmul_rn(nry, nry));
+				const float s = rsqrt_emul<STD>(L, cmap, d);
+				unpk2(mul2x(rxz2, pk2(s, s), nz2), nrx, nrz);
+				nry = __fmul_rn(nry, s);
+			}
+#else
 			const float rmul = __fmul_rn(-2.0f, __fadd_rn(__fadd_rn(__fmul_rn(nrx, nx), __fmul_rn(nry, ny)), __fmul_rn(nrz, nz)));
 			nrx = __fadd_rn(__fmul_rn(rmul, nx), nrx);
 			nry = __fadd_rn(__fmul_rn(rmul, ny), nry);
 			nrz = __fadd_rn(__fmul_rn(rmul, nz), nrz);
 			const float d = __fadd_rn(__fadd_rn(__fmul_rn(nrx, nrx), __fmul_rn(nrz, nrz)), __fmul_rn(nry, nry));
-			const float s = rsqrt_emul(L, d);
+			const float s = rsqrt_emul<STD>(L, cmap, d);
 			nrx = __fmul_rn(nrx, s); nry = __fmul_rn(nry, s); nrz = __fmul_rn(nrz, s);
+#endif
 		}
 
 		if(P.reflect_blur)   // trace.h:77-84: draws x, y, (discard), z, (discard)
 		{
+#if PWN_PACKED
+			{
+				// two draws, then both lanes together: randfs = r*fl(2/3759) - 1, ray += randfs*0.03
+				seed = (seed * 25739u + 4u) & 0x7FFFFFFFu;
+				const float r0 = (float)(seed % 3759u);
+				seed = (seed * 25739u + 4u) & 0x7FFFFFFFu;
+				const float r1 = (float)(seed % 3759u);
+				const float c = __uint_as_float(0x3A0B79B3u);
+				const f32x2 v = sub2(mul2x(pk2(r0, r1), pk2(c, c), nz2), pk2(1.0f, 1.0f));
+				unpk2(add2(pk2(nrx, nry), mul2x(v, pk2(0.03f, 0.03f), nz2)), nrx, nry);
+			}
+#else
 			nrx = __fadd_rn(nrx, __fmul_rn(randfs(seed), 0.03f));
 			nry = __fadd_rn(nry, __fmul_rn(randfs(seed), 0.03f));
+#endif
 			seed = (seed * 25739u + 4u) & 0x7FFFFFFFu;
 			nrz = __fadd_rn(nrz, __fmul_rn(randfs(seed), 0.03f));
 			seed = (seed * 25739u + 4u) & 0x7FFFFFFFu;
@@ -1018,16 +1068,32 @@ static_assert(K1_THREADS*4 == 512, "scratch row offsets");
 		PWN_LDS(lb, sl, 0); PWN_LDS(lg, sl, 512); PWN_LDS(lr, sl, 1024);
 		if(SPH) PWN_LDS(la, sl, 1536);
 		const float k = __fsub_rn(1.0f, refl);
+#if PWN_PACKED
+		{
+			// (b, g) and (r, a) as pairs.  Without spheres the parked alpha is +0 (ALPHA0): refl*oa + k*(+0) is refl*oa,
+			// which is never -0, so the pair form gives the same bits as leaving the term out.
+			const f32x2 rr2 = pk2(refl, refl), kk2 = pk2(k, k);
+			unpk2(add2(mul2x(rr2, pk2(ob, og), nz2), mul2x(kk2, pk2(lb, lg), nz2)), ob, og);
+			unpk2(add2(mul2x(rr2, pk2(orr, oa), nz2), mul2x(kk2, pk2(lr, la), nz2)), orr, oa);
+		}
+#else
 		ob = __fadd_rn(__fmul_rn(refl, ob), __fmul_rn(k, lb));
 		og = __fadd_rn(__fmul_rn(refl, og), __fmul_rn(k, lg));
 		orr = __fadd_rn(__fmul_rn(refl, orr), __fmul_rn(k, lr));
 		if(SPH) oa = __fadd_rn(__fmul_rn(refl, oa), __fmul_rn(k, la));
 		else oa = __fmul_rn(refl, oa);   // ALPHA0: + k*(+0) changes nothing, refl*oa is never -0
+#endif
 		if(fogl != 0.0f)
 		{
 			const float f = libm_expf<LFMA>(__fmul_rn(-0.6f, fogl)), g = __fsub_rn(1.0f, f);
+#if PWN_PACKED
+			const f32x2 ff2 = pk2(f, f), gg2 = pk2(g, g);
+			unpk2(add2(mul2x(ff2, pk2(ob, og), nz2), gg2), ob, og);
+			unpk2(add2(mul2x(ff2, pk2(orr, oa), nz2), gg2), orr, oa);
+#else
 			ob = __fadd_rn(__fmul_rn(f, ob), g); og = __fadd_rn(__fmul_rn(f, og), g);
 			orr = __fadd_rn(__fmul_rn(f, orr), g); oa = __fadd_rn(__fmul_rn(f, oa), g);
+#endif
 		}
 	}
 

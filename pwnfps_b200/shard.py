@@ -125,6 +125,28 @@ def close_all_peers(tr, bases):
             tr.ipc_close(b)
 
 
+def rebalance(bounds, times, nb):
+    """One round of the block balancing: `times[s]` is what shard s took for the bands [bounds[s], bounds[s+1]).  Each
+    block's cost is spread evenly over its bands, and the new boundaries are put where the cumulative cost is split
+    evenly (nearest band; every shard keeps at least one band).  Pure: every rank computes the same from the same times."""
+    world = len(bounds) - 1
+    cost = np.zeros(nb)
+    for s in range(world):
+        n = bounds[s + 1] - bounds[s]
+        if n > 0:
+            cost[bounds[s]:bounds[s + 1]] = float(times[s]) / n
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    new = [0]
+    for s in range(1, world):
+        target = cum[-1] * s / world
+        b = int(np.searchsorted(cum, target))
+        if b > 0 and abs(cum[b - 1] - target) < abs(cum[min(b, nb)] - target):
+            b -= 1
+        new.append(min(max(b, new[-1] + 1), nb - (world - s)))
+    new.append(nb)
+    return new
+
+
 def balance_blocks(tr, rank, world, dist, poses, w, h, rounds=3):
     """Block layout: move the block boundaries until the shards' traces take the same time.  Rows differ in cost (below
     the horizon the floor carries the wavy-normal bounce and the longer secondary rays), so an even split leaves the
@@ -142,27 +164,10 @@ def balance_blocks(tr, rank, world, dist, poses, w, h, rounds=3):
         for p in poses:
             tr.trace_cam(p["cam"], w, h, float(p["sec_current"]), 0)
             t += tr.last_kernel_ms()[0]
-        times = torch.zeros(world, dtype=torch.float64, device="cuda")
+        times = torch.zeros(world, dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
         times[rank] = t
         dist.all_reduce(times)
-        times = times.cpu().numpy()
-        # cost per band, piecewise constant over the current blocks; new boundaries at equal shares of the total
-        cost = np.zeros(nb)
-        for s in range(world):
-            n = bounds[s + 1] - bounds[s]
-            if n > 0:
-                cost[bounds[s]:bounds[s + 1]] = times[s] / n
-        cum = np.concatenate([[0.0], np.cumsum(cost)])
-        new = [0]
-        for s in range(1, world):
-            target = cum[-1] * s / world
-            b = int(np.searchsorted(cum, target))
-            # the boundary nearest to the target share
-            if b > 0 and abs(cum[b - 1] - target) < abs(cum[min(b, nb)] - target):
-                b -= 1
-            new.append(min(max(b, new[-1] + 1), nb - (world - s)))
-        new.append(nb)
-        bounds = new
+        bounds = rebalance(bounds, times.cpu().numpy(), nb)
     tr.shard_blocks(bounds)
     return bounds
 

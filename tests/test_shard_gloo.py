@@ -74,3 +74,85 @@ def test_two_rank_gloo_band_gather():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_rebalance_is_a_partition_and_evens_the_cost():
+    """shard.rebalance: boundaries stay a partition of the bands with at least one band per shard, and iterating it on a
+    known cost profile brings the blocks' costs together"""
+    rng = np.random.default_rng(3)
+    for nb, world in ((135, 8), (135, 2), (34, 4), (9, 8), (8, 8), (68, 3)):
+        cost = 1.0 + 0.4 * np.linspace(0, 1, nb) + 0.05 * rng.random(nb)          # rows below the horizon cost more
+        bounds = [s * nb // world for s in range(world + 1)]
+        for _ in range(4):
+            times = [cost[bounds[s]:bounds[s + 1]].sum() for s in range(world)]
+            bounds = shard.rebalance(bounds, times, nb)
+            assert bounds[0] == 0 and bounds[-1] == nb and len(bounds) == world + 1
+            assert all(bounds[s + 1] > bounds[s] for s in range(world)), bounds
+        times = np.array([cost[bounds[s]:bounds[s + 1]].sum() for s in range(world)])
+        even = np.array([cost[s * nb // world:(s + 1) * nb // world].sum() for s in range(world)])
+        if nb >= 4 * world:
+            assert times.max() / times.mean() <= min(even.max() / even.mean(), 1.0 + 2.0 * cost.max() / times.mean()), (nb, world, times)
+
+
+class _FakeTracer:
+    """stands in for api.Tracer in balance_blocks: trace_cam 'takes' the summed cost of the rank's block"""
+
+    def __init__(self, cost, world, rank):
+        self.cost, self.world, self.rank = cost, world, rank
+        self.bounds = None
+        self.last = 0.0
+
+    def shard_layout(self, blocks=False, halo_bands=0):
+        self.blocks = blocks
+
+    def shard_config(self, n, r):
+        assert (n, r) == (self.world, self.rank)
+
+    def shard_blocks(self, bounds):
+        self.bounds = list(bounds)
+
+    def trace_cam(self, cam, w, h, sec, flags):
+        self.last = float(self.cost[self.bounds[self.rank]:self.bounds[self.rank + 1]].sum())
+
+    def last_kernel_ms(self):
+        return self.last, 0.0
+
+
+def _balance_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        nb = 135
+        cost = 1.0 + 0.35 * np.linspace(0, 1, nb)
+        tr = _FakeTracer(cost, world, rank)
+        poses = np.zeros(2, [("cam", "<f4", (16,)), ("sec_current", "<f4")])
+        bounds = shard.balance_blocks(tr, rank, world, dist, poses, 7680, 4320)
+        q.put((rank, bounds, tr.bounds))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_block_balancing():
+    """balance_blocks over gloo: both ranks time their own block, all-reduce the times and arrive at the same boundaries,
+    which split the (known) cost evenly"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_balance_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = dict()
+    for _ in range(2):
+        rank, bounds, set_on_tracer = q.get(timeout=5)
+        got[rank] = bounds
+        assert bounds == set_on_tracer
+    assert got[0] == got[1] and got[0][0] == 0 and got[0][2] == 135
+    cost = 1.0 + 0.35 * np.linspace(0, 1, 135)
+    a, b = cost[:got[0][1]].sum(), cost[got[0][1]:].sum()
+    assert abs(a - b) / (a + b) < 0.02, got
