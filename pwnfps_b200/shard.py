@@ -224,7 +224,7 @@ def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), fr
     # needs), and sbuf alone (the frame the host reads; zbuf stays on the tracing GPU)
     tr.shard_config(world, rank)
     fused = fused_s = None
-    try:
+    if True:
         for with_z in (True, False):
             base = open_peer_frame(tr, rank, dist, with_z=with_z)
             got = []
@@ -252,15 +252,12 @@ def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), fr
             if rank == 0:
                 key = "fused_frames_equal_one_gpu" if with_z else "fused_sbuf_only_frames_equal_one_gpu"
                 out[key] = bool(got == [int(v) for v in want[::4]])
-    except api.PwnError as e:
-        out["fused_error"] = str(e)
-        tr.frame_redirect(0, 0, 0)
 
     # the same frames WITH the blur pass: all-gather fused into K1, device-side barriers, every
     # shard blurs its own bands into GPU 0's frame (pwn_trace_shard_blur); against it, the blur of
     # the gathered frame on GPU 0 alone
-    try:
-        want_b = tr_sums_blur = None
+    if True:
+        want_b = None
         tr.shard_config(1, 0)
         if rank == 0:
             want_b = tr.trace_poses(poses, w, h, api.PWN_F_BLUR, want_sums=True)
@@ -331,7 +328,7 @@ def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), fr
                 dist.barrier()
                 if rank == 0:
                     shm.unlink()
-        except Exception as e:      # shared memory may be unavailable on a box; the device numbers stand
+        except OSError as e:      # no POSIX shared memory on this box (an environment limit, reported; nothing else is caught)
             out["host_frame_error"] = "%s: %s" % (type(e).__name__, e)
         dist.barrier()
         close_all_peers(tr, bases)
@@ -341,9 +338,6 @@ def bench_band_gather(tr, rank, world, local_rank, stream, size=(7680, 4320), fr
             out["sharded_blur_timed_out"] = bool(timed_out)
             if host_ok is not None:
                 out["host_frame_equal_one_gpu"] = bool(host_ok)
-    except api.PwnError as e:
-        out["sharded_blur_error"] = str(e)
-        tr.frame_peers(None)
 
     # gather: local trace, then one NCCL gather of the packed rows (sbuf)
     s, _ = frame_tensors(tr)
