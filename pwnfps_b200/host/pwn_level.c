@@ -137,42 +137,51 @@ static int rd_getc(rd_t *r) { return r->p < r->end ? *r->p++ : -1; }
 static pwn_level *parse_extended(const char *text, size_t len);
 static int32_t cell_as_written(const pwn_level *lv, int x, int z);
 
+/*
+ * What one character of the grid does, in both text formats (the rules of level.h:137-178): '*' is the spawn, on a plain
+ * cell; a lower-case letter registers in its own pair and then stands for the NEXT letter; a capital registers in its pair.
+ * The cell keeps the byte as a signed char, as `char data[64][64]` does (defs.h:105).
+ */
+static int32_t place_char(pwn_level *lv, int x, int z, int c)
+{
+	if(c == '*') { lv->sx = x; lv->sz = z; c = ';'; }
+	if(c >= 'a' && c < 'z') { portal_register(&lv->portals[c - 'a'], x, z); c += 'A' - 'a' + 1; }
+	if(c >= 'A' && c <= 'Z') portal_register(&lv->portals[c - 'A'], x, z);
+	return (int32_t)(signed char)c;
+}
+
+/*
+ * The rows of the grid from a byte stream, one reader for both formats.  A line break ends a row that has cells and is
+ * skipped otherwise (blank lines, the LF of a CRLF); the stream may end anywhere; cells never reached keep their '.'.
+ * level.txt: a row of w characters runs on into the next row without a line break (level.h:118-182 has no notion of
+ * lines).  Extended: the rest of an over-long line is dropped, and a line beginning "@ " ends the grid.
+ */
+static void read_grid(rd_t *r, pwn_level *lv, int extended)
+{
+	int x = 0, z = 0;
+	while(z < lv->h)
+	{
+		const int c = rd_getc(r);
+		if(c == -1) return;
+		if(c == '\r' || c == '\n') { if(x > 0) { x = 0; z++; } continue; }
+		if(extended && x == 0 && c == '@' && r->p < r->end && *r->p == ' ') { r->p--; return; }
+		lv->cells[z*lv->w + x] = place_char(lv, x, z, c);
+		if(++x == lv->w)
+		{
+			x = 0; z++;
+			if(extended) while(r->p < r->end && *r->p != '\n') r->p++;
+		}
+	}
+}
+
 pwn_level *pwn_level_parse(const char *text, size_t len)
 {
-	int x, z;
 	rd_t r;
 	if(len >= 6 && memcmp(text, "!pwnlv", 6) == 0) return parse_extended(text, len);
 	r.p = (const unsigned char *)text; r.end = r.p + len;
 	pwn_level *lv = pwn_level_new(64, 64, 26);
 	if(lv == NULL) return NULL;
-
-	for(z = 0; z < 64; z++)
-	{
-		for(x = 0; x < 64; x++)
-		{
-			int c = rd_getc(&r);
-			if(c == -1 || c == '\r' || c == '\n')
-			{
-				if(c == -1) goto done_load;
-				else if(x == 0) { x--; continue; }   /* blank line / LF of a CRLF */
-				else break;
-			}
-			if(c == '*')   /* spawn (level.h:137-142) */
-			{
-				c = ';';
-				lv->sx = x; lv->sz = z;
-			}
-			if(c >= 'a' && c <= 'z'-1)   /* level.h:144-161: registers in its own slot, then becomes the NEXT letter */
-			{
-				portal_register(&lv->portals[c-'a'], x, z);
-				c = (c-'a')+'A' + 1;
-			}
-			if(c >= 'A' && c <= 'Z')     /* level.h:163-178 */
-				portal_register(&lv->portals[c-'A'], x, z);
-			lv->cells[z*64 + x] = (int32_t)(signed char)c;   /* `char data[64][64]` (defs.h:105): bytes >= 128 are negative there too */
-		}
-	}
-done_load:
+	read_grid(&r, lv, 0);
 	pwn_level_derive(lv);
 	return lv;
 }
@@ -183,7 +192,7 @@ done_load:
  */
 static pwn_level *parse_extended(const char *text, size_t len)
 {
-	int w = 0, h = 0, np = 0, x, z, used = 0;
+	int w = 0, h = 0, np = 0, used = 0;
 	char *copy = malloc(len + 1);
 	if(copy == NULL) return NULL;
 	memcpy(copy, text, len);
@@ -196,33 +205,7 @@ static pwn_level *parse_extended(const char *text, size_t len)
 	r.p = (const unsigned char *)copy + used; r.end = (const unsigned char *)copy + len;
 	while(r.p < r.end && *r.p != '\n') r.p++;      /* rest of the header line */
 	if(r.p < r.end) r.p++;
-	for(z = 0; z < h; z++)
-	{
-		for(x = 0; x < w; x++)
-		{
-			int c = rd_getc(&r);
-			if(c == -1 || c == '\r' || c == '\n')
-			{
-				if(c == -1) goto grid_done;
-				else if(x == 0) { x--; continue; }
-				else break;
-			}
-			if(x == 0 && c == '@' && r.p < r.end && *r.p == ' ') { r.p--; goto grid_done; }   /* fewer than h rows: the '@' lines begin */
-			if(c == '*') { c = ';'; lv->sx = x; lv->sz = z; }
-			if(c >= 'a' && c <= 'z'-1)
-			{
-				portal_register(&lv->portals[c-'a'], x, z);
-				c = (c-'a')+'A' + 1;
-			}
-			if(c >= 'A' && c <= 'Z') portal_register(&lv->portals[c-'A'], x, z);
-			lv->cells[z*w + x] = (int32_t)(signed char)c;
-		}
-		if(x == w)   /* a full row: drop the rest of its line, as a 64-wide row of the reference drops nothing */
-		{
-			while(r.p < r.end && *r.p != '\n') r.p++;
-		}
-	}
-grid_done:
+	read_grid(&r, lv, 1);
 	/* "@ id x z": the '@' cell at (x, z) belongs to portal pair id >= 26; registration in line order */
 	{
 		const char *q = (const char *)r.p;
