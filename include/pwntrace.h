@@ -203,6 +203,13 @@ int pwn_shard_layout(pwn_ctx *ctx, int layout, int halo_bands);
  * same boundaries.  NULL restores the even split.
  */
 int pwn_shard_blocks(pwn_ctx *ctx, int nshards, const int32_t *band_start);
+/*
+ * The block layout's arithmetic, without a context (host only, no GPU): for a frame of dimy rows in nshards blocks
+ * (band_start as for pwn_shard_blocks, or NULL) with halo_bands (0 = automatic), shard's
+ *   out[0], out[1]  first band and number of bands       out[2], out[3]  halo bands it sends up / down
+ *   out[4], out[5]  the bands [vlo, vhi) it will ever hold: its own and the halo bands its neighbours send
+ */
+int pwn_block_shape(int dimy, int nshards, int halo_bands, const int32_t *band_start, int shard, int32_t out[6]);
 
 /* ---- the hot path ------------------------------------------------------------------ */
 /*

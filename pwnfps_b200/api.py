@@ -63,7 +63,7 @@ ABI_SYMBOLS = [
     "pwn_screen_upscale", "pwn_surface_device_ptr", "pwn_last_upscale_ms", "pwn_trace_config",
     "pwn_frame_peers", "pwn_trace_shard_blur", "pwn_frame_peers_status",
     "pwn_host_register", "pwn_host_unregister", "pwn_debug_pack", "pwn_write_frame", "pwn_read_bands",
-    "pwn_math_status", "pwn_screen_chunks", "pwn_shard_layout", "pwn_debug_flags", "pwn_shard_blocks", "pwn_join",
+    "pwn_math_status", "pwn_screen_chunks", "pwn_shard_layout", "pwn_debug_flags", "pwn_shard_blocks", "pwn_join", "pwn_block_shape",
 ]
 
 
@@ -132,6 +132,7 @@ def lib():
     L.pwn_debug_flags.argtypes = [vp, vp, i]
     L.pwn_shard_blocks.argtypes = [vp, i, vp]
     L.pwn_join.argtypes = [vp]
+    L.pwn_block_shape.argtypes = [i, i, i, vp, i, vp]
     _lib = L
     return L
 
@@ -415,6 +416,14 @@ class Game:
             host().pwn_level_free(self._clv)
         except Exception:
             pass
+
+
+def block_shape(dimy, nshards, shard, halo_bands=0, band_start=None):
+    """(b0, nb, ht, hb, vlo, vhi) of a shard in the block layout -- pwn_block_shape, host only"""
+    out = np.zeros(6, np.int32)
+    b = None if band_start is None else np.ascontiguousarray(band_start, dtype=np.int32)
+    _check(lib().pwn_block_shape(dimy, nshards, halo_bands, b.ctypes.data if b is not None else None, shard, out.ctypes.data))
+    return tuple(int(v) for v in out)
 
 
 def ray_setup(cam, dimx, dimy):

@@ -733,16 +733,17 @@ extern "C" int pwn_shard_config(pwn_ctx *ctx, int nshards, int shard)
 }
 
 // ---- contiguous-block sharding (PWN_SHARD_BLOCKS): who owns which bands, and which of them are halo -------------
-static int blk_start(const pwn_ctx *ctx, int nbands, int s)
+// Pure host arithmetic (no context): exported as pwn_block_shape so that the CPU tests can check it for every shape.
+static int blk_start_pure(int nbands, int nshards, const int32_t *bounds, int s)
 {
 	// explicit boundaries (pwn_shard_blocks), valid for the frame height they were given for; else an even split
-	if((int)ctx->blk_bounds.size() == ctx->nshards + 1 && ctx->blk_bounds[ctx->nshards] == nbands) return ctx->blk_bounds[s];
-	return (int)((long long)s*nbands/ctx->nshards);
+	if(bounds != nullptr && bounds[nshards] == nbands) return bounds[s];
+	return (int)((long long)s*nbands/nshards);
 }
 
-static int blk_halo(const pwn_ctx *ctx, int dimy)
+static int blk_halo_pure(int halo_bands, int dimy)
 {
-	if(ctx->halo_bands > 0) return ctx->halo_bands;
+	if(halo_bands > 0) return halo_bands;
 	// the blur reaches 0.002*dimy*(z-1) rows (screen.h:86,100-102): bands enough for surfaces up to ~8.5 units away;
 	// farther ones are finished by k_blur_fix from the owning shard's rows
 	int h = (int)((0.015*dimy + 31.0)/32.0);
@@ -750,13 +751,46 @@ static int blk_halo(const pwn_ctx *ctx, int dimy)
 }
 
 // shard s: bands [b0, b0 + nb); its first ht bands are read by the shard above, its last hb by the shard below
+static void blk_shape_pure(int dimy, int nshards, int halo_bands, const int32_t *bounds, int s, int &b0, int &nb, int &ht, int &hb)
+{
+	const int nbands = (dimy + 31)/32, h = blk_halo_pure(halo_bands, dimy);
+	b0 = blk_start_pure(nbands, nshards, bounds, s);
+	nb = blk_start_pure(nbands, nshards, bounds, s + 1) - b0;
+	ht = (s > 0) ? (h < nb ? h : nb) : 0;
+	hb = (s + 1 < nshards) ? (h < nb - ht ? h : nb - ht) : 0;
+}
+
+// ... and the bands [vlo, vhi) whose rows shard s will ever hold: its own and the halo bands its neighbours send
+static void blk_window_pure(int dimy, int nshards, int halo_bands, const int32_t *bounds, int s, int &vlo, int &vhi)
+{
+	int b0, nb, ht, hb, ub0 = 0, unb = 0, uht = 0, uhb = 0, db0 = 0, dnb = 0, dht = 0, dhb = 0;
+	blk_shape_pure(dimy, nshards, halo_bands, bounds, s, b0, nb, ht, hb);
+	if(s > 0) blk_shape_pure(dimy, nshards, halo_bands, bounds, s - 1, ub0, unb, uht, uhb);
+	if(s + 1 < nshards) blk_shape_pure(dimy, nshards, halo_bands, bounds, s + 1, db0, dnb, dht, dhb);
+	vlo = b0 - uhb; vhi = b0 + nb + dht;
+}
+
+extern "C" int pwn_block_shape(int dimy, int nshards, int halo_bands, const int32_t *band_start, int shard, int32_t out[6])
+{
+	if(out == nullptr || dimy < 1 || nshards < 1 || nshards > 8 || shard < 0 || shard >= nshards || halo_bands < 0)
+		return fail(PWN_E_ARG, "pwn_block_shape: bad arguments");
+	int b0, nb, ht, hb, vlo, vhi;
+	blk_shape_pure(dimy, nshards, halo_bands, band_start, shard, b0, nb, ht, hb);
+	blk_window_pure(dimy, nshards, halo_bands, band_start, shard, vlo, vhi);
+	out[0] = b0; out[1] = nb; out[2] = ht; out[3] = hb; out[4] = vlo; out[5] = vhi;
+	return PWN_OK;
+}
+
+static const int32_t *blk_bounds_of(const pwn_ctx *ctx)
+{
+	return ((int)ctx->blk_bounds.size() == ctx->nshards + 1) ? ctx->blk_bounds.data() : nullptr;
+}
+
+static int blk_start(const pwn_ctx *ctx, int nbands, int s) { return blk_start_pure(nbands, ctx->nshards, blk_bounds_of(ctx), s); }
+static int blk_halo(const pwn_ctx *ctx, int dimy) { return blk_halo_pure(ctx->halo_bands, dimy); }
 static void blk_shape(const pwn_ctx *ctx, int dimy, int s, int &b0, int &nb, int &ht, int &hb)
 {
-	const int nbands = (dimy + 31)/32, h = blk_halo(ctx, dimy);
-	b0 = blk_start(ctx, nbands, s);
-	nb = blk_start(ctx, nbands, s + 1) - b0;
-	ht = (s > 0) ? (h < nb ? h : nb) : 0;
-	hb = (s + 1 < ctx->nshards) ? (h < nb - ht ? h : nb - ht) : 0;
+	blk_shape_pure(dimy, ctx->nshards, ctx->halo_bands, blk_bounds_of(ctx), s, b0, nb, ht, hb);
 }
 
 struct BlkTrace   // what a K1 launch of pwn_trace_shard_blur adds in the block layout
@@ -997,10 +1031,8 @@ static int trace_shard_blur_blocks(pwn_ctx *ctx, const float cam[16], int dimx, 
 	int b0, nb, ht, hb;
 	blk_shape(ctx, dimy, r, b0, nb, ht, hb);
 	// what reaches this shard from its neighbours: the last hb bands of the shard above, the first ht of the one below
-	int ub0 = 0, unb = 0, uht = 0, uhb = 0, db0 = 0, dnb = 0, dht = 0, dhb = 0;
-	if(r > 0) blk_shape(ctx, dimy, r - 1, ub0, unb, uht, uhb);
-	if(r + 1 < S) blk_shape(ctx, dimy, r + 1, db0, dnb, dht, dhb);
-	const int vlo = b0 - uhb, vhi = b0 + nb + dht;          // bands whose rows this shard will hold
+	int vlo, vhi;                                            // bands whose rows this shard will hold
+	blk_window_pure(dimy, S, ctx->halo_bands, blk_bounds_of(ctx), r, vlo, vhi);
 	ctx->epoch++;
 	ctx->blk_frames++;
 	ctx->barrier_pending = true;

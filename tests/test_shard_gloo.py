@@ -156,3 +156,41 @@ def test_two_rank_gloo_block_balancing():
     cost = 1.0 + 0.35 * np.linspace(0, 1, 135)
     a, b = cost[:got[0][1]].sum(), cost[got[0][1]:].sum()
     assert abs(a - b) / (a + b) < 0.02, got
+
+
+def test_block_shape_arithmetic():
+    """pwn_block_shape (host only): for every frame height, shard count, halo width and boundary set the blocks partition the
+    bands, a shard never sends more halo bands than it has, what it expects from its neighbours is exactly what they send,
+    and the rows it will hold contain its own block"""
+    from pwnfps_b200 import api
+    rng = np.random.default_rng(11)
+    for dimy in (1, 31, 32, 33, 360, 1080, 2160, 4320, 4321):
+        nbands = (dimy + 31) // 32
+        for n in range(1, 9):
+            for halo in (0, 1, 2, 3, 9, 200):
+                for explicit in (False, True):
+                    bounds = None
+                    if explicit:
+                        cuts = np.sort(rng.integers(0, nbands + 1, n - 1)).tolist()
+                        bounds = [0] + cuts + [nbands]
+                    shapes = [api.block_shape(dimy, n, r, halo, bounds) for r in range(n)]
+                    assert shapes[0][0] == 0 and shapes[-1][0] + shapes[-1][1] == nbands
+                    for r, (b0, nb, ht, hb, vlo, vhi) in enumerate(shapes):
+                        assert nb >= 0 and 0 <= ht and 0 <= hb and ht + hb <= nb
+                        if r + 1 < n:
+                            assert b0 + nb == shapes[r + 1][0]
+                        if r == 0:
+                            assert ht == 0 and vlo == b0
+                        else:
+                            assert vlo == b0 - shapes[r - 1][3]          # what the shard above sends down
+                        if r == n - 1:
+                            assert hb == 0 and vhi == b0 + nb
+                        else:
+                            assert vhi == b0 + nb + shapes[r + 1][2]     # what the shard below sends up
+                        assert 0 <= vlo <= b0 and b0 + nb <= vhi <= nbands
+                        if bounds is not None:
+                            assert (b0, nb) == (bounds[r], bounds[r + 1] - bounds[r])
+    # boundaries given for another frame height are ignored: the even split
+    assert api.block_shape(4320, 2, 1, 0, [0, 10, 99]) == api.block_shape(4320, 2, 1, 0, None)
+    with pytest.raises(api.PwnError):
+        api.block_shape(4320, 9, 0)
