@@ -420,7 +420,7 @@ def run_ours(args, rank, world, local_rank):
         tr.shard_config(world, rank)
         tr.shard_layout(blocks=True)          # contiguous band blocks: halo exchange instead of an all-gather
         # rows below the horizon cost more (floor bounce): the block boundaries are moved until the shards' traces take
-        # the same time on a sample of the batch (outside the timed region; the boundaries are part of `config`)
+        # the same time on a sample of the batch (outside the timed region; the boundaries are printed with the line)
         bounds = shard.balance_blocks(tr, rank, world, dist, poses[::8], w, h)
         rig.barrier()
         if blur:
@@ -642,7 +642,7 @@ def run_ours(args, rank, world, local_rank):
         }
         if shard_check is not None:
             line["sharded_frames_equal_one_gpu"] = shard_check
-            line["config"]["block_boundaries_bands"] = [int(b) for b in bounds]
+            line["block_boundaries_bands"] = [int(b) for b in bounds]      # (beside `config`, which both arms print identically)
         if others is not None:
             line["other_configs"] = others
         if beside is not None:
