@@ -880,9 +880,10 @@ def test_trace_screen_chunked_pipeline(tracer, oracle):
 def test_sharded_blur_block_layout_in_one_process(tracer, oracle, nsh, halo):
     """(see block_layout_case)  Every shard parks kernels on the device that spin until its neighbours' work arrives; in
     ONE process that only works while every stream has a hardware queue of its own (8 by default, two streams per
-    shard): the 4- and 8-shard cases run in a child process with CUDA_DEVICE_MAX_CONNECTIONS=32.  With one process per
+    shard, and the session's other contexts have theirs): the 3-, 4- and 8-shard cases run in a child process with
+    CUDA_DEVICE_MAX_CONNECTIONS=32.  With one process per
     GPU, as bench.py runs it, a shard waits for other GPUs only."""
-    if nsh <= 3:
+    if nsh <= 2:
         block_layout_case(tracer, oracle, nsh, halo)
         return
     import subprocess
